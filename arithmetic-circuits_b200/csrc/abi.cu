@@ -1,0 +1,918 @@
+// C ABI of the device path (include/acg.h): contexts, uploads, the R1CS check, NTT and the QAP
+// witness pipeline.  Host logic only orchestrates; all arithmetic on bulk data runs in the kernels
+// of r1cs_kernels.cu / ntt_kernels.cu / lagrange_kernels.cu.  There is no CPU fallback: every compute
+// entry point needs a CUDA device and reports ACG_ERR_NO_DEVICE / ACG_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/acg.h"
+#include "kernels.h"
+
+using namespace acg;
+
+// --------------------------------------------------------------------------------------------------
+// handles
+// --------------------------------------------------------------------------------------------------
+struct acg_ctx {
+    int field = 0;
+    int device = 0;
+    int sm_count = 148;
+    int check_kernel = ACG_CHECK_AUTO;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long* d_result = nullptr;  // {n_violations, first_bad_row}
+    int* d_flag = nullptr;
+    unsigned long long* h_result = nullptr;  // pinned
+    int* h_flag = nullptr;                   // pinned
+    std::string err;
+    acg_timing timing{};
+    uint64_t launches = 0;
+    std::map<std::pair<uint32_t, int>, NttPlan*> plans;
+    struct CosetTables {
+        fr_t *hi = nullptr, *lo = nullptr, *ihi = nullptr, *ilo = nullptr;
+        uint32_t lo_bits = 0;
+    };
+    std::map<uint32_t, CosetTables> coset;
+};
+
+struct acg_r1cs {
+    acg_ctx* ctx = nullptr;
+    uint32_t n_rows_total = 0, n_cols = 0, row_begin = 0, row_end = 0;
+    uint64_t nnz[3] = {0, 0, 0};
+    uint32_t* d_rowptr[3] = {nullptr, nullptr, nullptr};
+    uint32_t* d_col[3] = {nullptr, nullptr, nullptr};
+    fr_t* d_val[3] = {nullptr, nullptr, nullptr};
+    DevR1cs dev{};
+    Tile* d_tiles = nullptr;
+    uint32_t n_tiles = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> long_ranges;  // local row ranges too wide for a tile
+};
+
+struct acg_vec {
+    acg_ctx* ctx = nullptr;
+    fr_t* d = nullptr;
+    uint32_t n = 0;
+};
+
+namespace {
+
+int fail(acg_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+int fail_cuda(acg_ctx* ctx, cudaError_t e, const char* what) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    if (ctx) ctx->err = buf;
+    if (e == cudaErrorMemoryAllocation) return ACG_ERR_OOM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return ACG_ERR_NO_DEVICE;
+    return ACG_ERR_CUDA;
+}
+#define CU(ctx, expr)                                              \
+    do {                                                           \
+        cudaError_t e__ = (expr);                                  \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #expr); \
+    } while (0)
+
+struct DevBuf {  // scoped device allocation
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T>
+    T* as() const {
+        return static_cast<T*>(p);
+    }
+};
+
+template <class F>
+int with_field(int field, F&& f) {
+    if (field == ACG_FIELD_BN254_FR) return f(Bn254Fr{});
+    if (field == ACG_FIELD_BLS12_381_FR) return f(Bls12381Fr{});
+    return ACG_ERR_BAD_ARG;
+}
+
+template <class P>
+fr_t host_pow(fr_t base, uint64_t e) {
+    fr_t acc = fr_one<P>();
+    while (e) {
+        if (e & 1ull) acc = fr_mul<P>(acc, base);
+        base = fr_sqr<P>(base);
+        e >>= 1;
+    }
+    return acc;
+}
+template <class P>
+fr_t host_const(uint32_t (*f)(int)) {
+    fr_t r;
+    for (int i = 0; i < 8; ++i) r.l[i] = f(i);
+    return r;
+}
+template <class P>
+fr_t host_root_of_unity(uint32_t k) {  // Montgomery form
+    fr_t w = host_const<P>(&P::two_adic_root);
+    for (uint32_t i = k; i < (uint32_t)P::TWO_ADICITY; ++i) w = fr_sqr<P>(w);
+    return w;
+}
+void limbs_from_fr(uint64_t out[4], const fr_t& v) {
+    for (int i = 0; i < 4; ++i) out[i] = (uint64_t)v.l[2 * i] | ((uint64_t)v.l[2 * i + 1] << 32);
+}
+fr_t fr_from_limbs(const uint64_t in[4]) {
+    fr_t v;
+    for (int i = 0; i < 4; ++i) {
+        v.l[2 * i] = (uint32_t)in[i];
+        v.l[2 * i + 1] = (uint32_t)(in[i] >> 32);
+    }
+    return v;
+}
+
+int two_adicity(int field) { return field == 0 ? Bn254Fr::TWO_ADICITY : Bls12381Fr::TWO_ADICITY; }
+
+int activate(acg_ctx* ctx) {
+    if (!ctx) return ACG_ERR_BAD_ARG;
+    ctx->err.clear();
+    CU(ctx, cudaSetDevice(ctx->device));
+    return ACG_OK;
+}
+
+int get_plan(acg_ctx* ctx, uint32_t log_n, bool inverse, NttPlan** out) {
+    auto key = std::make_pair(log_n, inverse ? 1 : 0);
+    auto it = ctx->plans.find(key);
+    if (it != ctx->plans.end()) {
+        *out = it->second;
+        return ACG_OK;
+    }
+    if ((int)log_n > two_adicity(ctx->field))
+        return fail(ctx, ACG_ERR_UNSUPPORTED, "log_n exceeds the 2-adicity of the field");
+    NttPlan* p = nullptr;
+    CU(ctx, ntt_plan_create(ctx->field, log_n, inverse, &p));
+    ctx->launches += 3;
+    ctx->plans[key] = p;
+    *out = p;
+    return ACG_OK;
+}
+
+// convert n Montgomery elements at d (in place), copy them to host
+int download_canonical(acg_ctx* ctx, fr_t* d, uint64_t n, uint64_t* host) {
+    CU(ctx, launch_from_mont(ctx->field, d, n, ctx->stream));
+    ctx->launches += 1;
+    CU(ctx, cudaMemcpyAsync(host, d, n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return ACG_OK;
+}
+// copy n canonical elements to d, validate, convert to Montgomery.  Synchronises.
+int upload_canonical(acg_ctx* ctx, fr_t* d, const uint64_t* host, uint64_t n) {
+    if (n == 0) return ACG_OK;
+    CU(ctx, cudaMemcpyAsync(d, host, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    CU(ctx, launch_to_mont(ctx->field, d, n, ctx->d_flag, ctx->stream));
+    ctx->launches += 1;
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_flag) return fail(ctx, ACG_ERR_NON_CANONICAL, "field element >= modulus");
+    return ACG_OK;
+}
+
+// Greedy nnz-balanced tiling in groups of 4 rows (TMA needs 16-byte aligned row-pointer slices).
+void build_tiles(const uint32_t* rp[3], uint32_t n_local, std::vector<Tile>& tiles,
+                 std::vector<std::pair<uint32_t, uint32_t>>& long_ranges) {
+    uint32_t r = 0;
+    while (r < n_local) {
+        Tile t{};
+        t.row0 = r;
+        for (int k = 0; k < 3; ++k) t.e0[k] = rp[k][r];
+        uint32_t end = r;
+        while (end < n_local && end - r < (uint32_t)kTileRows) {
+            const uint32_t g_end = std::min(end + 4u, n_local);
+            uint64_t tot = 0;
+            for (int k = 0; k < 3; ++k) tot += (uint64_t)rp[k][g_end] - t.e0[k];
+            if (tot > (uint64_t)kTilePoolEntries) break;
+            end = g_end;
+        }
+        if (end == r) {  // a single 4-row group does not fit: row-wise kernel handles it
+            const uint32_t g_end = std::min(r + 4u, n_local);
+            if (!long_ranges.empty() && long_ranges.back().second == r)
+                long_ranges.back().second = g_end;
+            else
+                long_ranges.emplace_back(r, g_end);
+            r = g_end;
+            continue;
+        }
+        t.nrows = end - r;
+        for (int k = 0; k < 3; ++k) t.ne[k] = rp[k][end] - t.e0[k];
+        tiles.push_back(t);
+        r = end;
+    }
+}
+
+int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long long* d_result, fr_t* Aw, fr_t* Bw,
+                  fr_t* Cw, cudaStream_t s, uint32_t* launches) {
+    const uint32_t n_local = m->row_end - m->row_begin;
+    CU(ctx, launch_init_result(d_result, s));
+    ++*launches;
+    int which = ctx->check_kernel == ACG_CHECK_AUTO ? ACG_CHECK_TILED : ctx->check_kernel;
+    if (which == ACG_CHECK_ROWWISE) {
+        if (n_local) {
+            CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, 0, n_local, m->row_begin, d_result, Aw, Bw, Cw, s));
+            ++*launches;
+        }
+        return ACG_OK;
+    }
+    if (m->n_tiles) {
+        CU(ctx, launch_r1cs_tiled(ctx->field, m->dev, w, m->d_tiles, m->n_tiles, m->row_begin, d_result, Aw, Bw, Cw,
+                                  ctx->sm_count, s));
+        ++*launches;
+    }
+    for (const auto& lr : m->long_ranges) {
+        CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, lr.first, lr.second, m->row_begin, d_result, Aw, Bw, Cw, s));
+        ++*launches;
+    }
+    return ACG_OK;
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------------
+// library / context
+// --------------------------------------------------------------------------------------------------
+extern "C" {
+
+int acg_abi_version(void) { return ACG_ABI_VERSION; }
+
+const char* acg_strerror(int code) {
+    switch (code) {
+        case ACG_OK: return "ok";
+        case ACG_ERR_BAD_ARG: return "bad argument";
+        case ACG_ERR_NON_CANONICAL: return "non-canonical field element (>= modulus)";
+        case ACG_ERR_CUDA: return "CUDA error";
+        case ACG_ERR_OOM: return "out of device memory";
+        case ACG_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        case ACG_ERR_UNSUPPORTED: return "unsupported size or configuration";
+        case ACG_ERR_INTERNAL: return "internal error";
+        default: return "unknown error code";
+    }
+}
+
+const char* acg_last_error(const acg_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int acg_ctx_create(int field_id, int device, acg_ctx** out) {
+    if (!out || (field_id != ACG_FIELD_BN254_FR && field_id != ACG_FIELD_BLS12_381_FR)) return ACG_ERR_BAD_ARG;
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev <= 0) return ACG_ERR_NO_DEVICE;
+    if (device < 0 || device >= n_dev) return ACG_ERR_BAD_ARG;
+    acg_ctx* ctx = new (std::nothrow) acg_ctx();
+    if (!ctx) return ACG_ERR_OOM;
+    ctx->field = field_id;
+    ctx->device = device;
+    auto bail = [&](cudaError_t ce, const char* what) {
+        int rc = fail_cuda(nullptr, ce, what);
+        acg_ctx_destroy(ctx);
+        return rc;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop{};
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    if (prop.major < 10) {
+        acg_ctx_destroy(ctx);
+        return ACG_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(e, "cudaStreamCreate");
+    for (auto& ev : ctx->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMalloc(&ctx->d_result, 2 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->d_flag, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMallocHost(&ctx->h_result, 2 * sizeof(unsigned long long))) != cudaSuccess)
+        return bail(e, "cudaMallocHost");
+    if ((e = cudaMallocHost(&ctx->h_flag, sizeof(int))) != cudaSuccess) return bail(e, "cudaMallocHost");
+    *out = ctx;
+    return ACG_OK;
+}
+
+void acg_ctx_destroy(acg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto& kv : ctx->plans) ntt_plan_destroy(kv.second);
+    for (auto& kv : ctx->coset) {
+        cudaFree(kv.second.hi);
+        cudaFree(kv.second.lo);
+        cudaFree(kv.second.ihi);
+        cudaFree(kv.second.ilo);
+    }
+    if (ctx->d_result) cudaFree(ctx->d_result);
+    if (ctx->d_flag) cudaFree(ctx->d_flag);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int acg_ctx_set_check_kernel(acg_ctx* ctx, int which) {
+    if (!ctx || which < ACG_CHECK_AUTO || which > ACG_CHECK_TILED) return ACG_ERR_BAD_ARG;
+    ctx->check_kernel = which;
+    return ACG_OK;
+}
+
+int acg_last_timing(const acg_ctx* ctx, acg_timing* out) {
+    if (!ctx || !out) return ACG_ERR_BAD_ARG;
+    *out = ctx->timing;
+    return ACG_OK;
+}
+
+uint64_t acg_kernel_launch_count(const acg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int acg_field_constants(int field_id, uint64_t modulus[4], uint64_t mont_r[4], uint64_t mont_r2[4], uint64_t* ninv64,
+                        uint32_t* two_adic) {
+    return with_field(field_id, [&](auto p) {
+        using P = decltype(p);
+        if (modulus) limbs_from_fr(modulus, host_const<P>(&P::p));
+        if (mont_r) limbs_from_fr(mont_r, host_const<P>(&P::one));
+        if (mont_r2) limbs_from_fr(mont_r2, host_const<P>(&P::r2));
+        if (ninv64) *ninv64 = P::NINV64;
+        if (two_adic) *two_adic = (uint32_t)P::TWO_ADICITY;
+        return (int)ACG_OK;
+    });
+}
+
+int acg_root_of_unity(int field_id, uint32_t k, uint64_t out[4]) {
+    if (!out) return ACG_ERR_BAD_ARG;
+    return with_field(field_id, [&](auto p) {
+        using P = decltype(p);
+        if (k > (uint32_t)P::TWO_ADICITY) return (int)ACG_ERR_UNSUPPORTED;
+        limbs_from_fr(out, fr_from_mont<P>(host_root_of_unity<P>(k)));
+        return (int)ACG_OK;
+    });
+}
+
+// --------------------------------------------------------------------------------------------------
+// R1CS upload / check
+// --------------------------------------------------------------------------------------------------
+void acg_r1cs_free(acg_r1cs* m) {
+    if (!m) return;
+    if (m->ctx) cudaSetDevice(m->ctx->device);
+    for (int k = 0; k < 3; ++k) {
+        cudaFree(m->d_rowptr[k]);
+        cudaFree(m->d_col[k]);
+        cudaFree(m->d_val[k]);
+    }
+    cudaFree(m->d_tiles);
+    delete m;
+}
+
+int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_csr* A, const acg_csr* B,
+                    const acg_csr* C, uint32_t row_begin, uint32_t row_end, acg_r1cs** out) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!out || !A || !B || !C || row_begin > row_end || row_end > n_rows || n_cols == 0)
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: bad argument");
+    *out = nullptr;
+    const acg_csr* src[3] = {A, B, C};
+    const uint32_t n_local = row_end - row_begin;
+    // host-side structural validation of the uploaded slice
+    for (int k = 0; k < 3; ++k) {
+        const acg_csr* M = src[k];
+        if (!M->rowptr || (M->nnz && (!M->col || !M->val)) || M->nnz > 0xFFFFFFF0ull)
+            return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: null array or nnz too large");
+        if (M->rowptr[n_rows] != M->nnz) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: rowptr[n_rows] != nnz");
+        for (uint32_t r = row_begin; r < row_end; ++r)
+            if (M->rowptr[r] > M->rowptr[r + 1])
+                return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: rowptr not monotone");
+        const uint32_t e0 = M->rowptr[row_begin], e1 = M->rowptr[row_end];
+        if (e1 > M->nnz) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: rowptr exceeds nnz");
+        uint32_t bad = 0;
+        for (uint32_t e = e0; e < e1; ++e) bad |= (M->col[e] >= n_cols);
+        if (bad) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: column index >= n_cols");
+    }
+    acg_r1cs* m = new (std::nothrow) acg_r1cs();
+    if (!m) return ACG_ERR_OOM;
+    m->ctx = ctx;
+    m->n_rows_total = n_rows;
+    m->n_cols = n_cols;
+    m->row_begin = row_begin;
+    m->row_end = row_end;
+    struct Guard {
+        acg_r1cs* p;
+        ~Guard() {
+            if (p) acg_r1cs_free(p);
+        }
+    } guard{m};
+
+    CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    std::vector<uint32_t> local_rp[3];
+    uint32_t launches = 0;
+    CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    for (int k = 0; k < 3; ++k) {
+        const acg_csr* M = src[k];
+        const uint32_t e0 = M->rowptr[row_begin], e1 = M->rowptr[row_end];
+        const uint64_t cnt = e1 - e0;
+        m->nnz[k] = cnt;
+        local_rp[k].resize((size_t)n_local + 1);
+        for (uint32_t r = 0; r <= n_local; ++r) local_rp[k][r] = M->rowptr[row_begin + r] - e0;
+        // pads: TMA slices are rounded up to 16 bytes and may read a few elements past the end
+        CU(ctx, cudaMalloc(&m->d_rowptr[k], ((size_t)n_local + 1 + 8) * sizeof(uint32_t)));
+        CU(ctx, cudaMalloc(&m->d_col[k], (size_t)(cnt + 8) * sizeof(uint32_t)));
+        CU(ctx, cudaMalloc(&m->d_val[k], (size_t)(cnt + 1) * sizeof(fr_t)));
+        CU(ctx, cudaMemsetAsync(m->d_rowptr[k] + n_local + 1, 0, 8 * sizeof(uint32_t), ctx->stream));
+        CU(ctx, cudaMemsetAsync(m->d_col[k] + cnt, 0, 8 * sizeof(uint32_t), ctx->stream));
+        CU(ctx, cudaMemcpyAsync(m->d_rowptr[k], local_rp[k].data(), ((size_t)n_local + 1) * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, ctx->stream));
+        if (cnt) {
+            CU(ctx, cudaMemcpyAsync(m->d_col[k], M->col + e0, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                    ctx->stream));
+            CU(ctx, cudaMemcpyAsync(m->d_val[k], M->val + 4ull * e0, cnt * sizeof(fr_t), cudaMemcpyHostToDevice,
+                                    ctx->stream));
+            CU(ctx, launch_to_mont(ctx->field, m->d_val[k], cnt, ctx->d_flag, ctx->stream));
+            ++launches;
+        }
+        m->dev.m[k].rowptr = m->d_rowptr[k];
+        m->dev.m[k].col = m->d_col[k];
+        m->dev.m[k].val = m->d_val[k];
+    }
+    // tiles
+    std::vector<Tile> tiles;
+    const uint32_t* rp[3] = {local_rp[0].data(), local_rp[1].data(), local_rp[2].data()};
+    build_tiles(rp, n_local, tiles, m->long_ranges);
+    m->n_tiles = (uint32_t)tiles.size();
+    if (m->n_tiles) {
+        CU(ctx, cudaMalloc(&m->d_tiles, tiles.size() * sizeof(Tile)));
+        CU(ctx, cudaMemcpyAsync(m->d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice,
+                                ctx->stream));
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches += launches;
+    ctx->timing = acg_timing{elapsed(ctx->ev[0], ctx->ev[1]), 0.f, 0.f, launches, 0};
+    if (*ctx->h_flag) return fail(ctx, ACG_ERR_NON_CANONICAL, "acg_r1cs_upload: matrix coefficient >= modulus");
+    guard.p = nullptr;
+    *out = m;
+    return ACG_OK;
+}
+
+uint64_t acg_r1cs_algorithmic_bytes(const acg_r1cs* m) {
+    if (!m) return 0;
+    const uint64_t rows = m->row_end - m->row_begin;
+    uint64_t b = 32ull * m->n_cols + 8ull;
+    for (int k = 0; k < 3; ++k) b += m->nnz[k] * 36ull + 4ull * (rows + 1);
+    return b;
+}
+
+void acg_vec_free(acg_vec* v) {
+    if (!v) return;
+    if (v->ctx) cudaSetDevice(v->ctx->device);
+    cudaFree(v->d);
+    delete v;
+}
+uint32_t acg_vec_len(const acg_vec* v) { return v ? v->n : 0; }
+void* acg_vec_device_ptr(acg_vec* v) { return v ? v->d : nullptr; }
+
+int acg_witness_update(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t n_cols) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!v || !w || v->n != n_cols) return fail(ctx, ACG_ERR_BAD_ARG, "acg_witness_update: bad argument");
+    CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = upload_canonical(ctx, v->d, w, n_cols);
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(ctx, cudaEventSynchronize(ctx->ev[1]));
+    ctx->timing = acg_timing{elapsed(ctx->ev[0], ctx->ev[1]), 0.f, 0.f, 1, 0};
+    return ACG_OK;
+}
+
+int acg_witness_upload(acg_ctx* ctx, const uint64_t* w, uint32_t n_cols, acg_vec** out) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!out || !w || n_cols == 0) return fail(ctx, ACG_ERR_BAD_ARG, "acg_witness_upload: bad argument");
+    *out = nullptr;
+    acg_vec* v = new (std::nothrow) acg_vec();
+    if (!v) return ACG_ERR_OOM;
+    v->ctx = ctx;
+    v->n = n_cols;
+    cudaError_t e = cudaMalloc(&v->d, (size_t)n_cols * sizeof(fr_t));
+    if (e != cudaSuccess) {
+        delete v;
+        return fail_cuda(ctx, e, "cudaMalloc(witness)");
+    }
+    rc = acg_witness_update(ctx, v, w, n_cols);
+    if (rc) {
+        acg_vec_free(v);
+        return rc;
+    }
+    *out = v;
+    return ACG_OK;
+}
+
+int acg_r1cs_check_async(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* d_result, void* stream) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!m || !w || !d_result || m->ctx != ctx || w->ctx != ctx || w->n != m->n_cols)
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_check_async: bad argument");
+    uint32_t launches = 0;
+    rc = enqueue_check(ctx, m, w->d, reinterpret_cast<unsigned long long*>(d_result), nullptr, nullptr, nullptr,
+                       static_cast<cudaStream_t>(stream), &launches);
+    ctx->launches += launches;
+    ctx->timing.kernel_launches = launches;
+    return rc;
+}
+
+int acg_r1cs_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* n_violations,
+                   uint64_t* first_bad_row) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!m || !w || m->ctx != ctx || w->ctx != ctx || w->n != m->n_cols)
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_check: bad argument");
+    uint32_t launches = 0;
+    CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    rc = enqueue_check(ctx, m, w->d, ctx->d_result, nullptr, nullptr, nullptr, ctx->stream, &launches);
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches += launches;
+    ctx->timing = acg_timing{0.f, elapsed(ctx->ev[1], ctx->ev[2]), elapsed(ctx->ev[2], ctx->ev[3]), launches, 0};
+    if (n_violations) *n_violations = ctx->h_result[0];
+    if (first_bad_row) *first_bad_row = ctx->h_result[1];
+    return ACG_OK;
+}
+
+int acg_r1cs_check_host(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_csr* A, const acg_csr* B,
+                        const acg_csr* C, const uint64_t* w, uint64_t* n_violations, uint64_t* first_bad_row) {
+    acg_r1cs* m = nullptr;
+    acg_vec* v = nullptr;
+    int rc = acg_r1cs_upload(ctx, n_rows, n_cols, A, B, C, 0, n_rows, &m);
+    if (rc) return rc;
+    const float h2d_m = ctx->timing.h2d_ms;
+    const uint32_t l0 = ctx->timing.kernel_launches;
+    rc = acg_witness_upload(ctx, w, n_cols, &v);
+    if (rc) {
+        acg_r1cs_free(m);
+        return rc;
+    }
+    const float h2d_w = ctx->timing.h2d_ms;
+    rc = acg_r1cs_check(ctx, m, v, n_violations, first_bad_row);
+    if (rc == ACG_OK) {
+        ctx->timing.h2d_ms = h2d_m + h2d_w;
+        ctx->timing.kernel_launches += l0 + 1;
+    }
+    acg_vec_free(v);
+    acg_r1cs_free(m);
+    return rc;
+}
+
+int acg_r1cs_eval(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* Aw, uint64_t* Bw, uint64_t* Cw) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!m || !w || m->ctx != ctx || w->ctx != ctx || w->n != m->n_cols)
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_eval: bad argument");
+    const uint32_t n_local = m->row_end - m->row_begin;
+    if (n_local == 0) return ACG_OK;
+    DevBuf buf[3];
+    uint64_t* host[3] = {Aw, Bw, Cw};
+    for (int k = 0; k < 3; ++k) CU(ctx, buf[k].alloc((size_t)n_local * sizeof(fr_t)));
+    uint32_t launches = 0;
+    CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    rc = enqueue_check(ctx, m, w->d, ctx->d_result, buf[0].as<fr_t>(), buf[1].as<fr_t>(), buf[2].as<fr_t>(),
+                       ctx->stream, &launches);
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    for (int k = 0; k < 3; ++k) {
+        if (!host[k]) continue;
+        rc = download_canonical(ctx, buf[k].as<fr_t>(), n_local, host[k]);
+        if (rc) return rc;
+        ++launches;
+    }
+    CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches += launches;
+    ctx->timing = acg_timing{0.f, elapsed(ctx->ev[1], ctx->ev[2]), elapsed(ctx->ev[2], ctx->ev[3]), launches, 0};
+    return ACG_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// NTT
+// --------------------------------------------------------------------------------------------------
+int acg_ntt_device(acg_ctx* ctx, acg_vec* v, uint32_t log_n, int inverse, void* stream) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!v || v->ctx != ctx || log_n > 31 || v->n != (1u << log_n))
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_ntt_device: bad argument");
+    if (log_n == 0) return ACG_OK;
+    NttPlan* plan = nullptr;
+    if ((rc = get_plan(ctx, log_n, inverse != 0, &plan))) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    fr_t* scratch = nullptr;
+    CU(ctx, cudaMallocAsync(&scratch, (size_t)v->n * sizeof(fr_t), s));
+    uint32_t launches = 0;
+    cudaError_t e = ntt_run(plan, v->d, scratch, 1, s, &launches);
+    cudaFreeAsync(scratch, s);
+    ctx->launches += launches;
+    ctx->timing.kernel_launches = launches;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "ntt_run");
+    return ACG_OK;
+}
+
+static int ntt_host_batched(acg_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t n_batch, bool inverse) {
+    if (log_n > 31) return fail(ctx, ACG_ERR_BAD_ARG, "log_n too large");
+    if ((int)log_n > two_adicity(ctx->field))
+        return fail(ctx, ACG_ERR_UNSUPPORTED, "log_n exceeds the 2-adicity of the field");
+    if (n_batch == 0) return ACG_OK;
+    const uint64_t n = 1ull << log_n;
+    NttPlan* plan = nullptr;
+    int rc = ACG_OK;
+    if (log_n > 0 && (rc = get_plan(ctx, log_n, inverse, &plan))) return rc;
+    // chunk: a power-of-two number of transforms, at most ~256 MiB of elements at a time
+    uint32_t chunk = 1;
+    while ((uint64_t)chunk * 2 * n * sizeof(fr_t) <= (256ull << 20) && chunk * 2 <= n_batch) chunk *= 2;
+    DevBuf d, scratch;
+    CU(ctx, d.alloc((size_t)chunk * n * sizeof(fr_t)));
+    CU(ctx, scratch.alloc((size_t)chunk * n * sizeof(fr_t)));
+    uint32_t launches = 0;
+    float h2d = 0.f, ker = 0.f, d2h = 0.f;
+    for (uint32_t done = 0; done < n_batch;) {
+        uint32_t cur = chunk;
+        while (cur > n_batch - done) cur >>= 1;
+        uint64_t* hp = data + 4ull * n * done;
+        CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        rc = upload_canonical(ctx, d.as<fr_t>(), hp, (uint64_t)cur * n);
+        if (rc) return rc;
+        ++launches;
+        CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (log_n > 0) CU(ctx, ntt_run(plan, d.as<fr_t>(), scratch.as<fr_t>(), cur, ctx->stream, &launches));
+        CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+        rc = download_canonical(ctx, d.as<fr_t>(), (uint64_t)cur * n, hp);
+        if (rc) return rc;
+        ++launches;
+        CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        h2d += elapsed(ctx->ev[0], ctx->ev[1]);
+        ker += elapsed(ctx->ev[1], ctx->ev[2]);
+        d2h += elapsed(ctx->ev[2], ctx->ev[3]);
+        done += cur;
+    }
+    ctx->launches += launches;
+    ctx->timing = acg_timing{h2d, ker, d2h, launches, 0};
+    return ACG_OK;
+}
+
+int acg_ntt(acg_ctx* ctx, uint64_t* data, uint32_t log_n, int inverse) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!data) return fail(ctx, ACG_ERR_BAD_ARG, "acg_ntt: null data");
+    return ntt_host_batched(ctx, data, log_n, 1, inverse != 0);
+}
+
+int acg_interpolate_columns(acg_ctx* ctx, uint64_t* cols, uint32_t log_n, uint32_t n_cols_batch) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!cols && n_cols_batch) return fail(ctx, ACG_ERR_BAD_ARG, "acg_interpolate_columns: null data");
+    return ntt_host_batched(ctx, cols, log_n, n_cols_batch, true);
+}
+
+// --------------------------------------------------------------------------------------------------
+// QAP witness polynomials
+// --------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+template <class P>
+static int coset_tables(acg_ctx* ctx, uint32_t log_n, acg_ctx::CosetTables** out) {
+    auto it = ctx->coset.find(log_n);
+    if (it != ctx->coset.end()) {
+        *out = &it->second;
+        return ACG_OK;
+    }
+    acg_ctx::CosetTables t;
+    t.lo_bits = (log_n + 1) / 2;
+    const uint32_t lo_n = 1u << t.lo_bits, hi_n = 1u << (log_n - t.lo_bits);
+    const fr_t g = host_const<P>(&P::gen_mont), gi = host_const<P>(&P::gen_inv_mont);
+    CU(ctx, cudaMalloc(&t.lo, (size_t)lo_n * sizeof(fr_t)));
+    CU(ctx, cudaMalloc(&t.hi, (size_t)hi_n * sizeof(fr_t)));
+    CU(ctx, cudaMalloc(&t.ilo, (size_t)lo_n * sizeof(fr_t)));
+    CU(ctx, cudaMalloc(&t.ihi, (size_t)hi_n * sizeof(fr_t)));
+    CU(ctx, launch_fill_powers(ctx->field, t.lo, lo_n, g, 0, ctx->stream));
+    CU(ctx, launch_fill_powers(ctx->field, t.hi, hi_n, g, t.lo_bits, ctx->stream));
+    CU(ctx, launch_fill_powers(ctx->field, t.ilo, lo_n, gi, 0, ctx->stream));
+    CU(ctx, launch_fill_powers(ctx->field, t.ihi, hi_n, gi, t.lo_bits, ctx->stream));
+    ctx->launches += 4;
+    ctx->coset[log_n] = t;
+    *out = &ctx->coset[log_n];
+    return ACG_OK;
+}
+
+template <class P>
+static int qap_witness_impl(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, const uint64_t* delta, uint64_t* a_out,
+                            uint64_t* b_out, uint64_t* c_out, uint64_t* h_out, int* divisible) {
+    const uint32_t n_rows = m->n_rows_total;
+    uint32_t log_n = 0;
+    while ((1ull << log_n) < n_rows) ++log_n;
+    if ((int)log_n > P::TWO_ADICITY) return fail(ctx, ACG_ERR_UNSUPPORTED, "too many rows for the field's 2-adicity");
+    const uint64_t N = 1ull << log_n;
+    fr_t d[3] = {fr_zero<P>(), fr_zero<P>(), fr_zero<P>()};
+    bool any_delta = false;
+    if (delta) {
+        for (int k = 0; k < 3; ++k) {
+            fr_t x = fr_from_limbs(delta + 4 * k);
+            if (!fr_is_canonical<P>(x)) return fail(ctx, ACG_ERR_NON_CANONICAL, "delta >= modulus");
+            d[k] = fr_to_mont<P>(x);
+            any_delta = any_delta || !fr_is_zero(x);
+        }
+    }
+    cudaStream_t s = ctx->stream;
+    uint32_t launches = 0;
+    DevBuf ev[3], coef[2], hbuf, scratch;
+    for (int k = 0; k < 3; ++k) {
+        CU(ctx, ev[k].alloc(N * sizeof(fr_t)));
+        CU(ctx, cudaMemsetAsync(ev[k].p, 0, N * sizeof(fr_t), s));
+    }
+    CU(ctx, hbuf.alloc(N * sizeof(fr_t)));
+    CU(ctx, scratch.alloc(N * sizeof(fr_t)));
+    CU(ctx, cudaEventRecord(ctx->ev[1], s));
+    int rc = enqueue_check(ctx, m, w->d, ctx->d_result, ev[0].as<fr_t>(), ev[1].as<fr_t>(), ev[2].as<fr_t>(), s,
+                           &launches);
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+
+    uint64_t* outs[3] = {a_out, b_out, c_out};
+    NttPlan *inv = nullptr, *fwd = nullptr;
+    acg_ctx::CosetTables* ct = nullptr;
+    if (log_n == 0) {
+        // N = 1: a, b, c are constants, T = X - 1, h = 0 when divisible
+        CU(ctx, cudaMemsetAsync(hbuf.p, 0, sizeof(fr_t), s));
+    } else {
+        if ((rc = get_plan(ctx, log_n, true, &inv))) return rc;
+        if ((rc = get_plan(ctx, log_n, false, &fwd))) return rc;
+        if ((rc = coset_tables<P>(ctx, log_n, &ct))) return rc;
+        // values on the domain -> coefficients
+        for (int k = 0; k < 3; ++k)
+            CU(ctx, ntt_run(inv, ev[k].as<fr_t>(), scratch.as<fr_t>(), 1, s, &launches));
+    }
+    // hand the coefficients out (canonical) before they are overwritten by the coset evaluation
+    for (int k = 0; k < 3; ++k) {
+        if (!outs[k]) continue;
+        CU(ctx, cudaMemcpyAsync(scratch.p, ev[k].p, N * sizeof(fr_t), cudaMemcpyDeviceToDevice, s));
+        if ((rc = download_canonical(ctx, scratch.as<fr_t>(), N, outs[k]))) return rc;
+        ++launches;
+    }
+    if (log_n > 0) {
+        if (any_delta) {  // keep a and b coefficients for h += d1*b + d2*a
+            for (int k = 0; k < 2; ++k) {
+                CU(ctx, coef[k].alloc(N * sizeof(fr_t)));
+                CU(ctx, cudaMemcpyAsync(coef[k].p, ev[k].p, N * sizeof(fr_t), cudaMemcpyDeviceToDevice, s));
+            }
+        }
+        // coset evaluation g * w^i: scale coefficient i by g^i, forward DIF (bit-reversed order out)
+        for (int k = 0; k < 3; ++k) {
+            CU(ctx, launch_scale_by_powers(ctx->field, ev[k].as<fr_t>(), N, ct->hi, ct->lo, ct->lo_bits, fr_one<P>(),
+                                           false, false, log_n, s));
+            ++launches;
+            CU(ctx, ntt_run_dif(fwd, ev[k].as<fr_t>(), 1, s, &launches));
+        }
+        // h on the coset = (a*b - c) / (g^N - 1), any consistent order
+        const fr_t g = host_const<P>(&P::gen_mont);
+        const fr_t zinv = fr_inv<P>(fr_sub<P>(host_pow<P>(g, N), fr_one<P>()));
+        CU(ctx, launch_quotient_pointwise(ctx->field, ev[0].as<fr_t>(), ev[1].as<fr_t>(), ev[2].as<fr_t>(),
+                                          scratch.as<fr_t>(), N, zinv, s));
+        ++launches;
+        CU(ctx, launch_bitrev_permute(scratch.as<fr_t>(), hbuf.as<fr_t>(), log_n, 1, s));
+        ++launches;
+        CU(ctx, ntt_run(inv, hbuf.as<fr_t>(), scratch.as<fr_t>(), 1, s, &launches));
+        CU(ctx, launch_scale_by_powers(ctx->field, hbuf.as<fr_t>(), N, ct->ihi, ct->ilo, ct->lo_bits, fr_one<P>(),
+                                       false, false, log_n, s));
+        ++launches;
+        if (any_delta) {
+            CU(ctx, launch_axpy2(ctx->field, hbuf.as<fr_t>(), coef[0].as<fr_t>(), coef[1].as<fr_t>(), d[1], d[0], N, s));
+            ++launches;
+        }
+    }
+    CU(ctx, cudaEventRecord(ctx->ev[2], s));
+    if (h_out) {
+        if ((rc = download_canonical(ctx, hbuf.as<fr_t>(), N, h_out))) return rc;
+        ++launches;
+    }
+    CU(ctx, cudaEventRecord(ctx->ev[3], s));
+    CU(ctx, cudaStreamSynchronize(s));
+    ctx->launches += launches;
+    ctx->timing = acg_timing{0.f, elapsed(ctx->ev[1], ctx->ev[2]), elapsed(ctx->ev[2], ctx->ev[3]), launches, 0};
+    if (divisible) *divisible = ctx->h_result[0] == 0 ? 1 : 0;
+
+    // constant-size delta fix-ups on the host: T = X^N - 1
+    //   x' = x + dk*T      -> x'[0] -= dk, x'[N] = dk
+    //   h' = h + d1*b + d2*a + d1*d2*T - d3 -> h'[0] -= d1*d2 + d3, h'[N] = d1*d2   (axpy part done above)
+    auto sub_at0 = [&](uint64_t* poly, const fr_t& v_mont) {
+        fr_t x0 = fr_to_mont<P>(fr_from_limbs(poly));
+        limbs_from_fr(poly, fr_from_mont<P>(fr_sub<P>(x0, v_mont)));
+    };
+    for (int k = 0; k < 3; ++k) {
+        if (!outs[k]) continue;
+        sub_at0(outs[k], d[k]);
+        limbs_from_fr(outs[k] + 4 * N, fr_from_mont<P>(d[k]));
+    }
+    if (h_out) {
+        const fr_t d12 = fr_mul<P>(d[0], d[1]);
+        sub_at0(h_out, fr_add<P>(d12, d[2]));
+        limbs_from_fr(h_out + 4 * N, fr_from_mont<P>(d12));
+    }
+    return ACG_OK;
+}
+
+extern "C" {
+
+int acg_qap_witness(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, const uint64_t* delta, uint64_t* a,
+                    uint64_t* b, uint64_t* c, uint64_t* h, int* divisible) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!m || !w || m->ctx != ctx || w->ctx != ctx || w->n != m->n_cols)
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_qap_witness: bad argument");
+    if (m->row_begin != 0 || m->row_end != m->n_rows_total || m->n_rows_total == 0)
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_qap_witness: needs the full (non-empty) system, not a row shard");
+    return with_field(ctx->field, [&](auto p) {
+        using P = decltype(p);
+        return qap_witness_impl<P>(ctx, m, w, delta, a, b, c, h, divisible);
+    });
+}
+
+// --------------------------------------------------------------------------------------------------
+// Lagrange
+// --------------------------------------------------------------------------------------------------
+int acg_lagrange(acg_ctx* ctx, const uint64_t* xs, const uint64_t* ys, uint32_t n, uint32_t n_polys,
+                 uint64_t* coeffs, uint64_t* target) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!xs || n == 0 || n > 4096 || (n_polys && (!ys || !coeffs)))
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_lagrange: bad argument (1 <= n <= 4096)");
+    DevBuf dx, dy, dc, dt, ds;
+    const size_t np = (size_t)n_polys * n;
+    CU(ctx, dx.alloc((size_t)n * sizeof(fr_t)));
+    CU(ctx, dy.alloc(np * sizeof(fr_t)));
+    CU(ctx, dc.alloc(np * sizeof(fr_t)));
+    CU(ctx, dt.alloc((size_t)(n + 1) * sizeof(fr_t)));
+    CU(ctx, ds.alloc((2 * (size_t)(n + 1) + n + np) * sizeof(fr_t)));
+    CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    if ((rc = upload_canonical(ctx, dx.as<fr_t>(), xs, n))) return rc;
+    if ((rc = upload_canonical(ctx, dy.as<fr_t>(), ys, np))) return rc;
+    uint32_t launches = 2;
+    CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(ctx, launch_lagrange(ctx->field, dx.as<fr_t>(), dy.as<fr_t>(), n, n_polys, dc.as<fr_t>(), dt.as<fr_t>(),
+                            ds.as<fr_t>(), ctx->d_flag, ctx->stream, &launches));
+    CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (np) {
+        if ((rc = download_canonical(ctx, dc.as<fr_t>(), np, coeffs))) return rc;
+        ++launches;
+    }
+    if (target) {
+        if ((rc = download_canonical(ctx, dt.as<fr_t>(), n + 1, target))) return rc;
+        ++launches;
+    }
+    CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches += launches;
+    ctx->timing = acg_timing{elapsed(ctx->ev[0], ctx->ev[1]), elapsed(ctx->ev[1], ctx->ev[2]),
+                             elapsed(ctx->ev[2], ctx->ev[3]), launches, 0};
+    if (*ctx->h_flag) return fail(ctx, ACG_ERR_BAD_ARG, "acg_lagrange: interpolation nodes are not distinct");
+    return ACG_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// field ops self-test surface
+// --------------------------------------------------------------------------------------------------
+int acg_fr_binop(acg_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (op < 0 || op > 3 || !a || !out || (op != 3 && !b)) return fail(ctx, ACG_ERR_BAD_ARG, "acg_fr_binop: bad argument");
+    if (n == 0) return ACG_OK;
+    DevBuf da, db, dout;
+    CU(ctx, da.alloc(n * sizeof(fr_t)));
+    CU(ctx, db.alloc(n * sizeof(fr_t)));
+    CU(ctx, dout.alloc(n * sizeof(fr_t)));
+    if ((rc = upload_canonical(ctx, da.as<fr_t>(), a, n))) return rc;
+    if ((rc = upload_canonical(ctx, db.as<fr_t>(), op == 3 ? a : b, n))) return rc;
+    CU(ctx, launch_fr_binop(ctx->field, op, da.as<fr_t>(), db.as<fr_t>(), dout.as<fr_t>(), n, ctx->stream));
+    if ((rc = download_canonical(ctx, dout.as<fr_t>(), n, out))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 4;
+    ctx->timing = acg_timing{0.f, 0.f, 0.f, 4, 0};
+    return ACG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+// Host-visible launchers of the CUDA kernels (K1..K5 of SURVEY.md section 2).  Each launcher
+// dispatches on field_id to the template instantiation and only ENQUEUES on `stream`.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "fr.cuh"
+
+namespace acg {
+
+struct DevCsr {
+    const uint32_t* rowptr;  // shard-local rows + 1 entries, rebased to 0, padded by >= 8
+    const uint32_t* col;     // padded by >= 8
+    const fr_t* val;         // Montgomery form
+};
+struct DevR1cs {
+    DevCsr m[3];  // A, B, C
+};
+
+// One unit of work of the tiled check kernel: rows [row0, row0+nrows) and their entry ranges.
+struct alignas(16) Tile {
+    uint32_t row0;
+    uint32_t nrows;
+    uint32_t e0[3];
+    uint32_t ne[3];
+};
+static_assert(sizeof(Tile) == 32, "Tile must be 32 bytes");
+
+// tiled kernel geometry (see DESIGN.md "K2")
+constexpr int kTileRows = 256;        // consumer threads == max rows per tile
+constexpr int kTilePoolEntries = 1344;  // A+B+C entries staged per tile
+constexpr int kTileStages = 2;
+constexpr int kTiledThreads = kTileRows + 32;  // + one producer warp
+constexpr int kTiledCtasPerSm = 2;
+
+cudaError_t launch_to_mont(int field, fr_t* v, uint64_t n, int* d_bad_flag, cudaStream_t s);
+cudaError_t launch_from_mont(int field, fr_t* v, uint64_t n, cudaStream_t s);
+cudaError_t launch_fr_binop(int field, int op, const fr_t* a, const fr_t* b, fr_t* o, uint64_t n, cudaStream_t s);
+cudaError_t launch_init_result(unsigned long long* d_result, cudaStream_t s);
+
+// thread-per-row check over local rows [row_lo, row_hi); Aw/Bw/Cw may be null
+cudaError_t launch_r1cs_rowwise(int field, const DevR1cs& m, const fr_t* w, uint32_t row_lo, uint32_t row_hi,
+                                uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
+                                cudaStream_t s);
+// TMA-staged tile kernel over a list of tiles built at upload time
+cudaError_t launch_r1cs_tiled(int field, const DevR1cs& m, const fr_t* w, const Tile* d_tiles, uint32_t n_tiles,
+                              uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
+                              int sm_count, cudaStream_t s);
+size_t r1cs_tiled_smem_bytes();
+
+// NTT (K3).  A plan owns the twiddle tables of one (field, log_n, direction).
+struct NttPlan;
+cudaError_t ntt_plan_create(int field, uint32_t log_n, bool inverse, NttPlan** out);
+void ntt_plan_destroy(NttPlan* p);
+// natural -> natural (DIF passes + bit-reversal permutation); inverse plans also scale by 1/n.
+// data: batch * 2^log_n Montgomery elements (batch a power of two), scratch: same size.
+// *launches is incremented by the number of kernels enqueued.
+cudaError_t ntt_run(const NttPlan* p, fr_t* data, fr_t* scratch, uint32_t batch, cudaStream_t s, uint32_t* launches);
+// natural -> bit-reversed, no scaling (building block of the QAP pipeline)
+cudaError_t ntt_run_dif(const NttPlan* p, fr_t* data, uint32_t batch, cudaStream_t s, uint32_t* launches);
+
+// QAP pointwise kernels (K4)
+// out[i] = base^(i << shift), i < n
+cudaError_t launch_fill_powers(int field, fr_t* out, uint32_t n, fr_t base, uint32_t shift, cudaStream_t s);
+// v[i] *= pow_hi[e >> lo_bits] * pow_lo[e & mask] (* scale), e = i or bitrev_{log_n}(i)
+cudaError_t launch_scale_by_powers(int field, fr_t* v, uint64_t n, const fr_t* d_pow_hi, const fr_t* d_pow_lo,
+                                   uint32_t lo_bits, fr_t scale, bool use_scale, bool index_bitrev, uint32_t log_n,
+                                   cudaStream_t s);
+// h[i] = (a[i]*b[i] - c[i]) * zinv
+cudaError_t launch_quotient_pointwise(int field, const fr_t* a, const fr_t* b, const fr_t* c, fr_t* h, uint64_t n,
+                                      fr_t zinv, cudaStream_t s);
+// out[i] = in[bitrev(i)] within each 2^log_n block
+cudaError_t launch_bitrev_permute(const fr_t* in, fr_t* out, uint32_t log_n, uint32_t batch, cudaStream_t s);
+// h[i] += d2*a[i] + d1*b[i]  (delta terms of verificationWitnessZk)
+cudaError_t launch_axpy2(int field, fr_t* h, const fr_t* a, const fr_t* b, fr_t d2, fr_t d1, uint64_t n,
+                         cudaStream_t s);
+
+// Lagrange (K5): n <= 4096 distinct xs (Montgomery), n_polys value vectors -> coefficient vectors;
+// target: n+1 coefficients of prod (X - x_i) (may be null).  d_status: set to 1 if two xs coincide.
+cudaError_t launch_lagrange(int field, const fr_t* xs, const fr_t* ys, uint32_t n, uint32_t n_polys, fr_t* coeffs,
+                            fr_t* target, fr_t* scratch /* 2(n+1) + n + n_polys*n elements */, int* d_status, cudaStream_t s,
+                            uint32_t* launches);
+
+}  // namespace acg

@@ -1,0 +1,587 @@
+"""Host-side mirror of the reference's QAP / Circuit API for the accelerated path (Python binding of the
+C ABI; the Haskell binding with the same shape is hs/QAP/GPU.hs).  Names follow the reference
+(src/QAP.hs:11-39, src/Circuit/Arithmetic.hs:7-20) in snake_case:
+
+    reference                      here
+    ---------------------------    ---------------------------------------------
+    ArithCircuit [Gate Wire f]     ArithCircuit([Mul(..), Equal(..), Split(..)])
+    generateAssignment c inputs    generate_assignment(c, inputs) -> QapSet
+    arithCircuitToGenQAP roots c   arith_circuit_to_gen_qap(c, roots) -> GenQAP (CSR rows per root)
+    verifyAssignment qap asg       verify_assignment(ctx, gen_qap, asg) -> bool          [GPU]
+    verificationWitness[Zk]        verification_witness_zk(ctx, d1,d2,d3, gen_qap, asg)  [GPU]
+    createPolynomialsFFT           create_polynomials_fft(ctx, columns)                   [GPU]
+    createPolynomials (Lagrange)   create_polynomials(ctx, xs, ys)                        [GPU]
+    qapSetToMap                    QapSet.to_vector(layout)
+
+Every numeric step runs in libacg.so (CUDA for bulk arithmetic, C++ for per-gate host logic).  Field
+elements are Python ints at this level and (n, 4) uint64 little-endian limb arrays underneath."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import AcgCsr, AcgTiming
+
+BN254_FR = 0
+BLS12_381_FR = 1
+CHECK_AUTO, CHECK_ROWWISE, CHECK_TILED = 0, 1, 2
+UINT64_MAX = (1 << 64) - 1
+_M64 = UINT64_MAX
+
+
+class AcgError(RuntimeError):
+    def __init__(self, code: int, detail: str = ""):
+        self.code = code
+        msg = _lib.lib().acg_strerror(code).decode()
+        super().__init__("%s (%d)%s" % (msg, code, (": " + detail) if detail else ""))
+
+
+def _check(rc: int, ctx: Optional["Context"] = None):
+    if rc != 0:
+        detail = ""
+        if ctx is not None and ctx._h:
+            detail = _lib.lib().acg_last_error(ctx._h).decode()
+        raise AcgError(rc, detail)
+
+
+# ---------------------------------------------------------------------------------------------------
+# limb helpers
+# ---------------------------------------------------------------------------------------------------
+def to_limbs(vals: Iterable[int]) -> np.ndarray:
+    vals = list(vals)
+    out = np.empty((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        out[i, 0] = v & _M64
+        out[i, 1] = (v >> 64) & _M64
+        out[i, 2] = (v >> 128) & _M64
+        out[i, 3] = (v >> 192) & _M64
+    return out
+
+
+def from_limbs(a: np.ndarray) -> List[int]:
+    a = np.asarray(a, dtype=np.uint64).reshape(-1, 4)
+    return [int(r[0]) | (int(r[1]) << 64) | (int(r[2]) << 128) | (int(r[3]) << 192) for r in a]
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def field_constants(field: int) -> Dict[str, int]:
+    p = np.zeros(4, np.uint64); r = np.zeros(4, np.uint64); r2 = np.zeros(4, np.uint64)
+    ninv = C.c_uint64(); ta = C.c_uint32()
+    _check(_lib.lib().acg_field_constants(field, p.ctypes.data_as(_lib.u64p), r.ctypes.data_as(_lib.u64p),
+                                          r2.ctypes.data_as(_lib.u64p), C.byref(ninv), C.byref(ta)))
+    return {"modulus": from_limbs(p)[0], "mont_r": from_limbs(r)[0], "mont_r2": from_limbs(r2)[0],
+            "ninv64": ninv.value, "two_adicity": ta.value}
+
+
+def get_root_of_unity(field: int, k: int) -> int:
+    """getRootOfUnity k (pairing-1.0.0; Example.hs:26)."""
+    o = np.zeros(4, np.uint64)
+    _check(_lib.lib().acg_root_of_unity(field, k, o.ctypes.data_as(_lib.u64p)))
+    return from_limbs(o)[0]
+
+
+# ---------------------------------------------------------------------------------------------------
+# circuit IR (word-stream marshalling, include/acg.h)
+# ---------------------------------------------------------------------------------------------------
+def InputWire(i: int) -> int:
+    return (0 << 62) | i
+
+
+def IntermediateWire(i: int) -> int:
+    return (1 << 62) | i
+
+
+def OutputWire(i: int) -> int:
+    return (2 << 62) | i
+
+
+def Var(w):
+    return ("var", w)
+
+
+def ConstGate(f):
+    return ("const", f)
+
+
+def Add(l, r):
+    return ("add", l, r)
+
+
+def ScalarMul(s, c):
+    return ("scalar", s, c)
+
+
+def Mul(l, r, out):
+    return ("mul", l, r, out)
+
+
+def Equal(i, m, out):
+    return ("equal", i, m, out)
+
+
+def Split(i, outs):
+    return ("split", i, list(outs))
+
+
+def _limbs4(v: int) -> List[int]:
+    return [v & _M64, (v >> 64) & _M64, (v >> 128) & _M64, (v >> 192) & _M64]
+
+
+def _affine_words(c, modulus: int) -> List[int]:
+    out: List[int] = []
+    stack = [(c, False)]
+    while stack:  # iterative post-order (unsplit chains are 256 deep)
+        node, done = stack.pop()
+        tag = node[0]
+        if tag == "var":
+            out += [0, node[1]]
+        elif tag == "const":
+            out += [1] + _limbs4(node[1] % modulus)
+        elif tag == "add":
+            if done:
+                out.append(2)
+            else:
+                stack += [(node, True), (node[2], False), (node[1], False)]
+        elif tag == "scalar":
+            if done:
+                out += [3] + _limbs4(node[1] % modulus)
+            else:
+                stack += [(node, True), (node[2], False)]
+        else:
+            raise ValueError("bad affine node %r" % (tag,))
+    return out
+
+
+class ArithCircuit:
+    """ArithCircuit f = [Gate Wire f] (src/Circuit/Arithmetic.hs:149-150), parsed by the C++ host side."""
+
+    def __init__(self, field: int, gates: Sequence):
+        self.field = field
+        self.gates = list(gates)
+        modulus = field_constants(field)["modulus"]
+        words: List[int] = []
+        for g in self.gates:
+            if g[0] == "mul":
+                l, r = _affine_words(g[1], modulus), _affine_words(g[2], modulus)
+                words += [1, g[3], len(l)] + l + [len(r)] + r
+            elif g[0] == "equal":
+                words += [2, g[1], g[2], g[3]]
+            elif g[0] == "split":
+                words += [3, g[1], len(g[2])] + list(g[2])
+            else:
+                raise ValueError("bad gate %r" % (g[0],))
+        self.words = np.array(words, dtype=np.uint64)
+        h = C.c_void_p()
+        _check(_lib.lib().acg_circuit_parse(field, _ptr(self.words), len(words), C.byref(h)))
+        self._h = h
+
+    @classmethod
+    def from_words(cls, field: int, words: np.ndarray) -> "ArithCircuit":
+        self = cls.__new__(cls)
+        self.field = field
+        self.gates = None
+        self.words = np.ascontiguousarray(words, dtype=np.uint64)
+        h = C.c_void_p()
+        _check(_lib.lib().acg_circuit_parse(field, _ptr(self.words), len(self.words), C.byref(h)))
+        self._h = h
+        return self
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib.lib().acg_circuit_free(self._h)
+            self._h = None
+
+    @property
+    def num_gates(self) -> int:
+        return _lib.lib().acg_circuit_num_gates(self._h)
+
+    @property
+    def num_roots(self) -> int:
+        return _lib.lib().acg_circuit_num_roots(self._h)
+
+    def valid(self) -> bool:
+        """validArithCircuit (src/Circuit/Arithmetic.hs:158-185)."""
+        return bool(_lib.lib().acg_circuit_valid(self._h))
+
+
+def unsplit(wires: Sequence[int]):
+    """unsplit (src/Circuit/Arithmetic.hs:238-244)."""
+    acc = ConstGate(0)
+    for ix, w in enumerate(wires):
+        acc = Add(acc, ScalarMul(1 << ix, Var(w)))
+    return acc
+
+
+class QapSet:
+    """QapSet f of witness values (src/QAP.hs:66-71); constant = 1."""
+
+    def __init__(self, field: int, handle):
+        self.field = field
+        self._h = handle
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib.lib().acg_assignment_free(self._h)
+            self._h = None
+
+    def dims(self) -> Tuple[int, int, int]:
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(_lib.lib().acg_assignment_dims(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def lookup(self, wire: int) -> Optional[int]:
+        """lookupAtWire (src/QAP.hs:331-337)."""
+        o = np.zeros(4, np.uint64)
+        rc = _lib.lib().acg_assignment_lookup(self._h, wire, o.ctypes.data_as(_lib.u64p))
+        if rc < 0:
+            _check(rc)
+        return from_limbs(o)[0] if rc == 1 else None
+
+    def update(self, wire: int, value: int) -> "QapSet":
+        """updateAtWire (src/QAP.hs:341-347), in place."""
+        v = to_limbs([value])
+        _check(_lib.lib().acg_assignment_update(self._h, wire, v.ctypes.data_as(_lib.u64p)))
+        return self
+
+    def to_vector(self, layout: Optional[Tuple[int, int, int]] = None) -> np.ndarray:
+        """qapSetToMap (src/QAP.hs:605-620) as a dense (n_cols, 4) limb array."""
+        n_in, n_mid, n_out = layout if layout is not None else self.dims()
+        w = np.zeros((1 + n_in + n_mid + n_out, 4), np.uint64)
+        _check(_lib.lib().acg_assignment_to_vector(self._h, n_in, n_mid, n_out, _ptr(w)))
+        return w
+
+
+def generate_assignment(circuit: ArithCircuit, inputs: Dict[int, int]) -> QapSet:
+    """generateAssignment (src/QAP.hs:597-603)."""
+    ix = np.array(sorted(inputs), dtype=np.uint32)
+    vals = to_limbs([inputs[int(i)] for i in ix])
+    h = C.c_void_p()
+    _check(_lib.lib().acg_generate_assignment(circuit._h, _ptr(ix), _ptr(vals), len(ix), C.byref(h)))
+    return QapSet(circuit.field, h)
+
+
+class GenQAP:
+    """The R1CS rows of GenQAP (Map k) k (src/QAP.hs:94-99): three host CSR matrices, one row per root in
+    ascending-root order.  Owns (or borrows) the arrays."""
+
+    def __init__(self, field: int, n_rows: int, n_cols: int, layout: Tuple[int, int, int], mats, roots=None,
+                 owner=None):
+        self.field = field
+        self.n_rows, self.n_cols = n_rows, n_cols
+        self.layout = layout
+        self.mats = mats          # [(rowptr u32, col u32, val (nnz,4) u64)] * 3
+        self.roots = roots
+        self._owner = owner       # keeps the C++ object (and so the borrowed arrays) alive
+
+    def csr_structs(self):
+        out = []
+        for rowptr, col, val in self.mats:
+            out.append(AcgCsr(rowptr.ctypes.data_as(_lib.u32p), col.ctypes.data_as(_lib.u32p),
+                              val.ctypes.data_as(_lib.u64p), len(col)))
+        return out
+
+    @property
+    def nnz(self) -> Tuple[int, int, int]:
+        return tuple(len(m[1]) for m in self.mats)
+
+
+class _HostR1cs:
+    def __init__(self, h):
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib.lib().acg_r1cs_host_free(self._h)
+            self._h = None
+
+
+def _gen_qap_from_handle(field: int, h) -> GenQAP:
+    L = _lib.lib()
+    owner = _HostR1cs(h)
+    n_rows, n_cols, a, b, c = (C.c_uint32() for _ in range(5))
+    _check(L.acg_r1cs_host_dims(h, C.byref(n_rows), C.byref(n_cols), C.byref(a), C.byref(b), C.byref(c)))
+    mats = []
+    for k in range(3):
+        s = AcgCsr()
+        _check(L.acg_r1cs_host_csr(h, k, C.byref(s)))
+        nnz = int(s.nnz)
+        rowptr = np.ctypeslib.as_array(s.rowptr, shape=(n_rows.value + 1,))
+        col = np.ctypeslib.as_array(s.col, shape=(nnz,)) if nnz else np.zeros(0, np.uint32)
+        val = np.ctypeslib.as_array(s.val, shape=(nnz, 4)) if nnz else np.zeros((0, 4), np.uint64)
+        mats.append((rowptr, col, val))
+    rp = L.acg_r1cs_host_roots(h)
+    roots = np.ctypeslib.as_array(rp, shape=(n_rows.value, 4)) if n_rows.value else np.zeros((0, 4), np.uint64)
+    return GenQAP(field, n_rows.value, n_cols.value, (a.value, b.value, c.value), mats, roots, owner)
+
+
+def arith_circuit_to_gen_qap(circuit: ArithCircuit, roots: Optional[Sequence[Sequence[int]]] = None,
+                             root_start: int = 0, layout: Tuple[int, int, int] = (0, 0, 0)) -> GenQAP:
+    """arithCircuitToGenQAP (src/QAP.hs:530-539) as sparse rows.  roots: [[k]] per gate as in the
+    reference, or None for `fromIntegral <$> fresh` counting from root_start."""
+    flat = None
+    if roots is not None:
+        flat_list = [r for per_gate in roots for r in per_gate]
+        if len(flat_list) != circuit.num_roots:
+            raise AcgError(-1, "gateToGenQAP: wrong number of roots supplied")
+        modulus = field_constants(circuit.field)["modulus"]
+        flat = to_limbs([r % modulus for r in flat_list])
+    h = C.c_void_p()
+    _check(_lib.lib().acg_circuit_to_r1cs(circuit._h, _ptr(flat), root_start, layout[0], layout[1], layout[2],
+                                          C.byref(h)))
+    return _gen_qap_from_handle(circuit.field, h)
+
+
+def synth_r1cs(field: int, n: int, seed: int, dense: bool = False) -> Tuple[GenQAP, np.ndarray]:
+    """S(n, seed, field) of SURVEY.md 8(d): (rows, honest witness vector)."""
+    h = C.c_void_p()
+    wp = _lib.u64p()
+    _check(_lib.lib().acg_synth_r1cs(field, n, seed, int(dense), C.byref(h), C.byref(wp)))
+    g = _gen_qap_from_handle(field, h)
+    w = np.ctypeslib.as_array(wp, shape=(g.n_cols, 4)).copy()
+    _lib.lib().acg_free(wp)
+    return g, w
+
+
+def synth_circuit(field: int, n: int, seed: int, dense: bool = False) -> Tuple[ArithCircuit, Dict[int, int]]:
+    """The same family as a reference-style ArithCircuit plus its inputs (small n; cross-checks)."""
+    L = _lib.lib()
+    wp, ivp, ixp = _lib.u64p(), _lib.u64p(), _lib.u32p()
+    nw, ni = C.c_uint64(), C.c_uint32()
+    _check(L.acg_synth_circuit_words(field, n, seed, int(dense), C.byref(wp), C.byref(nw), C.byref(ixp),
+                                     C.byref(ivp), C.byref(ni)))
+    words = np.ctypeslib.as_array(wp, shape=(nw.value,)).copy()
+    ix = np.ctypeslib.as_array(ixp, shape=(ni.value,)).copy()
+    iv = np.ctypeslib.as_array(ivp, shape=(ni.value, 4)).copy()
+    for p in (wp, ivp, ixp):
+        L.acg_free(p)
+    return ArithCircuit.from_words(field, words), dict(zip((int(i) for i in ix), from_limbs(iv)))
+
+
+# ---------------------------------------------------------------------------------------------------
+# device side
+# ---------------------------------------------------------------------------------------------------
+class Context:
+    """One CUDA device + one field (acg_ctx).  Raises AcgError(ACG_ERR_NO_DEVICE) without a GPU."""
+
+    def __init__(self, field: int = BN254_FR, device: int = 0):
+        self.field = field
+        self.device = device
+        self._h = C.c_void_p()
+        _check(_lib.lib().acg_ctx_create(field, device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().acg_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_check_kernel(self, which: int):
+        _check(_lib.lib().acg_ctx_set_check_kernel(self._h, which), self)
+
+    def last_timing(self) -> Dict[str, float]:
+        t = AcgTiming()
+        _check(_lib.lib().acg_last_timing(self._h, C.byref(t)), self)
+        return {"h2d_ms": t.h2d_ms, "kernel_ms": t.kernel_ms, "d2h_ms": t.d2h_ms, "kernel_launches": t.kernel_launches}
+
+    def kernel_launch_count(self) -> int:
+        return _lib.lib().acg_kernel_launch_count(self._h)
+
+    # ---- uploads
+    def upload_r1cs(self, g: GenQAP, row_begin: int = 0, row_end: Optional[int] = None) -> "DeviceR1cs":
+        row_end = g.n_rows if row_end is None else row_end
+        a, b, c = g.csr_structs()
+        h = C.c_void_p()
+        _check(_lib.lib().acg_r1cs_upload(self._h, g.n_rows, g.n_cols, C.byref(a), C.byref(b), C.byref(c), row_begin,
+                                          row_end, C.byref(h)), self)
+        return DeviceR1cs(self, h, g, row_begin, row_end)
+
+    def upload_witness(self, w: np.ndarray) -> "DeviceVec":
+        w = np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4)
+        h = C.c_void_p()
+        _check(_lib.lib().acg_witness_upload(self._h, _ptr(w), w.shape[0], C.byref(h)), self)
+        return DeviceVec(self, h)
+
+    # ---- R1CS check
+    def r1cs_check(self, m: "DeviceR1cs", w: "DeviceVec") -> Tuple[int, int]:
+        """(number of violated rows, first violated global row or -1)."""
+        nv, fb = C.c_uint64(), C.c_uint64()
+        _check(_lib.lib().acg_r1cs_check(self._h, m._h, w._h, C.byref(nv), C.byref(fb)), self)
+        return nv.value, (-1 if fb.value == UINT64_MAX else fb.value)
+
+    def r1cs_check_async(self, m: "DeviceR1cs", w: "DeviceVec", d_result_ptr: int, stream: int):
+        _check(_lib.lib().acg_r1cs_check_async(self._h, m._h, w._h, C.c_void_p(d_result_ptr), C.c_void_p(stream)), self)
+
+    def r1cs_check_host(self, g: GenQAP, w: np.ndarray) -> Tuple[int, int]:
+        w = np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4)
+        a, b, c = g.csr_structs()
+        nv, fb = C.c_uint64(), C.c_uint64()
+        _check(_lib.lib().acg_r1cs_check_host(self._h, g.n_rows, g.n_cols, C.byref(a), C.byref(b), C.byref(c),
+                                              _ptr(w), C.byref(nv), C.byref(fb)), self)
+        return nv.value, (-1 if fb.value == UINT64_MAX else fb.value)
+
+    def r1cs_eval(self, m: "DeviceR1cs", w: "DeviceVec"):
+        n = m.row_end - m.row_begin
+        outs = [np.zeros((n, 4), np.uint64) for _ in range(3)]
+        _check(_lib.lib().acg_r1cs_eval(self._h, m._h, w._h, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2])), self)
+        return outs
+
+    # ---- NTT / interpolation
+    def ntt(self, data: np.ndarray, inverse: bool = False) -> np.ndarray:
+        d = np.array(data, dtype=np.uint64, copy=True).reshape(-1, 4)
+        n = d.shape[0]
+        log_n = n.bit_length() - 1
+        if n == 0 or (1 << log_n) != n:
+            raise AcgError(-1, "NTT length must be a power of two")
+        _check(_lib.lib().acg_ntt(self._h, _ptr(d), log_n, int(inverse)), self)
+        return d
+
+    def interpolate_columns(self, cols: np.ndarray) -> np.ndarray:
+        """cols: (n_cols_batch, N, 4) values in ascending-root order, N a power of two."""
+        d = np.array(cols, dtype=np.uint64, copy=True)
+        nb, n = d.shape[0], d.shape[1]
+        log_n = n.bit_length() - 1
+        if (1 << log_n) != n:
+            raise AcgError(-1, "column length must be a power of two")
+        _check(_lib.lib().acg_interpolate_columns(self._h, _ptr(d), log_n, nb), self)
+        return d
+
+    def qap_witness(self, m: "DeviceR1cs", w: "DeviceVec", delta=(0, 0, 0), want=("a", "b", "c", "h")):
+        N = 1
+        while N < m.gen_qap.n_rows:
+            N <<= 1
+        bufs = {k: (np.zeros((N + 1, 4), np.uint64) if k in want else None) for k in ("a", "b", "c", "h")}
+        d = to_limbs(list(delta))
+        div = C.c_int()
+        _check(_lib.lib().acg_qap_witness(self._h, m._h, w._h, _ptr(d), _ptr(bufs["a"]), _ptr(bufs["b"]),
+                                          _ptr(bufs["c"]), _ptr(bufs["h"]), C.byref(div)), self)
+        return bufs, bool(div.value)
+
+    def lagrange(self, xs: Sequence[int], ys: Sequence[Sequence[int]], want_target: bool = True):
+        n = len(xs)
+        x = to_limbs(xs)
+        y = to_limbs([v for row in ys for v in row]) if ys else np.zeros((0, 4), np.uint64)
+        co = np.zeros((max(1, len(ys) * n), 4), np.uint64)
+        tg = np.zeros((n + 1, 4), np.uint64) if want_target else None
+        _check(_lib.lib().acg_lagrange(self._h, _ptr(x), _ptr(y), n, len(ys), _ptr(co), _ptr(tg)), self)
+        polys = [from_limbs(co[i * n:(i + 1) * n]) for i in range(len(ys))]
+        return polys, (from_limbs(tg) if want_target else None)
+
+    def fr_binop(self, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, np.uint64).reshape(-1, 4)
+        b = np.ascontiguousarray(b, np.uint64).reshape(-1, 4)
+        o = np.empty_like(a)
+        _check(_lib.lib().acg_fr_binop(self._h, op, _ptr(a), _ptr(b), _ptr(o), a.shape[0]), self)
+        return o
+
+
+class DeviceR1cs:
+    def __init__(self, ctx: Context, h, g: GenQAP, row_begin: int, row_end: int):
+        self.ctx, self._h, self.gen_qap = ctx, h, g
+        self.row_begin, self.row_end = row_begin, row_end
+
+    def free(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            _lib.lib().acg_r1cs_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        self.free()
+
+    @property
+    def algorithmic_bytes(self) -> int:
+        return _lib.lib().acg_r1cs_algorithmic_bytes(self._h)
+
+
+class DeviceVec:
+    def __init__(self, ctx: Context, h):
+        self.ctx, self._h = ctx, h
+
+    def free(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            _lib.lib().acg_vec_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        self.free()
+
+    def __len__(self):
+        return _lib.lib().acg_vec_len(self._h)
+
+    @property
+    def device_ptr(self) -> int:
+        return _lib.lib().acg_vec_device_ptr(self._h)
+
+    def update(self, w: np.ndarray):
+        w = np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4)
+        _check(_lib.lib().acg_witness_update(self.ctx._h, self._h, _ptr(w), w.shape[0]), self.ctx)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference-named entry points (GPU)
+# ---------------------------------------------------------------------------------------------------
+def strip(poly: Sequence[int]) -> List[int]:
+    """VPoly normal form: no trailing zero coefficients (poly-0.4; matters for `== 0`, src/QAP.hs:310)."""
+    p = list(poly)
+    while p and p[-1] == 0:
+        p.pop()
+    return p
+
+
+def verify_assignment(ctx: Context, g: GenQAP, assignment: QapSet) -> bool:
+    """verifyAssignment (src/QAP.hs:276-282) in R1CS form: one upload + one check."""
+    w = assignment.to_vector(g.layout)
+    nv, _ = ctx.r1cs_check_host(g, w)
+    return nv == 0
+
+
+def verification_witness_zk(ctx: Context, d1: int, d2: int, d3: int, g: GenQAP, assignment: QapSet):
+    """verificationWitnessZk (src/QAP.hs:300-327) on the FFT-built QAP: `Just h` (stripped coefficient
+    list) or None."""
+    m = ctx.upload_r1cs(g)
+    w = ctx.upload_witness(assignment.to_vector(g.layout))
+    try:
+        bufs, ok = ctx.qap_witness(m, w, (d1, d2, d3), want=("h",))
+    finally:
+        w.free()
+        m.free()
+    return strip(from_limbs(bufs["h"])) if ok else None
+
+
+def verification_witness(ctx: Context, g: GenQAP, assignment: QapSet):
+    """verificationWitness (src/QAP.hs:292-298)."""
+    return verification_witness_zk(ctx, 0, 0, 0, g, assignment)
+
+
+def create_polynomials_fft(ctx: Context, columns: Sequence[Sequence[int]]) -> List[List[int]]:
+    """The per-wire work of createPolynomialsFFT (src/QAP.hs:512-525): each column is a wire's values in
+    ascending-root order; returns the stripped interpolants."""
+    n = max((len(c) for c in columns), default=1)
+    N = 1
+    while N < n:
+        N <<= 1
+    arr = np.zeros((len(columns), N, 4), np.uint64)
+    for i, col in enumerate(columns):
+        if len(col):
+            arr[i, :len(col)] = to_limbs(col)
+    out = ctx.interpolate_columns(arr)
+    return [strip(from_limbs(out[i])) for i in range(len(columns))]
+
+
+def create_polynomials(ctx: Context, xs: Sequence[int], ys: Sequence[Sequence[int]]):
+    """createPolynomials' Lagrange build (src/QAP.hs:486-508): (stripped interpolants, target)."""
+    polys, target = ctx.lagrange(xs, ys, True)
+    return [strip(p) for p in polys], strip(target)

@@ -1,0 +1,243 @@
+/* acg.h -- C ABI of the B200-native R1CS / QAP hot path ("arithmetic-circuits on GPU").
+ *
+ * The reference (sdiehl/arithmetic-circuits @ 18e15de) is pure Haskell and has NO FFI today; the
+ * drop-in boundary is the export list of module QAP (src/QAP.hs:11-39).  Each entry point below names
+ * the reference function(s) whose numeric work it replaces; the Haskell module that binds them
+ * (`foreign import ccall safe`) and keeps the reference's names/types is
+ * arithmetic-circuits_b200/hs/QAP/GPU.hs, described in INTEGRATION.md.
+ *
+ * Conventions
+ *   - Field element  = 4 little-endian uint64 limbs (32 bytes), CANONICAL residue in [0, r) on both
+ *     sides of the ABI (`fromP` of galois-field's `Prime r`).  A non-canonical input is an error
+ *     (ACG_ERR_NON_CANONICAL), never silently reduced.
+ *   - Witness vector = dense w in qapSetToMap order (src/QAP.hs:605-620): index 0 the constant 1,
+ *     then inputs, intermediates, outputs.
+ *   - R1CS           = three CSR matrices A, B, C with one row per root, rows in ascending-root order
+ *     (the Map key order of GenQAP (Map k) k, src/QAP.hs:94-99, 530-539), columns = witness indices.
+ *   - Caller owns every host buffer; the library copies in/out and owns device memory behind opaque
+ *     handles.  No callbacks, no exceptions, no exit() across the ABI.
+ *   - Return value: 0 = ACG_OK, negative = error class.  AN INVALID WITNESS IS NOT AN ERROR
+ *     (mirrors `Nothing`, src/QAP.hs:310-312): it is reported through the out-parameters.
+ *   - One in-flight call per context.  Blocking calls return when the result is on the host.
+ *     `_async` calls only enqueue on the given CUDA stream (cudaStream_t passed as void*).
+ *   - There is NO CPU fallback: without a CUDA device every compute call fails with ACG_ERR_NO_DEVICE.
+ */
+#ifndef ACG_H
+#define ACG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACG_ABI_VERSION 1
+
+/* field_id: the reference's type parameter `f` / `k`, monomorphised (FFI cannot be class-polymorphic) */
+enum { ACG_FIELD_BN254_FR = 0,       /* Data.Pairing.BN254.Fr   (bench/Circuit.hs:10, test/Test/QAP.hs:12) */
+       ACG_FIELD_BLS12_381_FR = 1 }; /* BASELINE.json configs[4] */
+
+enum {
+    ACG_OK = 0,
+    ACG_ERR_BAD_ARG = -1,        /* also the reference's `panic` cases, e.g. src/QAP.hs:445,474 */
+    ACG_ERR_NON_CANONICAL = -2,  /* a field element >= r crossed the ABI */
+    ACG_ERR_CUDA = -3,
+    ACG_ERR_OOM = -4,
+    ACG_ERR_NO_DEVICE = -5,
+    ACG_ERR_UNSUPPORTED = -6,    /* e.g. log_n above the field's 2-adicity */
+    ACG_ERR_INTERNAL = -7
+};
+
+typedef struct acg_ctx acg_ctx;          /* one CUDA device + one field */
+typedef struct acg_r1cs acg_r1cs;        /* device-resident A, B, C (a row range of them) */
+typedef struct acg_vec acg_vec;          /* device-resident vector of field elements (Montgomery form) */
+
+/* CSR matrix on the host: rowptr[n_rows+1], col[nnz], val[4*nnz] canonical limbs. */
+typedef struct {
+    const uint32_t* rowptr;
+    const uint32_t* col;
+    const uint64_t* val;
+    uint64_t nnz;
+} acg_csr;
+
+/* Device time (CUDA events) of the phases of the last call on this context, milliseconds. */
+typedef struct {
+    float h2d_ms;
+    float kernel_ms;
+    float d2h_ms;
+    uint32_t kernel_launches;   /* launches of this library's own kernels in the last call */
+    uint32_t reserved;
+} acg_timing;
+
+/* Which K2 kernel acg_r1cs_check uses (tuning / A-B measurement; results are identical). */
+enum { ACG_CHECK_AUTO = 0, ACG_CHECK_ROWWISE = 1, ACG_CHECK_TILED = 2 };
+
+/* ---- library / context --------------------------------------------------------------------------- */
+int acg_abi_version(void);
+const char* acg_strerror(int code);
+/* Detail of the last failure on this context (empty string if none).  Valid until the next call. */
+const char* acg_last_error(const acg_ctx* ctx);
+/* device: CUDA ordinal.  Fails with ACG_ERR_NO_DEVICE when no usable GPU exists (no CPU fallback). */
+int acg_ctx_create(int field_id, int device, acg_ctx** out);
+void acg_ctx_destroy(acg_ctx* ctx);
+int acg_ctx_set_check_kernel(acg_ctx* ctx, int which);
+int acg_last_timing(const acg_ctx* ctx, acg_timing* out);
+/* Total launches of this library's kernels on this context since creation. */
+uint64_t acg_kernel_launch_count(const acg_ctx* ctx);
+
+/* Field constants, host-only (no device needed): modulus, Montgomery R, R^2, -r^-1 mod 2^64, and
+ * getRootOfUnity k (pairing-1.0.0; call sites Example.hs:26, bench/Circuit.hs:33). */
+int acg_field_constants(int field_id, uint64_t modulus[4], uint64_t mont_r[4], uint64_t mont_r2[4],
+                        uint64_t* ninv64, uint32_t* two_adicity);
+int acg_root_of_unity(int field_id, uint32_t k, uint64_t out[4]);
+
+/* ---- R1CS check: replaces verifyAssignment / verificationWitness's predicate ---------------------
+ * src/QAP.hs:276-327 in its evaluation-domain form: valid <=> for every root g
+ * (A.w)_g * (B.w)_g - (C.w)_g == 0, each dot product as src/Circuit/Affine.hs:121-125 (missing = 0). */
+
+/* Upload rows [row_begin, row_end) of A, B, C (pass 0, n_rows for everything; a strict sub-range is a
+ * shard for multi-GPU row partitioning).  CSR arrays describe the FULL matrices. */
+int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_csr* A, const acg_csr* B,
+                    const acg_csr* C, uint32_t row_begin, uint32_t row_end, acg_r1cs** out);
+void acg_r1cs_free(acg_r1cs* m);
+/* Algorithmic bytes one check of this (shard of the) system reads: SURVEY.md 8(d) formula
+ * sum_M [nnz_M*(32+4) + 4*(rows+1)] + 32*n_cols + 8. */
+uint64_t acg_r1cs_algorithmic_bytes(const acg_r1cs* m);
+
+/* w: n_cols canonical elements in qapSetToMap order (src/QAP.hs:605-620). */
+int acg_witness_upload(acg_ctx* ctx, const uint64_t* w, uint32_t n_cols, acg_vec** out);
+/* Overwrite an existing device witness from host memory (same length). */
+int acg_witness_update(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t n_cols);
+void acg_vec_free(acg_vec* v);
+uint32_t acg_vec_len(const acg_vec* v);
+/* Raw device pointer of the vector's storage (Montgomery form), for zero-copy interop. */
+void* acg_vec_device_ptr(acg_vec* v);
+
+/* Blocking.  n_violations = number of rows with a non-zero residual; first_bad_row = smallest such
+ * GLOBAL row index, or UINT64_MAX when valid.  valid <=> *n_violations == 0  (verifyAssignment). */
+int acg_r1cs_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* n_violations,
+                   uint64_t* first_bad_row);
+/* Enqueue only: d_result points to 2 device uint64 {n_violations, first_bad_row}; the kernel sequence
+ * zero-initialises them itself.  Used to all-reduce the residual count across row shards (NCCL) and
+ * to time the kernels with CUDA events on `stream`. */
+int acg_r1cs_check_async(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* d_result,
+                         void* stream);
+/* One-shot from host buffers (upload + check + read-back): the end-to-end call a Haskell wrapper of
+ * verifyAssignmentR1CS makes. */
+int acg_r1cs_check_host(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_csr* A, const acg_csr* B,
+                        const acg_csr* C, const uint64_t* w, uint64_t* n_violations, uint64_t* first_bad_row);
+/* A.w, B.w, C.w for the uploaded rows, canonical, to host buffers of 4*rows limbs (any may be NULL). */
+int acg_r1cs_eval(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* Aw, uint64_t* Bw,
+                  uint64_t* Cw);
+
+/* ---- NTT: replaces FFT.interpolate / the DFT of galois-fft (src/QAP.hs:521-523) -------------------
+ * In place on 2^log_n canonical elements, natural order in and out.  inverse=0: out[i] = sum_j
+ * in[j] w^(ij); inverse=1: the inverse (scaled by 1/n), w = getRootOfUnity log_n. */
+int acg_ntt(acg_ctx* ctx, uint64_t* data, uint32_t log_n, int inverse);
+/* Same on a device vector (Montgomery form), enqueue only. */
+int acg_ntt_device(acg_ctx* ctx, acg_vec* v, uint32_t log_n, int inverse, void* stream);
+/* createPolynomialsFFT's per-wire work (src/QAP.hs:512-525): n_cols_batch columns, each 2^log_n
+ * canonical values in ascending-root order (zero-padded by the caller), replaced in place by the
+ * coefficients of the interpolating polynomial (little-endian, length 2^log_n, NOT stripped). */
+int acg_interpolate_columns(acg_ctx* ctx, uint64_t* cols, uint32_t log_n, uint32_t n_cols_batch);
+
+/* ---- QAP witness polynomials: replaces verificationWitnessZk (src/QAP.hs:300-327) ------------------
+ * on the FFT-built QAP of arithCircuitToQAPFFT with N = 2^ceil(log2 n_rows) and T = X^N - 1, using
+ * the linearity collapse sum_k w_k * interpolate(col_k) = interpolate(A.w).
+ * delta = {delta1, delta2, delta3} (12 limbs; NULL = zeros).  Outputs (each N+1 elements, canonical,
+ * little-endian coefficients, not stripped; any may be NULL): a = delta1*T + sum w_k A_k, b, c
+ * likewise, h = (a*b - c) / T.  *divisible = 1 iff the remainder is zero (then h is the reference's
+ * `Just quotient`); when 0 the reference returns Nothing and h is unspecified.
+ * Requires the full system (row_begin = 0, row_end = n_rows). */
+int acg_qap_witness(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, const uint64_t* delta,
+                    uint64_t* a, uint64_t* b, uint64_t* c, uint64_t* h, int* divisible);
+
+/* ---- Lagrange: replaces createPolynomials.lagrangeInterpolate (src/QAP.hs:495-508) ----------------
+ * n distinct canonical xs, n_polys value vectors ys (n_polys*n elements) -> n_polys coefficient
+ * vectors (n each, little-endian, not stripped); target (n+1 coefficients, may be NULL) =
+ * prod (X - x_i) (src/QAP.hs:492).  O(n^2) per polynomial; n <= 4096. */
+int acg_lagrange(acg_ctx* ctx, const uint64_t* xs, const uint64_t* ys, uint32_t n, uint32_t n_polys,
+                 uint64_t* coeffs, uint64_t* target);
+
+/* ---- field ops on the device (K1 self-test surface) ------------------------------------------------
+ * op: 0 add, 1 sub, 2 mul, 3 inverse of a (inv 0 = 0, as evalGate treats it, Arithmetic.hs:130).
+ * n canonical elements each; blocking. */
+int acg_fr_binop(acg_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n);
+
+/* ================================================================================================
+ * Host side of the path (C++ behind this ABI; no GPU needed): circuit IR, witness generation and
+ * R1CS row construction, mirroring the reference functions so a caller can go ArithCircuit ->
+ * {QapSet, CSR} -> GPU without Haskell in the loop.
+ * ================================================================================================ */
+typedef struct acg_circuit acg_circuit;       /* ArithCircuit f,  src/Circuit/Arithmetic.hs:149-150 */
+typedef struct acg_assignment acg_assignment; /* QapSet f,        src/QAP.hs:66-71 */
+typedef struct acg_r1cs_host acg_r1cs_host;   /* GenQAP (Map k) k as CSR, src/QAP.hs:94-99 */
+
+/* Wire encoding (src/Circuit/Arithmetic.hs:32-36): kind in the top 2 bits, index below. */
+#define ACG_WIRE_INPUT 0u
+#define ACG_WIRE_INTERMEDIATE 1u
+#define ACG_WIRE_OUTPUT 2u
+#define ACG_WIRE(kind, ix) ((((uint64_t)(kind)) << 62) | (uint64_t)(ix))
+
+/* Circuit = flat stream of uint64 words (what a Haskell `ArithCircuit Fr -> [Word64]` marshaller emits):
+ *   Mul l r out      : 1, out, n_l, <l tokens>, n_r, <r tokens>      (n_* = number of WORDS)
+ *   Equal i m out    : 2, i, m, out
+ *   Split i outs     : 3, i, n_outs, outs...
+ * Affine circuit tokens in POST-ORDER (src/Circuit/Affine.hs:26-31):
+ *   Var w : 0, w      ConstGate f : 1, f0..f3      Add : 2 (pops r, l)      ScalarMul f : 3, f0..f3 (pops 1)
+ */
+int acg_circuit_parse(int field_id, const uint64_t* words, uint64_t n_words, acg_circuit** out);
+void acg_circuit_free(acg_circuit* c);
+uint64_t acg_circuit_num_gates(const acg_circuit* c);
+/* validArithCircuit, src/Circuit/Arithmetic.hs:158-185: returns 1/0. */
+int acg_circuit_valid(const acg_circuit* c);
+/* Total number of roots generateRoots draws (src/Circuit/Arithmetic.hs:194-216) = number of R1CS rows. */
+uint64_t acg_circuit_num_roots(const acg_circuit* c);
+
+/* generateAssignment (src/QAP.hs:597-603 -> evalArithCircuit, Arithmetic.hs:221-235).
+ * inputs: n_inputs pairs (index, canonical value). */
+int acg_generate_assignment(const acg_circuit* c, const uint32_t* input_ix, const uint64_t* input_vals,
+                            uint32_t n_inputs, acg_assignment** out);
+void acg_assignment_free(acg_assignment* a);
+/* Sizes of the QapSet's three maps as qapSetToMap counts them (maxKey+1) and number of present keys. */
+int acg_assignment_dims(const acg_assignment* a, uint32_t* n_in, uint32_t* n_mid, uint32_t* n_out);
+/* Look one wire up (lookupAtWire, src/QAP.hs:331-337): returns 1 and fills out when present, else 0. */
+int acg_assignment_lookup(const acg_assignment* a, uint64_t wire, uint64_t out[4]);
+/* Replace/insert a value (updateAtWire, src/QAP.hs:341-347) -- used to build faulty assignments. */
+int acg_assignment_update(acg_assignment* a, uint64_t wire, const uint64_t val[4]);
+/* qapSetToMap (src/QAP.hs:605-620) densified: fills w[4*n_cols]; wires not present are 0.  The block
+ * sizes are those of the LAYOUT (n_in, n_mid, n_out), which must cover the assignment's keys. */
+int acg_assignment_to_vector(const acg_assignment* a, uint32_t n_in, uint32_t n_mid, uint32_t n_out,
+                             uint64_t* w);
+
+/* arithCircuitToGenQAP (src/QAP.hs:530-539) without addMissingZeroes' densification: gateToGenQAP per
+ * gate (src/QAP.hs:366-474), rows sorted by ascending root.  roots: acg_circuit_num_roots canonical
+ * elements in generateRoots order, or NULL for `fromIntegral <$> fresh` starting at root_start
+ * (bench/Circuit.hs:31 uses 0, Example.hs:24 uses 1).  Layout block sizes as above; pass zeros to let
+ * the library derive them from the circuit's wires. */
+int acg_circuit_to_r1cs(const acg_circuit* c, const uint64_t* roots, uint64_t root_start, uint32_t n_in,
+                        uint32_t n_mid, uint32_t n_out, acg_r1cs_host** out);
+void acg_r1cs_host_free(acg_r1cs_host* m);
+int acg_r1cs_host_dims(const acg_r1cs_host* m, uint32_t* n_rows, uint32_t* n_cols, uint32_t* n_in,
+                       uint32_t* n_mid, uint32_t* n_out);
+/* Borrow the CSR arrays (valid until acg_r1cs_host_free).  which: 0 = A, 1 = B, 2 = C. */
+int acg_r1cs_host_csr(const acg_r1cs_host* m, int which, acg_csr* out);
+/* Sorted roots, one per row (4*n_rows limbs). */
+const uint64_t* acg_r1cs_host_roots(const acg_r1cs_host* m);
+
+/* Synthetic family S(n, seed, field) of SURVEY.md 8(d) (bench / parity workloads): n Mul gates over
+ * 1024 inputs, ~5.5 nnz per row.  Returns the lowered system and its honest witness directly
+ * (same result as parse -> generate_assignment -> to_r1cs on the equivalent ArithCircuit, which
+ * acg_synth_circuit_words emits for cross-checking at small n).  dense != 0: every coefficient a
+ * uniform field element. */
+int acg_synth_r1cs(int field_id, uint32_t n, uint64_t seed, int dense, acg_r1cs_host** out_m,
+                   uint64_t** out_w /* malloc'ed 4*n_cols limbs; free with acg_free */);
+int acg_synth_circuit_words(int field_id, uint32_t n, uint64_t seed, int dense, uint64_t** out_words,
+                            uint64_t* out_n_words, uint32_t** out_input_ix, uint64_t** out_input_vals,
+                            uint32_t* out_n_inputs);
+void acg_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACG_H */
