@@ -34,6 +34,8 @@ PROTOTYPES = {
     "acg_ctx_set_check_kernel": (C.c_int, [vp, C.c_int]),
     "acg_last_timing": (C.c_int, [vp, C.POINTER(AcgTiming)]),
     "acg_kernel_launch_count": (C.c_uint64, [vp]),
+    "acg_profile_begin": (C.c_int, [vp, C.c_uint32]),
+    "acg_profile_end": (C.c_int, [vp, C.POINTER(C.c_float), C.c_uint32, u32p]),
     "acg_field_constants": (C.c_int, [C.c_int, u64p, u64p, u64p, u64p, u32p]),
     "acg_root_of_unity": (C.c_int, [C.c_int, C.c_uint32, u64p]),
     "acg_r1cs_upload": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.POINTER(AcgCsr), C.POINTER(AcgCsr),
@@ -73,6 +75,8 @@ PROTOTYPES = {
     "acg_r1cs_host_csr": (C.c_int, [vp, C.c_int, C.POINTER(AcgCsr)]),
     "acg_r1cs_host_roots": (u64p, [vp]),
     "acg_synth_r1cs": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(vp), C.POINTER(u64p)]),
+    "acg_synth_r1cs_rows": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(vp),
+                                      C.POINTER(u64p)]),
     "acg_synth_circuit_words": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(u64p), u64p,
                                           C.POINTER(u32p), C.POINTER(u64p), u32p]),
     "acg_free": (None, [vp]),

@@ -40,6 +40,9 @@ struct acg_ctx {
         uint32_t lo_bits = 0;
     };
     std::map<uint32_t, CosetTables> coset;
+    // optional per-launch device timing of the main check kernel (acg_profile_*)
+    std::vector<cudaEvent_t> prof_ev;  // pairs
+    uint32_t prof_used = 0;
 };
 
 struct acg_r1cs {
@@ -219,16 +222,28 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long 
     ++*launches;
     int which = ctx->check_kernel == ACG_CHECK_AUTO ? ACG_CHECK_TILED : ctx->check_kernel;
     if (which == ACG_CHECK_ROWWISE) {
+        const bool prof_r = 2 * (ctx->prof_used + 1) <= ctx->prof_ev.size();
+        if (prof_r) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
         if (n_local) {
             CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, 0, n_local, m->row_begin, d_result, Aw, Bw, Cw, s));
             ++*launches;
         }
+        if (prof_r) {
+            CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], s));
+            ++ctx->prof_used;
+        }
         return ACG_OK;
     }
+    const bool prof = 2 * (ctx->prof_used + 1) <= ctx->prof_ev.size();
+    if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
     if (m->n_tiles) {
         CU(ctx, launch_r1cs_tiled(ctx->field, m->dev, w, m->d_tiles, m->n_tiles, m->row_begin, d_result, Aw, Bw, Cw,
                                   ctx->sm_count, s));
         ++*launches;
+    }
+    if (prof) {
+        CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], s));
+        ++ctx->prof_used;
     }
     for (const auto& lr : m->long_ranges) {
         CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, lr.first, lr.second, m->row_begin, d_result, Aw, Bw, Cw, s));
@@ -321,6 +336,7 @@ void acg_ctx_destroy(acg_ctx* ctx) {
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -338,6 +354,37 @@ int acg_last_timing(const acg_ctx* ctx, acg_timing* out) {
 }
 
 uint64_t acg_kernel_launch_count(const acg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int acg_profile_begin(acg_ctx* ctx, uint32_t max_launches) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    while (ctx->prof_ev.size() < 2ull * max_launches) {
+        cudaEvent_t e;
+        CU(ctx, cudaEventCreate(&e));
+        ctx->prof_ev.push_back(e);
+    }
+    while (ctx->prof_ev.size() > 2ull * max_launches) {
+        cudaEventDestroy(ctx->prof_ev.back());
+        ctx->prof_ev.pop_back();
+    }
+    ctx->prof_used = 0;
+    return ACG_OK;
+}
+
+int acg_profile_end(acg_ctx* ctx, float* ms_out, uint32_t capacity, uint32_t* n_out) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    uint32_t n = ctx->prof_used < capacity ? ctx->prof_used : capacity;
+    for (uint32_t i = 0; i < n; ++i) {
+        CU(ctx, cudaEventSynchronize(ctx->prof_ev[2 * i + 1]));
+        CU(ctx, cudaEventElapsedTime(&ms_out[i], ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+    }
+    if (n_out) *n_out = n;
+    for (auto e : ctx->prof_ev) cudaEventDestroy(e);
+    ctx->prof_ev.clear();
+    ctx->prof_used = 0;
+    return ACG_OK;
+}
 
 int acg_field_constants(int field_id, uint64_t modulus[4], uint64_t mont_r[4], uint64_t mont_r2[4], uint64_t* ninv64,
                         uint32_t* two_adic) {

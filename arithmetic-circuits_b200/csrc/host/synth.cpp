@@ -88,24 +88,26 @@ El term_coef_mont(const Term& t) {
 }
 
 template <class P>
-int synth_r1cs_impl(uint32_t n, uint64_t seed, bool dense, acg_r1cs_host* m, uint64_t* w) {
+int synth_r1cs_impl(uint32_t n, uint64_t seed, bool dense, uint32_t rb, uint32_t re, acg_r1cs_host* m, uint64_t* w) {
     SplitMix64 rng{seed};
     const uint32_t n_cols = 1 + kInputs + n;
     std::vector<El> wm((size_t)n_cols);  // Montgomery witness
     wm[0] = Fr<P>::one();
     for (uint32_t i = 0; i < kInputs; ++i) wm[1 + i] = Fr<P>::to_mont(rng.field<P>());
     for (int k = 0; k < 3; ++k) {
-        m->rowptr[k].reserve((size_t)n + 1);
+        m->rowptr[k].reserve((size_t)(re - rb) + 1);
         m->rowptr[k].push_back(0);
     }
-    m->col[0].reserve((size_t)n * 9 / 4 + 16);
-    m->col[1].reserve((size_t)n * 9 / 4 + 16);
-    m->col[2].reserve(n);
-    m->val[0].reserve((size_t)n * 9 + 64);
-    m->val[1].reserve((size_t)n * 9 + 64);
-    m->val[2].reserve((size_t)n * 4);
+    const size_t nl = re - rb;
+    m->col[0].reserve(nl * 9 / 4 + 16);
+    m->col[1].reserve(nl * 9 / 4 + 16);
+    m->col[2].reserve(nl);
+    m->val[0].reserve(nl * 9 + 64);
+    m->val[1].reserve(nl * 9 + 64);
+    m->val[2].reserve(nl * 4);
     for (uint32_t g = 0; g < n; ++g) {
         const uint32_t avail = 1 + kInputs + g;
+        const bool keep = g >= rb && g < re;
         El side_val[2];
         for (int side = 0; side < 2; ++side) {
             Term t[3];
@@ -137,31 +139,34 @@ int synth_r1cs_impl(uint32_t n, uint64_t seed, bool dense, acg_r1cs_host* m, uin
             for (int i = 0; i < nu; ++i) {
                 if (coefs[i].is_zero()) continue;
                 acc = Fr<P>::add(acc, Fr<P>::mul(coefs[i], wm[cols[i]]));
+                if (!keep) continue;
                 m->col[side].push_back(cols[i]);
                 const El c = Fr<P>::from_mont(coefs[i]);
                 m->val[side].insert(m->val[side].end(), c.v, c.v + 4);
             }
-            m->rowptr[side].push_back((uint32_t)m->col[side].size());
+            if (keep) m->rowptr[side].push_back((uint32_t)m->col[side].size());
             side_val[side] = acc;
         }
         const uint32_t out_col = 1 + kInputs + g;
         wm[out_col] = Fr<P>::mul(side_val[0], side_val[1]);
-        m->col[2].push_back(out_col);
-        const uint64_t one[4] = {1, 0, 0, 0};
-        m->val[2].insert(m->val[2].end(), one, one + 4);
-        m->rowptr[2].push_back((uint32_t)m->col[2].size());
+        if (keep) {
+            m->col[2].push_back(out_col);
+            const uint64_t one[4] = {1, 0, 0, 0};
+            m->val[2].insert(m->val[2].end(), one, one + 4);
+            m->rowptr[2].push_back((uint32_t)m->col[2].size());
+        }
     }
     for (uint32_t i = 0; i < n_cols; ++i) {
         const El c = Fr<P>::from_mont(wm[i]);
         std::memcpy(w + 4ull * i, c.v, 32);
     }
-    m->n_rows = n;
+    m->n_rows = re - rb;
     m->n_cols = n_cols;
     m->n_in = kInputs;
     m->n_mid = n ? n - 1 : 0;
     m->n_out = n ? 1 : 0;
-    m->roots.resize(4ull * n);
-    for (uint32_t r = 0; r < n; ++r) m->roots[4ull * r] = r;
+    m->roots.resize(4ull * (re - rb));
+    for (uint32_t r = rb; r < re; ++r) m->roots[4ull * (r - rb)] = r;
     return ACG_OK;
 }
 
@@ -218,7 +223,13 @@ int synth_words_impl(uint32_t n, uint64_t seed, bool dense, std::vector<uint64_t
 extern "C" {
 
 int acg_synth_r1cs(int field_id, uint32_t n, uint64_t seed, int dense, acg_r1cs_host** out_m, uint64_t** out_w) {
-    if (!out_m || !out_w || n == 0 || n > 0xF0000000u - kInputs) return ACG_ERR_BAD_ARG;
+    return acg_synth_r1cs_rows(field_id, n, seed, dense, 0, n, out_m, out_w);
+}
+
+int acg_synth_r1cs_rows(int field_id, uint32_t n, uint64_t seed, int dense, uint32_t row_begin, uint32_t row_end,
+                        acg_r1cs_host** out_m, uint64_t** out_w) {
+    if (!out_m || !out_w || n == 0 || n > 0xF0000000u - kInputs || row_begin > row_end || row_end > n)
+        return ACG_ERR_BAD_ARG;
     *out_m = nullptr;
     *out_w = nullptr;
     acg_r1cs_host* m = new (std::nothrow) acg_r1cs_host();
@@ -231,8 +242,8 @@ int acg_synth_r1cs(int field_id, uint32_t n, uint64_t seed, int dense, acg_r1cs_
     m->field = field_id;
     int rc = ACG_ERR_BAD_ARG;
     try {
-        if (field_id == ACG_FIELD_BN254_FR) rc = synth_r1cs_impl<Bn254Fr>(n, seed, dense != 0, m, w);
-        if (field_id == ACG_FIELD_BLS12_381_FR) rc = synth_r1cs_impl<Bls12381Fr>(n, seed, dense != 0, m, w);
+        if (field_id == ACG_FIELD_BN254_FR) rc = synth_r1cs_impl<Bn254Fr>(n, seed, dense != 0, row_begin, row_end, m, w);
+        if (field_id == ACG_FIELD_BLS12_381_FR) rc = synth_r1cs_impl<Bls12381Fr>(n, seed, dense != 0, row_begin, row_end, m, w);
     } catch (const std::bad_alloc&) {
         rc = ACG_ERR_OOM;
     }

@@ -337,11 +337,14 @@ def arith_circuit_to_gen_qap(circuit: ArithCircuit, roots: Optional[Sequence[Seq
     return _gen_qap_from_handle(circuit.field, h)
 
 
-def synth_r1cs(field: int, n: int, seed: int, dense: bool = False) -> Tuple[GenQAP, np.ndarray]:
-    """S(n, seed, field) of SURVEY.md 8(d): (rows, honest witness vector)."""
+def synth_r1cs(field: int, n: int, seed: int, dense: bool = False,
+               rows: Optional[Tuple[int, int]] = None) -> Tuple[GenQAP, np.ndarray]:
+    """S(n, seed, field) of SURVEY.md 8(d): (rows, honest witness vector).  rows=(begin, end) materialises
+    only that row shard (GenQAP.n_rows = end - begin); the witness is always complete."""
     h = C.c_void_p()
     wp = _lib.u64p()
-    _check(_lib.lib().acg_synth_r1cs(field, n, seed, int(dense), C.byref(h), C.byref(wp)))
+    rb, re = rows if rows is not None else (0, n)
+    _check(_lib.lib().acg_synth_r1cs_rows(field, n, seed, int(dense), rb, re, C.byref(h), C.byref(wp)))
     g = _gen_qap_from_handle(field, h)
     w = np.ctypeslib.as_array(wp, shape=(g.n_cols, 4)).copy()
     _lib.lib().acg_free(wp)
@@ -399,6 +402,15 @@ class Context:
 
     def kernel_launch_count(self) -> int:
         return _lib.lib().acg_kernel_launch_count(self._h)
+
+    def profile_begin(self, max_launches: int):
+        _check(_lib.lib().acg_profile_begin(self._h, max_launches), self)
+
+    def profile_end(self, capacity: int) -> List[float]:
+        ms = (C.c_float * max(1, capacity))()
+        n = C.c_uint32()
+        _check(_lib.lib().acg_profile_end(self._h, ms, capacity, C.byref(n)), self)
+        return [ms[i] for i in range(n.value)]
 
     # ---- uploads
     def upload_r1cs(self, g: GenQAP, row_begin: int = 0, row_end: Optional[int] = None) -> "DeviceR1cs":

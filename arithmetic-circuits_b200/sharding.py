@@ -1,0 +1,54 @@
+"""Multi-GPU row sharding of the R1CS check: one process per GPU (torch.distributed),
+rows split in contiguous blocks, witness replicated, and ONE all-reduce (sum) of the per-shard
+violated-row count.  The first violated row index needs a second (min) reduction, issued only when the
+count is non-zero.  No other data-path collective exists: the NTT / QAP build stays single-GPU."""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+INT64_MAX = (1 << 63) - 1
+
+
+def row_shard(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block of rows for `rank`: sizes differ by at most one."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, rem = divmod(n_rows, world_size)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def row_shard_balanced(rowptrs: Sequence[np.ndarray], world_size: int, rank: int) -> Tuple[int, int]:
+    """nnz-balanced contiguous split (Split gates make rows very uneven, src/QAP.hs:443-473): cut points
+    where the cumulative entry count of A+B+C crosses k/world_size of the total."""
+    n_rows = len(rowptrs[0]) - 1
+    cum = np.zeros(n_rows + 1, dtype=np.int64)
+    for rp in rowptrs:
+        cum += np.asarray(rp, dtype=np.int64)
+    cum += np.arange(n_rows + 1, dtype=np.int64)  # one unit per row so empty rows still spread
+    total = int(cum[-1])
+    cuts = [int(np.searchsorted(cum, (total * k) // world_size, side="left")) for k in range(world_size + 1)]
+    cuts[0], cuts[-1] = 0, n_rows
+    for k in range(1, world_size + 1):
+        cuts[k] = max(cuts[k], cuts[k - 1])
+    return cuts[rank], cuts[rank + 1]
+
+
+def reduce_check_result(result, group=None):
+    """result: int64 tensor [n_violations, first_bad_row] (first_bad_row = -1, i.e. UINT64_MAX, when the
+    shard is clean), on the device of the process group's backend.  Returns (total violations, first bad
+    row or -1).  One all-reduce on the common path."""
+    import torch
+    import torch.distributed as dist
+
+    count = result[0:1]
+    dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+    total = int(count.item())
+    if total == 0:
+        return 0, -1
+    first = result[1:2].clone()
+    first[first < 0] = INT64_MAX
+    dist.all_reduce(first, op=dist.ReduceOp.MIN, group=group)
+    return total, int(first.item())

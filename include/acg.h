@@ -84,6 +84,11 @@ int acg_ctx_set_check_kernel(acg_ctx* ctx, int which);
 int acg_last_timing(const acg_ctx* ctx, acg_timing* out);
 /* Total launches of this library's kernels on this context since creation. */
 uint64_t acg_kernel_launch_count(const acg_ctx* ctx);
+/* Per-launch device timing of the dominant check kernel: after acg_profile_begin, each of the next
+ * max_launches acg_r1cs_check[_async] calls records a CUDA event pair around its main kernel on the
+ * launching stream (no synchronisation).  acg_profile_end waits for them and returns the durations. */
+int acg_profile_begin(acg_ctx* ctx, uint32_t max_launches);
+int acg_profile_end(acg_ctx* ctx, float* ms_out, uint32_t capacity, uint32_t* n_out);
 
 /* Field constants, host-only (no device needed): modulus, Montgomery R, R^2, -r^-1 mod 2^64, and
  * getRootOfUnity k (pairing-1.0.0; call sites Example.hs:26, bench/Circuit.hs:33). */
@@ -232,6 +237,10 @@ const uint64_t* acg_r1cs_host_roots(const acg_r1cs_host* m);
  * uniform field element. */
 int acg_synth_r1cs(int field_id, uint32_t n, uint64_t seed, int dense, acg_r1cs_host** out_m,
                    uint64_t** out_w /* malloc'ed 4*n_cols limbs; free with acg_free */);
+/* Same system, but only rows [row_begin, row_end) are materialised (a shard for multi-GPU runs): the
+ * returned matrices have row_end-row_begin rows; the witness is complete. */
+int acg_synth_r1cs_rows(int field_id, uint32_t n, uint64_t seed, int dense, uint32_t row_begin, uint32_t row_end,
+                        acg_r1cs_host** out_m, uint64_t** out_w);
 int acg_synth_circuit_words(int field_id, uint32_t n, uint64_t seed, int dense, uint64_t** out_words,
                             uint64_t* out_n_words, uint32_t** out_input_ix, uint64_t** out_input_vals,
                             uint32_t* out_n_inputs);

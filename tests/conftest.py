@@ -1,0 +1,38 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def acg():
+    import arithmetic_circuits_b200 as m
+    m._lib.lib()  # fail loudly if libacg.so is missing
+    return m
+
+
+@pytest.fixture(scope="session")
+def ctx_bn(acg):
+    c = acg.Context(acg.BN254_FR, 0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="session")
+def ctx_bls(acg):
+    c = acg.Context(acg.BLS12_381_FR, 0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="session")
+def ctxs(ctx_bn, ctx_bls):
+    return {0: ctx_bn, 1: ctx_bls}

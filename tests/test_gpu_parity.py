@@ -1,0 +1,393 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI (libacg.so);
+expected values come from the oracle (Python big-int / C), the committed golden vectors, or -- at
+BASELINE sizes -- size-independent properties.  Integer work: the bar is bit-exact."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as CO
+from oracle import qap_oracle as O
+from helpers import FIELDS, csr_from_json, gates_acg, gates_oracle, golden, make_genqap, oracle_check, unhex
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("fid", [0, 1])
+def test_field_ops_device(acg, ctxs, fid):
+    F, ctx = FIELDS[fid], ctxs[fid]
+    rnd = random.Random(11 + fid)
+    r = F.r
+    edge = [0, 1, 2, r - 1, r - 2, F.mont_R, (r - F.mont_R) % r, (1 << 32) - 1, (1 << 64) - 1, 1 << 253, r >> 1,
+            (r >> 1) + 1, (1 << 224) - 1, 1 << 32, (1 << 96) + 5]
+    xs = [rnd.randrange(r) for _ in range(20000)] + [e for e in edge for _ in edge]
+    ys = [rnd.randrange(r) for _ in range(20000)] + [e for _ in edge for e in edge]
+    a, b = acg.to_limbs(xs), acg.to_limbs(ys)
+    assert acg.from_limbs(ctx.fr_binop(0, a, b)) == [(x + y) % r for x, y in zip(xs, ys)]
+    assert acg.from_limbs(ctx.fr_binop(1, a, b)) == [(x - y) % r for x, y in zip(xs, ys)]
+    assert acg.from_limbs(ctx.fr_binop(2, a, b)) == [(x * y) % r for x, y in zip(xs, ys)]
+    inv_in = xs[:300] + edge
+    assert acg.from_limbs(ctx.fr_binop(3, acg.to_limbs(inv_in), acg.to_limbs(inv_in))) == \
+        [pow(x, -1, r) if x else 0 for x in inv_in]
+    # a million random products against the C oracle
+    n = 1 << 20
+    rng = np.random.default_rng(5)
+    big = rng.integers(0, 1 << 63, size=(2, n, 4), dtype=np.uint64)
+    big[:, :, 3] &= np.uint64((1 << (r.bit_length() - 192 - 1)) - 1)   # < 2^(bits-1) < r
+    assert (ctx.fr_binop(2, big[0], big[1]) == CO.fr_binop(fid, 2, big[0], big[1])).all()
+    with pytest.raises(acg.AcgError) as e:
+        ctx.fr_binop(0, acg.to_limbs([r]), acg.to_limbs([1]))
+    assert e.value.code == -2
+
+
+# ------------------------------------------------------------------------------------------------ K2
+def _both_kernels(acg, ctx, fn):
+    out = []
+    for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
+        ctx.set_check_kernel(which)
+        out.append(fn())
+    ctx.set_check_kernel(acg.CHECK_AUTO)
+    assert out[0] == out[1], out
+    return out[0]
+
+
+def test_reference_unit_tests_on_gpu(acg, ctx_bn):
+    """unit_arithCircuitToQapCorrect / NoFalsePositive (test/Test/QAP.hs:68-90), bench + Example circuit,
+    through the reference-named API: verify_assignment -> acg_r1cs_check_host."""
+    gates = [acg.Mul(acg.Var(acg.InputWire(0)), acg.Var(acg.InputWire(1)), acg.IntermediateWire(0)),
+             acg.Mul(acg.Var(acg.InputWire(2)), acg.Var(acg.InputWire(3)), acg.IntermediateWire(1)),
+             acg.Mul(acg.Add(acg.ConstGate(10), acg.Var(acg.IntermediateWire(0))), acg.Var(acg.IntermediateWire(1)),
+                     acg.OutputWire(0))]
+    c = acg.ArithCircuit(0, gates)
+    g = acg.arith_circuit_to_gen_qap(c, [[7], [8], [9]])
+    a = acg.generate_assignment(c, {0: 2, 1: 3, 2: 4, 3: 5})
+    assert _both_kernels(acg, ctx_bn, lambda: acg.verify_assignment(ctx_bn, g, a)) is True
+    a.update(acg.IntermediateWire(0), 7)
+    assert _both_kernels(acg, ctx_bn, lambda: acg.verify_assignment(ctx_bn, g, a)) is False
+    assert _both_kernels(acg, ctx_bn, lambda: ctx_bn.r1cs_check_host(g, a.to_vector(g.layout))) == (2, 0)
+    # bench/Circuit.hs:17-24 + Example.hs: KAT-3, h against the oracle's FFT-built QAP
+    c3 = acg.ArithCircuit(0, [acg.Mul(acg.Var(acg.InputWire(0)), acg.Var(acg.InputWire(1)), acg.IntermediateWire(0)),
+                              acg.Mul(acg.Var(acg.IntermediateWire(0)), acg.Add(acg.Var(acg.InputWire(0)), acg.Var(acg.InputWire(2))),
+                                      acg.OutputWire(0))])
+    a3 = acg.generate_assignment(c3, {0: 7, 1: 5, 2: 4})
+    assert (a3.lookup(acg.IntermediateWire(0)), a3.lookup(acg.OutputWire(0))) == (35, 385)
+    k3 = golden("kats.json")["kat3"]["qaps"]
+    for start, name in ((0, "bench_fft"), (1, "example_fft")):
+        g3 = acg.arith_circuit_to_gen_qap(c3, None, start)
+        assert acg.verify_assignment(ctx_bn, g3, a3)
+        assert acg.verification_witness(ctx_bn, g3, a3) == unhex(k3[name]["h"])
+    a3.update(acg.OutputWire(0), 386)
+    assert acg.verification_witness(ctx_bn, acg.arith_circuit_to_gen_qap(c3), a3) is None
+
+
+def test_eq_and_split_gates_on_gpu(acg, ctx_bn):
+    eq = acg.ArithCircuit(0, [acg.Equal(acg.InputWire(0), acg.IntermediateWire(0), acg.OutputWire(0))])
+    g = acg.arith_circuit_to_gen_qap(eq, [[1, 2]])
+    for v in (0, 1, 2, 3, O.BN254.r - 1):
+        a = acg.generate_assignment(eq, {0: v})
+        assert acg.verify_assignment(ctx_bn, g, a)
+        a.update(acg.OutputWire(0), 1 - a.lookup(acg.OutputWire(0)))
+        assert not acg.verify_assignment(ctx_bn, g, a)
+    mids = [acg.IntermediateWire(i) for i in range(256)]
+    sp = acg.ArithCircuit(0, [acg.Split(acg.InputWire(0), mids), acg.Mul(acg.ConstGate(1), acg.unsplit(mids), acg.OutputWire(0))])
+    gs = acg.arith_circuit_to_gen_qap(sp, None, 1)
+    assert gs.n_rows == 258
+    rnd = random.Random(4)
+    for v in (0, 1, O.BN254.r - 1, rnd.randrange(O.BN254.r)):
+        a = acg.generate_assignment(sp, {0: v})
+        assert a.lookup(acg.OutputWire(0)) == v
+        assert _both_kernels(acg, ctx_bn, lambda: acg.verify_assignment(ctx_bn, gs, a)) is True
+        a.update(acg.IntermediateWire(200), 1 - a.lookup(acg.IntermediateWire(200)))   # flip one bit
+        nv, first = _both_kernels(acg, ctx_bn, lambda: ctx_bn.r1cs_check_host(gs, a.to_vector(gs.layout)))
+        assert nv >= 1 and first == 0   # row 0 (the recomposition) breaks; the bit stays boolean
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_mixed_circuits_gpu(acg, ctxs, idx):
+    """Golden Mul/Equal/Split circuits (256-entry Split rows, empty C rows): counts, first bad row and
+    A.w/B.w/C.w bit-exact, both kernels; coset quotient with deltas vs the big-int oracle."""
+    case = golden("mixed_circuits.json")[idx]
+    fid = case["field"]
+    ctx = ctxs[fid]
+    c = acg.ArithCircuit(fid, gates_acg(acg, gates_oracle(case["gates"])))
+    g = acg.arith_circuit_to_gen_qap(c, None, 1)
+    w = acg.to_limbs(unhex(case["w"]))
+    wb = acg.to_limbs(unhex(case["bad_w"]))
+    assert _both_kernels(acg, ctx, lambda: ctx.r1cs_check_host(g, w)) == (0, -1)
+    assert list(_both_kernels(acg, ctx, lambda: ctx.r1cs_check_host(g, wb))) == case["bad_check"]
+    m, dw = ctx.upload_r1cs(g), ctx.upload_witness(w)
+    for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
+        ctx.set_check_kernel(which)
+        aw, bw, cw = ctx.r1cs_eval(m, dw)
+        assert acg.from_limbs(aw) == unhex(case["Aw"])
+        assert acg.from_limbs(bw) == unhex(case["Bw"])
+        assert acg.from_limbs(cw) == unhex(case["Cw"])
+    ctx.set_check_kernel(acg.CHECK_AUTO)
+    if "qap_delta_3_5_7" in case:
+        q = case["qap_delta_3_5_7"]
+        bufs, ok = ctx.qap_witness(m, dw, (3, 5, 7))
+        assert ok == q["ok"]
+        for k in ("a", "b", "c", "h"):
+            assert acg.strip(acg.from_limbs(bufs[k])) == unhex(q[k]), k
+
+
+@pytest.mark.parametrize("fid,n,seed,dense", [(0, 96, 20260002, False), (0, 64, 7, True), (1, 96, 20260005, False),
+                                              (0, 1 << 12, 1, False), (0, 5000, 2, True), (1, (1 << 13) + 3, 3, False)])
+def test_synth_parity_small(acg, ctxs, fid, n, seed, dense):
+    ctx = ctxs[fid]
+    g, w = acg.synth_r1cs(fid, n, seed, dense)
+    ref = oracle_check(fid, g, w, True)
+    assert ref["n_violations"] == 0
+    m, dw = ctx.upload_r1cs(g), ctx.upload_witness(w)
+    assert m.algorithmic_bytes == sum(36 * k for k in g.nnz) + 3 * 4 * (n + 1) + 32 * g.n_cols + 8
+    for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
+        ctx.set_check_kernel(which)
+        assert ctx.r1cs_check(m, dw) == (0, -1)
+        aw, bw, cw = ctx.r1cs_eval(m, dw)
+        assert (aw == ref["Aw"]).all() and (bw == ref["Bw"]).all() and (cw == ref["Cw"]).all()
+    # negative variants: SURVEY 8d (+1 on w[1025 + n/3]) and a few random single-limb flips
+    rnd = random.Random(seed)
+    for t in [1025 + n // 3] + [rnd.randrange(1, g.n_cols) for _ in range(3)]:
+        wb = w.copy()
+        wb[t, rnd.randrange(3)] ^= np.uint64(1 << rnd.randrange(60))
+        refb = oracle_check(fid, g, wb)
+        dw.update(wb)
+        for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
+            ctx.set_check_kernel(which)
+            assert ctx.r1cs_check(m, dw) == (refb["n_violations"], refb["first_bad_row"])
+    ctx.set_check_kernel(acg.CHECK_AUTO)
+    if n <= 96:  # golden h through the reference-named call
+        case = [c for c in golden("synth.json") if (c["field"], c["n"], c["seed"]) == (fid, n, seed)][0]
+        dw.update(w)
+        bufs, ok = ctx.qap_witness(m, dw)
+        assert ok and acg.strip(acg.from_limbs(bufs["h"])) == unhex(case["h"])
+        assert acg.strip(acg.from_limbs(bufs["a"])) == unhex(case["a"])
+
+
+def test_edge_shapes(acg, ctx_bn):
+    """Empty rows, a single row, rows longer than a tile (row-wise fallback inside the tiled path),
+    tile-boundary sizes, and argument validation."""
+    F = O.BN254
+    rnd = random.Random(9)
+    n_cols = 3000
+    w = [1] + [rnd.randrange(F.r) for _ in range(n_cols - 1)]
+    specs = {
+        "single_row": [3],
+        "empty_rows": [0, 0, 5, 0, 0, 0, 2, 0],
+        "all_empty": [0] * 9,
+        "long_row_2000": [4, 2000, 4, 4, 0, 1500, 3],
+        "boundary_255_256_257": [5] * 255 + [6] + [7],
+        "tile_pool_edge": [448] * 3 + [447, 1, 449] + [2] * 300,
+    }
+    for name, lens in specs.items():
+        n = len(lens)
+        mats = []
+        for k in range(3):
+            rowptr, col, val = [0], [], []
+            for ln in lens:
+                ln_k = ln if k < 2 else min(ln, 1)
+                for _ in range(ln_k):
+                    col.append(rnd.randrange(n_cols))
+                    kind = rnd.randrange(4)
+                    val.append(1 if kind < 2 else (F.r - 1 if kind == 2 else rnd.randrange(F.r)))
+                rowptr.append(len(col))
+            mats.append(O.CSR(rowptr, col, val))
+        g = make_genqap(acg, 0, n, n_cols, (n_cols - 1, 0, 0), *mats)
+        wl = acg.to_limbs(w)
+        ref = oracle_check(0, g, wl, True)
+        m, dw = ctx_bn.upload_r1cs(g), ctx_bn.upload_witness(wl)
+        for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
+            ctx_bn.set_check_kernel(which)
+            assert ctx_bn.r1cs_check(m, dw) == (ref["n_violations"], ref["first_bad_row"]), name
+            aw, bw, cw = ctx_bn.r1cs_eval(m, dw)
+            assert (aw == ref["Aw"]).all() and (bw == ref["Bw"]).all() and (cw == ref["Cw"]).all(), name
+        ctx_bn.set_check_kernel(acg.CHECK_AUTO)
+    # validation: column out of range, non-monotone rowptr, non-canonical coefficient / witness
+    good = make_genqap(acg, 0, 1, 4, (3, 0, 0), O.CSR([0, 1], [1], [5]), O.CSR([0, 1], [2], [1]), O.CSR([0, 1], [3], [1]))
+    assert ctx_bn.r1cs_check_host(good, acg.to_limbs([1, 2, 3, 30])) == (0, -1)
+    assert ctx_bn.r1cs_check_host(good, acg.to_limbs([1, 2, 3, 31])) == (1, 0)
+    for bad, code in ((make_genqap(acg, 0, 1, 4, (3, 0, 0), O.CSR([0, 1], [4], [5]), O.CSR([0, 1], [2], [1]), O.CSR([0, 1], [3], [1])), -1),
+                      (make_genqap(acg, 0, 1, 4, (3, 0, 0), O.CSR([0, 1], [1], [F.r]), O.CSR([0, 1], [2], [1]), O.CSR([0, 1], [3], [1])), -2)):
+        with pytest.raises(acg.AcgError) as e:
+            ctx_bn.r1cs_check_host(bad, acg.to_limbs([1, 2, 3, 30]))
+        assert e.value.code == code
+    with pytest.raises(acg.AcgError) as e:
+        ctx_bn.r1cs_check_host(good, acg.to_limbs([1, 2, 3, F.r]))
+    assert e.value.code == -2
+
+
+def test_row_shards_cover_the_system(acg, ctx_bn):
+    """rows partition across devices; here the shards run one after another on one GPU and the
+    per-shard results combine (sum / min) to the full-system answer."""
+    from arithmetic_circuits_b200 import sharding
+    n = 10000
+    g, w = acg.synth_r1cs(0, n, 77)
+    w[1025 + 1234, 0] ^= np.uint64(2)
+    w[1025 + 8000, 1] ^= np.uint64(4)
+    ref = oracle_check(0, g, w)
+    dw = ctx_bn.upload_witness(w)
+    for world in (2, 4, 8):
+        tot, first = 0, None
+        for r in range(world):
+            rb, re = sharding.row_shard(n, world, r)
+            m = ctx_bn.upload_r1cs(g, rb, re)
+            nv, fb = ctx_bn.r1cs_check(m, dw)
+            tot += nv
+            if fb >= 0:
+                assert rb <= fb < re
+                first = fb if first is None else min(first, fb)
+            m.free()
+        assert (tot, first) == (ref["n_violations"], ref["first_bad_row"])
+
+
+def test_full_size_properties(acg, ctx_bn):
+    """BASELINE configs[1]: S(2^20, 20260002, BN254).  Honest witness -> 0 violations; tampered -> exactly
+    the C oracle's count and first row; both kernels agree; A.w o B.w == C.w recomputed from emitted vectors."""
+    n = 1 << 20
+    g, w = acg.synth_r1cs(0, n, 20260002)
+    m, dw = ctx_bn.upload_r1cs(g), ctx_bn.upload_witness(w)
+    for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
+        ctx_bn.set_check_kernel(which)
+        assert ctx_bn.r1cs_check(m, dw) == (0, -1)
+    wb = w.copy()
+    wb[1025 + n // 3, 0] += np.uint64(1)       # the SURVEY 8d negative variant
+    for t in (1, 1024, 1025 + n - 1):
+        wb[t, 2] ^= np.uint64(1 << 17)
+    ref = oracle_check(0, g, wb, True, n_threads=8)
+    assert ref["n_violations"] > 0
+    dw.update(wb)
+    for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
+        ctx_bn.set_check_kernel(which)
+        assert ctx_bn.r1cs_check(m, dw) == (ref["n_violations"], ref["first_bad_row"])
+    ctx_bn.set_check_kernel(acg.CHECK_AUTO)
+    aw, bw, cw = ctx_bn.r1cs_eval(m, dw)
+    assert (aw == ref["Aw"]).all() and (bw == ref["Bw"]).all() and (cw == ref["Cw"]).all()
+
+
+# ------------------------------------------------------------------------------------------------ K3 / K4
+def test_ntt_golden(acg, ctxs):
+    for case in golden("ntt.json"):
+        ctx = ctxs[case["field"]]
+        v = acg.to_limbs(unhex(case["in"]))
+        assert acg.from_limbs(ctx.ntt(v, False)) == unhex(case["fwd"])
+        assert acg.from_limbs(ctx.ntt(v, True)) == unhex(case["inv"])
+
+
+@pytest.mark.parametrize("fid,log_n", [(0, 3), (0, 9), (0, 11), (0, 12), (0, 13), (0, 16), (0, 17), (0, 20), (1, 10), (1, 14), (1, 18)])
+def test_ntt_vs_c_oracle(acg, ctxs, fid, log_n):
+    ctx = ctxs[fid]
+    rng = np.random.default_rng(log_n)
+    v = rng.integers(0, 1 << 63, size=(1 << log_n, 4), dtype=np.uint64)
+    v[:, 3] &= np.uint64((1 << 60) - 1)
+    fwd = ctx.ntt(v, False)
+    assert (fwd == CO.ntt(fid, v, False, 8)).all()
+    assert (ctx.ntt(fwd, True) == v).all()          # round trip
+    assert (ctx.ntt(v, True) == CO.ntt(fid, v, True, 8)).all()
+
+
+def test_ntt_2_22_properties(acg, ctx_bn):
+    """BASELINE configs[2] size: round trip, linearity, and a spot check of P(w^i) = v_i by Horner on a
+    sparse input (delta at position p -> coefficients are w^(-p*j)/N)."""
+    log_n = 22
+    n = 1 << log_n
+    rng = np.random.default_rng(22)
+    v = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    v[:, 3] &= np.uint64((1 << 60) - 1)
+    c = ctx_bn.ntt(v, True)
+    assert (ctx_bn.ntt(c, False) == v).all()
+    F = O.BN254
+    d = np.zeros((n, 4), np.uint64)
+    p = 123457
+    d[p, 0] = 1
+    coef = acg.from_limbs(ctx_bn.ntt(d, True)[:5])
+    om_inv = pow(F.root_of_unity(log_n), -1, F.r)
+    ninv = pow(n, -1, F.r)
+    assert coef == [pow(om_inv, p * j, F.r) * ninv % F.r for j in range(5)]
+    with pytest.raises(acg.AcgError) as e:   # beyond the 2-adicity of BN254 Fr
+        acg.qap._check(acg._lib.lib().acg_ntt(ctx_bn._h, d.ctypes.data_as(__import__("ctypes").c_void_p), 29, 0), ctx_bn)
+    assert e.value.code == -6
+
+
+def test_interpolate_columns(acg, ctx_bn):
+    """createPolynomialsFFT's per-wire interpolation (src/QAP.hs:512-525): odd batch counts, padding."""
+    F = O.BN254
+    rnd = random.Random(8)
+    cols = [[rnd.randrange(F.r) for _ in range(ln)] for ln in (1, 2, 3, 5, 8, 13, 16)]
+    polys = acg.create_polynomials_fft(ctx_bn, cols)
+    for col, p in zip(cols, polys):
+        assert p == O.fft_interpolate(F, col + [0] * (16 - len(col)))
+    big = np.stack([acg.to_limbs([rnd.randrange(F.r) for _ in range(1 << 10)]) for _ in range(5)])
+    out = ctx_bn.interpolate_columns(big)
+    for i in range(5):
+        assert (out[i] == CO.ntt(0, big[i], True)).all()
+
+
+@pytest.mark.parametrize("fid,n,delta", [(0, 1000, (0, 0, 0)), (0, 1 << 12, (3, 5, 7)), (1, 3000, (0, 9, 0)), (0, 1, (1, 2, 3))])
+def test_qap_witness_vs_c_oracle(acg, ctxs, fid, n, delta):
+    ctx = ctxs[fid]
+    g, w = acg.synth_r1cs(fid, n, 31 + n)
+    m, dw = ctx.upload_r1cs(g), ctx.upload_witness(w)
+    bufs, ok = ctx.qap_witness(m, dw, delta)
+    ref = oracle_check(fid, g, w, True)
+    N = O.next_pow2(n)
+    pad = lambda v: np.vstack([v, np.zeros((N - n, 4), np.uint64)])
+    a, b, c, h, rok = CO.qap_witness(fid, pad(ref["Aw"]), pad(ref["Bw"]), pad(ref["Cw"]), delta, 8)
+    assert ok and rok
+    for k, r in (("a", a), ("b", b), ("c", c), ("h", h)):
+        assert (bufs[k] == r).all(), k
+    # tampered witness: Nothing
+    wb = w.copy()
+    wb[g.n_cols - 1, 0] ^= np.uint64(1)
+    dw.update(wb)
+    assert ctx.qap_witness(m, dw, delta, want=())[1] is False
+
+
+def test_qap_identity_at_random_point_2_20(acg, ctx_bn):
+    """Full-size property: a(z) * b(z) - c(z) == h(z) * (z^N - 1) at a random z (Schwartz-Zippel), with
+    Horner evaluation in Python big ints over the returned coefficient vectors."""
+    n = 1 << 16
+    F = O.BN254
+    g, w = acg.synth_r1cs(0, n, 5)
+    m, dw = ctx_bn.upload_r1cs(g), ctx_bn.upload_witness(w)
+    bufs, ok = ctx_bn.qap_witness(m, dw, (11, 13, 17))
+    assert ok
+    z = random.Random(1).randrange(F.r)
+    ev = {k: O.p_eval(F, acg.from_limbs(bufs[k]), z) for k in ("a", "b", "c", "h")}
+    assert (ev["a"] * ev["b"] - ev["c"]) % F.r == ev["h"] * (pow(z, n, F.r) - 1) % F.r
+
+
+# ------------------------------------------------------------------------------------------------ K5
+def test_lagrange_golden(acg, ctxs):
+    for case in golden("lagrange.json"):
+        ctx = ctxs[case["field"]]
+        polys, target = acg.create_polynomials(ctx, unhex(case["xs"]), [unhex(y) for y in case["ys"]])
+        assert polys == [unhex(p) for p in case["polys"]]
+        assert target == unhex(case["target"])
+
+
+def test_lagrange_matches_reference_qap_build(acg, ctx_bn):
+    """arithCircuitToQAP (Lagrange build, roots 7,8,9) on the unit-test circuit: target and a column vs KAT-1;
+    on roots of unity it coincides with the FFT build."""
+    F = O.BN254
+    k = golden("kats.json")["kat1"]
+    A = csr_from_json(k["A"])
+    w = unhex(k["w"])
+    aw = O.csr_matvec(F, A, w)
+    polys, target = acg.create_polynomials(ctx_bn, [7, 8, 9], [aw])
+    assert target == unhex(k["target"]) and polys[0] == unhex(k["a"])
+    n = 64
+    om = F.root_of_unity(6)
+    xs = [pow(om, i, F.r) for i in range(n)]
+    rnd = random.Random(6)
+    ys = [rnd.randrange(F.r) for _ in range(n)]
+    polys, target = acg.create_polynomials(ctx_bn, xs, [ys])
+    assert polys[0] == O.fft_interpolate(F, ys) and target == [F.r - 1] + [0] * (n - 1) + [1]
+    with pytest.raises(acg.AcgError):
+        ctx_bn.lagrange([1, 2, 1], [[1, 2, 3]])
+    big_n = 1024
+    xs = rnd.sample(range(1, 1 << 40), big_n)
+    ys = [rnd.randrange(F.r) for _ in range(big_n)]
+    polys, _ = ctx_bn.lagrange(xs, [ys], False)
+    for i in (0, 1, 500, big_n - 1):
+        assert O.p_eval(F, polys[0], xs[i]) == ys[i]

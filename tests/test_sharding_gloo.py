@@ -1,0 +1,88 @@
+"""world_size-2 gloo test of the multi-GPU plumbing: contiguous row shards, one all-reduce of
+the per-shard violated-row count, min-reduction of the first bad row.  On CPU the per-shard count comes
+from the C oracle (the product has no CPU compute path); what is under test is the sharding and the
+reduction, which the GPU path uses unchanged."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as CO
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, seed, tamper, q):
+    import torch
+    import torch.distributed as dist
+    import arithmetic_circuits_b200 as acg
+    from arithmetic_circuits_b200 import sharding
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g, w = acg.synth_r1cs(0, n, seed)
+        for t in tamper:
+            w[t, 0] ^= np.uint64(1)
+        rb, re = sharding.row_shard_balanced([m[0] for m in g.mats], world, rank) if seed % 2 else \
+            sharding.row_shard(g.n_rows, world, rank)
+        # shard-local CSR slices, as acg_r1cs_upload(row_begin, row_end) takes them
+        mats = []
+        for rp, col, val in g.mats:
+            e0, e1 = int(rp[rb]), int(rp[re])
+            mats.append(((rp[rb:re + 1] - rp[rb]).astype(np.uint32), col[e0:e1].copy(), val[e0:e1].copy()))
+        res = CO.r1cs_eval_check(0, re - rb, g.n_cols, mats[0], mats[1], mats[2], w)
+        first = -1 if res["first_bad_row"] < 0 else res["first_bad_row"] + rb
+        t = torch.tensor([res["n_violations"], first], dtype=torch.int64)
+        total, first_bad = sharding.reduce_check_result(t)
+        if rank == 0:
+            q.put((total, first_bad, (rb, re)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tamper,seed", [((), 20260002), ((1025 + 100,), 20260002), ((1025 + 100, 1025 + 900), 3)])
+def test_sharded_check_two_ranks(tamper, seed):
+    import torch.multiprocessing as mp
+    import arithmetic_circuits_b200 as acg
+
+    n, world = 1500, 2
+    g, w = acg.synth_r1cs(0, n, seed)
+    for t in tamper:
+        w[t, 0] ^= np.uint64(1)
+    full = CO.r1cs_eval_check(0, n, g.n_cols, *[(m[0], m[1], m[2]) for m in g.mats], w)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, seed, tamper, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    total, first_bad, shard0 = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert (total, first_bad) == (full["n_violations"], full["first_bad_row"])
+    assert (total == 0) == (len(tamper) == 0)
+    assert shard0[0] == 0 and 0 < shard0[1] < n
+
+
+def test_row_shard_partitions():
+    from arithmetic_circuits_b200 import sharding
+    for n in (0, 1, 7, 1 << 20, (1 << 24) + 3):
+        for world in (1, 2, 4, 8):
+            cuts = [sharding.row_shard(n, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in cuts]
+            assert max(sizes) - min(sizes) <= 1
+    # nnz-balanced: one huge row does not starve the others
+    rp = np.concatenate([[0], np.cumsum([1] * 100 + [10000] + [1] * 100)]).astype(np.uint32)
+    cuts = [sharding.row_shard_balanced([rp, rp, rp], 4, r) for r in range(4)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == 201 and all(cuts[i][1] == cuts[i + 1][0] for i in range(3))
