@@ -25,6 +25,7 @@ struct acg_ctx {
     int device = 0;
     int sm_count = 148;
     int check_kernel = ACG_CHECK_AUTO;
+    int tiled_variant = 0;  // index into kTileGeom
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* d_result = nullptr;  // {n_violations, first_bad_row}
@@ -53,9 +54,12 @@ struct acg_r1cs {
     uint32_t* d_col[3] = {nullptr, nullptr, nullptr};
     fr_t* d_val[3] = {nullptr, nullptr, nullptr};
     DevR1cs dev{};
-    Tile* d_tiles = nullptr;
-    uint32_t n_tiles = 0;
-    std::vector<std::pair<uint32_t, uint32_t>> long_ranges;  // local row ranges too wide for a tile
+    fr_t* d_gval[3] = {nullptr, nullptr, nullptr};  // general-coefficient values only (tiled kernel)
+    // tilings for both geometry variants of the tiled kernel (tiny: 64 bytes per tile)
+    Tile* d_tiles[2] = {nullptr, nullptr};
+    uint16_t* d_glist[2] = {nullptr, nullptr};
+    uint32_t n_tiles[2] = {0, 0};
+    std::vector<std::pair<uint32_t, uint32_t>> long_ranges[2];  // local row ranges too wide for a tile
 };
 
 struct acg_vec {
@@ -183,23 +187,32 @@ int upload_canonical(acg_ctx* ctx, fr_t* d, const uint64_t* host, uint64_t n) {
     return ACG_OK;
 }
 
-// Greedy nnz-balanced tiling in groups of 4 rows (TMA needs 16-byte aligned row-pointer slices).
-void build_tiles(const uint32_t* rp[3], uint32_t n_local, std::vector<Tile>& tiles,
-                 std::vector<std::pair<uint32_t, uint32_t>>& long_ranges) {
+// Greedy tiling in groups of 4 rows (TMA needs 16-byte aligned row-pointer slices): a tile holds at most
+// geom.threads rows, geom.pool entries (A+B+C) and geom.max_gen general-coefficient entries.
+// gcum[k][r] = number of general entries of matrix k in local rows < r.
+void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t* gcum[3], uint32_t n_local,
+                 std::vector<Tile>& tiles, std::vector<std::pair<uint32_t, uint32_t>>& long_ranges) {
     uint32_t r = 0;
     while (r < n_local) {
         Tile t{};
         t.row0 = r;
-        for (int k = 0; k < 3; ++k) t.e0[k] = rp[k][r];
+        uint32_t g_base = 0;
+        for (int k = 0; k < 3; ++k) {
+            t.e0[k] = rp[k][r];
+            g_base += gcum[k][r];
+        }
         uint32_t end = r;
-        while (end < n_local && end - r < (uint32_t)kTileRows) {
+        while (end < n_local && end - r < geom.threads) {
             const uint32_t g_end = std::min(end + 4u, n_local);
-            uint64_t tot = 0;
-            for (int k = 0; k < 3; ++k) tot += (uint64_t)rp[k][g_end] - t.e0[k];
-            if (tot > (uint64_t)kTilePoolEntries) break;
+            uint64_t tot = 0, gen = 0;
+            for (int k = 0; k < 3; ++k) {
+                tot += (uint64_t)rp[k][g_end] - t.e0[k];
+                gen += gcum[k][g_end];
+            }
+            if (tot > (uint64_t)geom.pool || gen - g_base > (uint64_t)geom.max_gen) break;
             end = g_end;
         }
-        if (end == r) {  // a single 4-row group does not fit: row-wise kernel handles it
+        if (end == r) {  // a single 4-row group does not fit: the row-wise kernel handles it
             const uint32_t g_end = std::min(r + 4u, n_local);
             if (!long_ranges.empty() && long_ranges.back().second == r)
                 long_ranges.back().second = g_end;
@@ -209,7 +222,11 @@ void build_tiles(const uint32_t* rp[3], uint32_t n_local, std::vector<Tile>& til
             continue;
         }
         t.nrows = end - r;
-        for (int k = 0; k < 3; ++k) t.ne[k] = rp[k][end] - t.e0[k];
+        for (int k = 0; k < 3; ++k) {
+            t.ne[k] = rp[k][end] - t.e0[k];
+            t.gv0[k] = gcum[k][r];
+            t.ngv[k] = gcum[k][end] - gcum[k][r];
+        }
         tiles.push_back(t);
         r = end;
     }
@@ -236,16 +253,19 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long 
     }
     const bool prof = 2 * (ctx->prof_used + 1) <= ctx->prof_ev.size();
     if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
-    if (m->n_tiles) {
-        CU(ctx, launch_r1cs_tiled(ctx->field, m->dev, w, m->d_tiles, m->n_tiles, m->row_begin, d_result, Aw, Bw, Cw,
-                                  ctx->sm_count, s));
+    const int v = ctx->tiled_variant;
+    DevR1cs dev = m->dev;
+    dev.glist = m->d_glist[v];
+    if (m->n_tiles[v]) {
+        CU(ctx, launch_r1cs_tiled(ctx->field, dev, w, m->d_tiles[v], m->n_tiles[v], m->row_begin, d_result, Aw, Bw, Cw,
+                                  ctx->sm_count, v, s));
         ++*launches;
     }
     if (prof) {
         CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], s));
         ++ctx->prof_used;
     }
-    for (const auto& lr : m->long_ranges) {
+    for (const auto& lr : m->long_ranges[v]) {
         CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, lr.first, lr.second, m->row_begin, d_result, Aw, Bw, Cw, s));
         ++*launches;
     }
@@ -307,6 +327,13 @@ int acg_ctx_create(int field_id, int device, acg_ctx** out) {
         return ACG_ERR_NO_DEVICE;  // kernels are built for sm_100a only
     }
     ctx->sm_count = prop.multiProcessorCount;
+    {   // keep stream-ordered scratch (one-shot path) cached in the pool instead of returning it at every sync
+        cudaMemPool_t mp;
+        if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
         return bail(e, "cudaStreamCreate");
     for (auto& ev : ctx->ev)
@@ -344,6 +371,12 @@ void acg_ctx_destroy(acg_ctx* ctx) {
 int acg_ctx_set_check_kernel(acg_ctx* ctx, int which) {
     if (!ctx || which < ACG_CHECK_AUTO || which > ACG_CHECK_TILED) return ACG_ERR_BAD_ARG;
     ctx->check_kernel = which;
+    return ACG_OK;
+}
+
+int acg_ctx_set_tiled_variant(acg_ctx* ctx, int variant) {
+    if (!ctx || (variant != 0 && variant != 1)) return ACG_ERR_BAD_ARG;
+    ctx->tiled_variant = variant;
     return ACG_OK;
 }
 
@@ -420,7 +453,11 @@ void acg_r1cs_free(acg_r1cs* m) {
         cudaFree(m->d_col[k]);
         cudaFree(m->d_val[k]);
     }
-    cudaFree(m->d_tiles);
+    for (int k = 0; k < 3; ++k) cudaFree(m->d_gval[k]);
+    for (int v = 0; v < 2; ++v) {
+        cudaFree(m->d_tiles[v]);
+        cudaFree(m->d_glist[v]);
+    }
     delete m;
 }
 
@@ -430,10 +467,17 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     if (rc) return rc;
     if (!out || !A || !B || !C || row_begin > row_end || row_end > n_rows || n_cols == 0)
         return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: bad argument");
+    if (n_cols > kColMask) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_r1cs_upload: more than 2^30 witness columns");
     *out = nullptr;
     const acg_csr* src[3] = {A, B, C};
     const uint32_t n_local = row_end - row_begin;
-    // host-side structural validation of the uploaded slice
+    // canonical 1 and r-1: the two coefficient values with a multiplication-free fast path
+    uint64_t modulus[4], minus_one[4];
+    acg_field_constants(ctx->field, modulus, nullptr, nullptr, nullptr, nullptr);
+    std::memcpy(minus_one, modulus, 32);
+    minus_one[0] -= 1;  // r is odd
+    // host pass over the uploaded slice: structural validation, coefficient tags, per-row general counts
+    std::vector<uint32_t> local_rp[3], tagged_col[3], gcum[3];
     for (int k = 0; k < 3; ++k) {
         const acg_csr* M = src[k];
         if (!M->rowptr || (M->nnz && (!M->col || !M->val)) || M->nnz > 0xFFFFFFF0ull)
@@ -444,8 +488,28 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
                 return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: rowptr not monotone");
         const uint32_t e0 = M->rowptr[row_begin], e1 = M->rowptr[row_end];
         if (e1 > M->nnz) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: rowptr exceeds nnz");
-        uint32_t bad = 0;
-        for (uint32_t e = e0; e < e1; ++e) bad |= (M->col[e] >= n_cols);
+        local_rp[k].resize((size_t)n_local + 1);
+        gcum[k].resize((size_t)n_local + 1);
+        tagged_col[k].resize((size_t)(e1 - e0));
+        uint32_t bad = 0, gen = 0;
+        for (uint32_t r = 0; r < n_local; ++r) {
+            local_rp[k][r] = M->rowptr[row_begin + r] - e0;
+            gcum[k][r] = gen;
+            for (uint32_t e = M->rowptr[row_begin + r]; e < M->rowptr[row_begin + r + 1]; ++e) {
+                const uint32_t c = M->col[e];
+                bad |= (c >= n_cols);
+                const uint64_t* v = M->val + 4ull * e;
+                uint32_t tag = kTagGeneral;
+                if (v[0] == 1 && (v[1] | v[2] | v[3]) == 0)
+                    tag = kTagPlusOne;
+                else if (v[0] == minus_one[0] && v[1] == minus_one[1] && v[2] == minus_one[2] && v[3] == minus_one[3])
+                    tag = kTagMinusOne;
+                gen += (tag == kTagGeneral);
+                tagged_col[k][e - e0] = (c & kColMask) | (tag << 30);
+            }
+        }
+        local_rp[k][n_local] = e1 - e0;
+        gcum[k][n_local] = gen;
         if (bad) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: column index >= n_cols");
     }
     acg_r1cs* m = new (std::nothrow) acg_r1cs();
@@ -463,16 +527,14 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     } guard{m};
 
     CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    std::vector<uint32_t> local_rp[3];
     uint32_t launches = 0;
+    std::vector<uint64_t> gen_vals[3];  // must outlive the asynchronous copies below
     CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
     for (int k = 0; k < 3; ++k) {
         const acg_csr* M = src[k];
-        const uint32_t e0 = M->rowptr[row_begin], e1 = M->rowptr[row_end];
-        const uint64_t cnt = e1 - e0;
+        const uint32_t e0 = M->rowptr[row_begin];
+        const uint64_t cnt = tagged_col[k].size();
         m->nnz[k] = cnt;
-        local_rp[k].resize((size_t)n_local + 1);
-        for (uint32_t r = 0; r <= n_local; ++r) local_rp[k][r] = M->rowptr[row_begin + r] - e0;
         // pads: TMA slices are rounded up to 16 bytes and may read a few elements past the end
         CU(ctx, cudaMalloc(&m->d_rowptr[k], ((size_t)n_local + 1 + 8) * sizeof(uint32_t)));
         CU(ctx, cudaMalloc(&m->d_col[k], (size_t)(cnt + 8) * sizeof(uint32_t)));
@@ -482,27 +544,67 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
         CU(ctx, cudaMemcpyAsync(m->d_rowptr[k], local_rp[k].data(), ((size_t)n_local + 1) * sizeof(uint32_t),
                                 cudaMemcpyHostToDevice, ctx->stream));
         if (cnt) {
-            CU(ctx, cudaMemcpyAsync(m->d_col[k], M->col + e0, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice,
+            CU(ctx, cudaMemcpyAsync(m->d_col[k], tagged_col[k].data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                     ctx->stream));
             CU(ctx, cudaMemcpyAsync(m->d_val[k], M->val + 4ull * e0, cnt * sizeof(fr_t), cudaMemcpyHostToDevice,
                                     ctx->stream));
             CU(ctx, launch_to_mont(ctx->field, m->d_val[k], cnt, ctx->d_flag, ctx->stream));
             ++launches;
         }
+        // compact copy of the general-coefficient values, in entry order
+        const uint32_t n_gen = gcum[k][n_local];
+        gen_vals[k].resize(4ull * n_gen + 4);
+        {
+            uint64_t* dst = gen_vals[k].data();
+            for (uint64_t e = 0; e < cnt; ++e)
+                if ((tagged_col[k][e] >> 30) == kTagGeneral) {
+                    std::memcpy(dst, M->val + 4ull * (e0 + e), 32);
+                    dst += 4;
+                }
+        }
+        CU(ctx, cudaMalloc(&m->d_gval[k], ((size_t)n_gen + 1) * sizeof(fr_t)));
+        if (n_gen) {
+            CU(ctx, cudaMemcpyAsync(m->d_gval[k], gen_vals[k].data(), (size_t)n_gen * sizeof(fr_t),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, launch_to_mont(ctx->field, m->d_gval[k], n_gen, ctx->d_flag, ctx->stream));
+            ++launches;
+        }
         m->dev.m[k].rowptr = m->d_rowptr[k];
         m->dev.m[k].col = m->d_col[k];
         m->dev.m[k].val = m->d_val[k];
+        m->dev.m[k].gval = m->d_gval[k];
     }
-    // tiles
-    std::vector<Tile> tiles;
+    // tiles and their static lists of general entries (pool indices, uint16)
     const uint32_t* rp[3] = {local_rp[0].data(), local_rp[1].data(), local_rp[2].data()};
-    build_tiles(rp, n_local, tiles, m->long_ranges);
-    m->n_tiles = (uint32_t)tiles.size();
-    if (m->n_tiles) {
-        CU(ctx, cudaMalloc(&m->d_tiles, tiles.size() * sizeof(Tile)));
-        CU(ctx, cudaMemcpyAsync(m->d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice,
-                                ctx->stream));
+    const uint32_t* gc[3] = {gcum[0].data(), gcum[1].data(), gcum[2].data()};
+    std::vector<Tile> tiles[2];
+    std::vector<uint16_t> glist[2];
+    for (int v = 0; v < 2; ++v) {
+        build_tiles(kTileGeom[v], rp, gc, n_local, tiles[v], m->long_ranges[v]);
+        for (Tile& t : tiles[v]) {
+            t.g0 = (uint32_t)glist[v].size();
+            uint32_t vstart = 0;
+            for (int k = 0; k < 3; ++k) {
+                for (uint32_t e = 0; e < t.ne[k]; ++e)
+                    if ((tagged_col[k][t.e0[k] + e] >> 30) == kTagGeneral) glist[v].push_back((uint16_t)(vstart + e));
+                vstart += t.ne[k];
+            }
+            t.ng = (uint32_t)glist[v].size() - t.g0;
+            while (glist[v].size() % 8) glist[v].push_back(0);  // keep every slice 16-byte aligned
+        }
+        for (int i = 0; i < 8; ++i) glist[v].push_back(0);
+        m->n_tiles[v] = (uint32_t)tiles[v].size();
+        if (m->n_tiles[v]) {
+            CU(ctx, cudaMalloc(&m->d_tiles[v], tiles[v].size() * sizeof(Tile)));
+            CU(ctx, cudaMemcpyAsync(m->d_tiles[v], tiles[v].data(), tiles[v].size() * sizeof(Tile),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CU(ctx, cudaMalloc(&m->d_glist[v], glist[v].size() * sizeof(uint16_t)));
+        CU(ctx, cudaMemcpyAsync(m->d_glist[v], glist[v].data(), glist[v].size() * sizeof(uint16_t),
+                                cudaMemcpyHostToDevice, ctx->stream));
     }
+    m->dev.glist = m->d_glist[0];
+    m->dev.tagged = 1;
     CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -602,28 +704,85 @@ int acg_r1cs_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* 
     return ACG_OK;
 }
 
+// One-shot path: no host-side preprocessing (a single check cannot amortise it).  Plain copies from the
+// caller's buffers on the context stream, validation + Montgomery conversion + row-wise check on the
+// device, stream-ordered allocations.
 int acg_r1cs_check_host(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_csr* A, const acg_csr* B,
                         const acg_csr* C, const uint64_t* w, uint64_t* n_violations, uint64_t* first_bad_row) {
-    acg_r1cs* m = nullptr;
-    acg_vec* v = nullptr;
-    int rc = acg_r1cs_upload(ctx, n_rows, n_cols, A, B, C, 0, n_rows, &m);
+    int rc = activate(ctx);
     if (rc) return rc;
-    const float h2d_m = ctx->timing.h2d_ms;
-    const uint32_t l0 = ctx->timing.kernel_launches;
-    rc = acg_witness_upload(ctx, w, n_cols, &v);
-    if (rc) {
-        acg_r1cs_free(m);
-        return rc;
+    if (!A || !B || !C || !w || n_cols == 0 || n_cols > kColMask)
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_check_host: bad argument");
+    const acg_csr* src[3] = {A, B, C};
+    for (int k = 0; k < 3; ++k)
+        if (!src[k]->rowptr || (src[k]->nnz && (!src[k]->col || !src[k]->val)) || src[k]->nnz > 0xFFFFFFF0ull)
+            return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_check_host: null array or nnz too large");
+    cudaStream_t s = ctx->stream;
+    struct Pool {  // stream-ordered scratch, released in reverse order on every exit path
+        cudaStream_t s;
+        std::vector<void*> ptrs;
+        ~Pool() {
+            for (auto it = ptrs.rbegin(); it != ptrs.rend(); ++it) cudaFreeAsync(*it, s);
+        }
+        cudaError_t get(void** p, size_t bytes) {
+            cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, s);
+            if (e == cudaSuccess) ptrs.push_back(*p);
+            return e;
+        }
+    } pool{s, {}};
+    DevR1cs dev{};
+    uint32_t launches = 0;
+    fr_t* d_w = nullptr;
+    CU(ctx, cudaEventRecord(ctx->ev[0], s));
+    CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
+    for (int k = 0; k < 3; ++k) {
+        const acg_csr* M = src[k];
+        uint32_t *d_rp = nullptr, *d_col = nullptr;
+        fr_t* d_val = nullptr;
+        CU(ctx, pool.get((void**)&d_rp, ((size_t)n_rows + 1) * sizeof(uint32_t)));
+        CU(ctx, pool.get((void**)&d_col, (size_t)M->nnz * sizeof(uint32_t)));
+        CU(ctx, pool.get((void**)&d_val, (size_t)M->nnz * sizeof(fr_t)));
+        CU(ctx, cudaMemcpyAsync(d_rp, M->rowptr, ((size_t)n_rows + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        if (M->nnz) {
+            CU(ctx, cudaMemcpyAsync(d_col, M->col, (size_t)M->nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            CU(ctx, cudaMemcpyAsync(d_val, M->val, (size_t)M->nnz * sizeof(fr_t), cudaMemcpyHostToDevice, s));
+            CU(ctx, launch_to_mont(ctx->field, d_val, M->nnz, ctx->d_flag, s));
+            ++launches;
+        }
+        CU(ctx, launch_validate_csr(d_rp, d_col, n_rows, M->nnz, n_cols, ctx->d_flag, s));
+        ++launches;
+        dev.m[k].rowptr = d_rp;
+        dev.m[k].col = d_col;
+        dev.m[k].val = d_val;
     }
-    const float h2d_w = ctx->timing.h2d_ms;
-    rc = acg_r1cs_check(ctx, m, v, n_violations, first_bad_row);
-    if (rc == ACG_OK) {
-        ctx->timing.h2d_ms = h2d_m + h2d_w;
-        ctx->timing.kernel_launches += l0 + 1;
+    CU(ctx, pool.get((void**)&d_w, (size_t)n_cols * sizeof(fr_t)));
+    CU(ctx, cudaMemcpyAsync(d_w, w, (size_t)n_cols * sizeof(fr_t), cudaMemcpyHostToDevice, s));
+    CU(ctx, launch_to_mont(ctx->field, d_w, n_cols, ctx->d_flag, s));
+    ++launches;
+    // the check must not run on unvalidated indices: read the flag back first
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaEventRecord(ctx->ev[1], s));
+    CU(ctx, cudaStreamSynchronize(s));
+    if (*ctx->h_flag & 2) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_check_host: malformed CSR (rowptr / column index)");
+    if (*ctx->h_flag & 1) return fail(ctx, ACG_ERR_NON_CANONICAL, "acg_r1cs_check_host: field element >= modulus");
+    dev.glist = nullptr;
+    dev.tagged = 0;
+    CU(ctx, launch_init_result(ctx->d_result, s));
+    ++launches;
+    if (n_rows) {
+        CU(ctx, launch_r1cs_rowwise(ctx->field, dev, d_w, 0, n_rows, 0, ctx->d_result, nullptr, nullptr, nullptr, s));
+        ++launches;
     }
-    acg_vec_free(v);
-    acg_r1cs_free(m);
-    return rc;
+    CU(ctx, cudaEventRecord(ctx->ev[2], s));
+    CU(ctx, cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaEventRecord(ctx->ev[3], s));
+    CU(ctx, cudaStreamSynchronize(s));
+    ctx->launches += launches;
+    ctx->timing = acg_timing{elapsed(ctx->ev[0], ctx->ev[1]), elapsed(ctx->ev[1], ctx->ev[2]),
+                             elapsed(ctx->ev[2], ctx->ev[3]), launches, 0};
+    if (n_violations) *n_violations = ctx->h_result[0];
+    if (first_bad_row) *first_bad_row = ctx->h_result[1];
+    return ACG_OK;
 }
 
 int acg_r1cs_eval(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* Aw, uint64_t* Bw, uint64_t* Cw) {
@@ -819,13 +978,13 @@ static int qap_witness_impl(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, c
         if ((rc = download_canonical(ctx, scratch.as<fr_t>(), N, outs[k]))) return rc;
         ++launches;
     }
-    if (log_n > 0) {
-        if (any_delta) {  // keep a and b coefficients for h += d1*b + d2*a
-            for (int k = 0; k < 2; ++k) {
-                CU(ctx, coef[k].alloc(N * sizeof(fr_t)));
-                CU(ctx, cudaMemcpyAsync(coef[k].p, ev[k].p, N * sizeof(fr_t), cudaMemcpyDeviceToDevice, s));
-            }
+    if (any_delta) {  // keep a and b coefficients for h += d1*b + d2*a
+        for (int k = 0; k < 2; ++k) {
+            CU(ctx, coef[k].alloc(N * sizeof(fr_t)));
+            CU(ctx, cudaMemcpyAsync(coef[k].p, ev[k].p, N * sizeof(fr_t), cudaMemcpyDeviceToDevice, s));
         }
+    }
+    if (log_n > 0) {
         // coset evaluation g * w^i: scale coefficient i by g^i, forward DIF (bit-reversed order out)
         for (int k = 0; k < 3; ++k) {
             CU(ctx, launch_scale_by_powers(ctx->field, ev[k].as<fr_t>(), N, ct->hi, ct->lo, ct->lo_bits, fr_one<P>(),
@@ -845,10 +1004,10 @@ static int qap_witness_impl(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, c
         CU(ctx, launch_scale_by_powers(ctx->field, hbuf.as<fr_t>(), N, ct->ihi, ct->ilo, ct->lo_bits, fr_one<P>(),
                                        false, false, log_n, s));
         ++launches;
-        if (any_delta) {
-            CU(ctx, launch_axpy2(ctx->field, hbuf.as<fr_t>(), coef[0].as<fr_t>(), coef[1].as<fr_t>(), d[1], d[0], N, s));
-            ++launches;
-        }
+    }
+    if (any_delta) {
+        CU(ctx, launch_axpy2(ctx->field, hbuf.as<fr_t>(), coef[0].as<fr_t>(), coef[1].as<fr_t>(), d[1], d[0], N, s));
+        ++launches;
     }
     CU(ctx, cudaEventRecord(ctx->ev[2], s));
     if (h_out) {

@@ -8,30 +8,50 @@
 
 namespace acg {
 
+// Column words carry a 2-bit coefficient tag in bits 31:30 when the system was preprocessed at upload
+// (DevR1cs::tagged): the sparsity pattern and the coefficients are static, so classifying them once is
+// free for every later check.
+constexpr uint32_t kColMask = 0x3FFFFFFFu;
+constexpr uint32_t kTagPlusOne = 0u;   // coefficient == 1
+constexpr uint32_t kTagMinusOne = 1u;  // coefficient == r - 1
+constexpr uint32_t kTagGeneral = 2u;
+
 struct DevCsr {
     const uint32_t* rowptr;  // shard-local rows + 1 entries, rebased to 0, padded by >= 8
-    const uint32_t* col;     // padded by >= 8
-    const fr_t* val;         // Montgomery form
+    const uint32_t* col;     // padded by >= 8; tagged when DevR1cs::tagged
+    const fr_t* val;         // Montgomery form, one per entry (row-wise kernel)
+    const fr_t* gval;        // Montgomery form, general-coefficient entries only, in entry order (tiled kernel)
 };
 struct DevR1cs {
-    DevCsr m[3];  // A, B, C
+    DevCsr m[3];             // A, B, C
+    const uint16_t* glist;   // per-tile lists of general-coefficient entries (pool indices), or null
+    uint32_t tagged;
 };
 
-// One unit of work of the tiled check kernel: rows [row0, row0+nrows) and their entry ranges.
+// One unit of work of the tiled check kernel: rows [row0, row0+nrows), their entry ranges in A, B, C,
+// the ranges of their general-coefficient values, and the slice [g0, g0+ng) of the general-entry list.
 struct alignas(16) Tile {
     uint32_t row0;
     uint32_t nrows;
     uint32_t e0[3];
     uint32_t ne[3];
+    uint32_t gv0[3];  // first general value of the tile in m[k].gval
+    uint32_t ngv[3];  // number of general values per matrix (sum == ng)
+    uint32_t g0;      // multiple of 8 (16-byte aligned uint16 slice)
+    uint32_t ng;
 };
-static_assert(sizeof(Tile) == 32, "Tile must be 32 bytes");
+static_assert(sizeof(Tile) == 64, "Tile must be 64 bytes");
 
-// tiled kernel geometry (see DESIGN.md "K2")
-constexpr int kTileRows = 256;        // consumer threads == max rows per tile
-constexpr int kTilePoolEntries = 1344;  // A+B+C entries staged per tile
-constexpr int kTileStages = 2;
-constexpr int kTiledThreads = kTileRows + 32;  // + one producer warp
-constexpr int kTiledCtasPerSm = 2;
+// Tiled kernel geometry (see DESIGN.md "K2").  Two variants, chosen at upload time:
+//   variant 0: 128-thread CTAs, tiles of <= 128 rows / 640 entries / 176 general entries, 7 CTAs per SM
+//   variant 1: 256-thread CTAs, tiles of <= 256 rows / 1344 entries / 384 general entries, 3 CTAs per SM
+struct TileGeometry {
+    uint32_t threads;   // == max rows per tile
+    uint32_t pool;      // A+B+C entries staged per tile
+    uint32_t max_gen;   // general-coefficient entries per tile
+    uint32_t ctas_per_sm;
+};
+constexpr TileGeometry kTileGeom[2] = {{128, 640, 176, 7}, {256, 1344, 384, 3}};
 
 cudaError_t launch_to_mont(int field, fr_t* v, uint64_t n, int* d_bad_flag, cudaStream_t s);
 cudaError_t launch_from_mont(int field, fr_t* v, uint64_t n, cudaStream_t s);
@@ -42,11 +62,14 @@ cudaError_t launch_init_result(unsigned long long* d_result, cudaStream_t s);
 cudaError_t launch_r1cs_rowwise(int field, const DevR1cs& m, const fr_t* w, uint32_t row_lo, uint32_t row_hi,
                                 uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
                                 cudaStream_t s);
-// TMA-staged tile kernel over a list of tiles built at upload time
+// TMA-staged tile kernel over a list of tiles built at upload time for geometry `variant` (requires m.tagged).
 cudaError_t launch_r1cs_tiled(int field, const DevR1cs& m, const fr_t* w, const Tile* d_tiles, uint32_t n_tiles,
                               uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
-                              int sm_count, cudaStream_t s);
-size_t r1cs_tiled_smem_bytes();
+                              int sm_count, int variant, cudaStream_t s);
+size_t r1cs_tiled_smem_bytes(int variant);
+// structural validation on the device: rowptr monotone and ending at nnz, col < n_cols.  Sets *d_flag |= 2.
+cudaError_t launch_validate_csr(const uint32_t* rowptr, const uint32_t* col, uint32_t n_rows, uint64_t nnz,
+                                uint32_t n_cols, int* d_flag, cudaStream_t s);
 
 // NTT (K3).  A plan owns the twiddle tables of one (field, log_n, direction).
 struct NttPlan;

@@ -6,18 +6,23 @@
 // the test  a*b*R^-1 == c  is exactly  (A.w)(B.w) == (C.w)  on canonical residues.
 //
 // Two kernels compute the same thing:
-//   k_r1cs_rowwise : thread per row, direct global loads.  Simple; also the path for rows too long to
-//                    stage in shared memory (Split gates wider than a tile).
-//   k_r1cs_tiled   : persistent CTAs; a producer warp streams each tile's CSR slices (values, columns,
-//                    row pointers of A, B and C) into shared memory with TMA bulk copies
-//                    (cp.async.bulk + mbarrier, SASS UBLKCP) through a 2-stage ring; 256 consumer
-//                    threads then (P1) turn every +-1-coefficient entry into its term +-w[col] in place,
-//                    thread-per-ENTRY so the witness gathers are independent and the work is balanced,
-//                    and queue the general-coefficient entries, (P2) run the queued 256-bit Montgomery
-//                    products densely -- one entry per lane, no divergence between coefficient kinds --
-//                    and (P3) sum each row's terms thread-per-row and test a*b == c.
-//                    HBM traffic is exactly one pass over the CSR arrays; the witness is gathered
-//                    through L2.
+//   k_r1cs_rowwise : thread per row, direct global loads.  Used for one-shot checks (no preprocessing)
+//                    and for rows too long to stage in shared memory.
+//   k_r1cs_tiled   : persistent CTAs over tiles of <= 128 (or 256) rows built at upload time.  Per tile:
+//                    (load) one thread issues TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) of
+//                           the tile's slices -- tagged columns and row pointers of A, B, C, the values
+//                           of the general-coefficient entries and their static index list -- into
+//                           shared memory; several CTAs per SM hide each other's load latency;
+//                    (P1)   thread per ENTRY: the witness element of every entry is gathered with
+//                           cp.async (LDGSTS, no register staging, all gathers of the tile in flight at
+//                           once) into two 16-byte planes (bank-conflict-free 128-bit accesses);
+//                    (P2)   one lane per general entry: the 256-bit Montgomery product, in place --
+//                           dense, no divergence between coefficient kinds;
+//                    (P3)   thread per row: signed sum of the row's terms, then the test a*b == c.
+//                    The coefficient classification (+1 / -1 / general) lives in two tag bits of the
+//                    column word and is computed once at upload: the sparsity pattern is static, and the
+//                    32-byte encodings of +-1 never need to be re-read.  HBM traffic per check is one
+//                    pass over columns, row pointers and general values; the witness is gathered via L2.
 #include "dev.cuh"
 #include "kernels.h"
 
@@ -68,15 +73,19 @@ __global__ void k_init_result(unsigned long long* r) {
 // row-wise kernel
 // ------------------------------------------------------------------------------------------------
 template <class P>
-__device__ __forceinline__ fr_t row_dot(const DevCsr& M, uint32_t row, const fr_t* __restrict__ w) {
+__device__ __forceinline__ fr_t row_dot(const DevCsr& M, uint32_t row, const fr_t* __restrict__ w, bool tagged) {
     fr_t acc = fr_zero<P>();
     const uint32_t s = M.rowptr[row], e = M.rowptr[row + 1];
     for (uint32_t k = s; k < e; ++k) {
-        const fr_t v = M.val[k];
-        const fr_t x = w[M.col[k]];
-        if (fr_is_one<P>(v)) {
+        const uint32_t c = M.col[k];
+        const fr_t x = w[c & kColMask];
+        uint32_t tag = c >> 30;
+        fr_t v;
+        if (!tagged || tag == kTagGeneral) v = M.val[k];
+        if (!tagged) tag = fr_is_one<P>(v) ? kTagPlusOne : (fr_is_minus_one<P>(v) ? kTagMinusOne : kTagGeneral);
+        if (tag == kTagPlusOne) {
             acc = fr_add<P>(acc, x);
-        } else if (fr_is_minus_one<P>(v)) {
+        } else if (tag == kTagMinusOne) {
             acc = fr_sub<P>(acc, x);
         } else {
             acc = fr_add<P>(acc, fr_mul<P>(v, x));
@@ -98,9 +107,9 @@ __global__ void __launch_bounds__(256) k_r1cs_rowwise(DevR1cs m, const fr_t* __r
         const uint32_t row = row_lo + g * 32u + lane_id();
         bool bad = false;
         if (row < row_hi) {
-            const fr_t a = row_dot<P>(m.m[0], row, w);
-            const fr_t b = row_dot<P>(m.m[1], row, w);
-            const fr_t c = row_dot<P>(m.m[2], row, w);
+            const fr_t a = row_dot<P>(m.m[0], row, w, m.tagged != 0);
+            const fr_t b = row_dot<P>(m.m[1], row, w, m.tagged != 0);
+            const fr_t c = row_dot<P>(m.m[2], row, w, m.tagged != 0);
             if (EMIT) {
                 if (Aw) Aw[row] = a;
                 if (Bw) Bw[row] = b;
@@ -114,185 +123,189 @@ __global__ void __launch_bounds__(256) k_r1cs_rowwise(DevR1cs m, const fr_t* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+// structural validation (one-shot path: the host does not walk the arrays)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_validate_csr(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, uint32_t n_rows,
+                               uint64_t nnz, uint32_t n_cols, int* __restrict__ flag) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t t0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    bool bad = false;
+    for (uint64_t r = t0; r < n_rows; r += stride) bad |= rowptr[r] > rowptr[r + 1];
+    if (t0 == 0) bad |= rowptr[0] != 0u || (uint64_t)rowptr[n_rows] != nnz;
+    for (uint64_t e = t0; e < nnz; e += stride) bad |= col[e] >= n_cols;
+    if (bad) atomicOr(flag, 2);
+}
+
+// ------------------------------------------------------------------------------------------------
 // tiled kernel
 // ------------------------------------------------------------------------------------------------
 namespace tiled {
-constexpr uint32_t kConsumers = kTileRows;                 // 256
-constexpr uint32_t kPool = kTilePoolEntries;               // entries
-constexpr uint32_t kColsCap = kPool + 24;                  // 3 chunks, each <= ne + 6 after 16-byte alignment
-constexpr uint32_t kRpCap = kTileRows + 8;                 // per matrix, (nrows + 1) rounded up to 4
-constexpr uint32_t kOffVals = 0;
-constexpr uint32_t kOffCols = kOffVals + kPool * 32;
-constexpr uint32_t kOffRp = kOffCols + kColsCap * 4;
-constexpr uint32_t kOffWork = kOffRp + 3 * kRpCap * 4;
-constexpr uint32_t kOffDesc = kOffWork + kPool * 2;
-constexpr uint32_t kStageBytes = ((kOffDesc + 32 + 127) / 128) * 128;
-static_assert(kOffCols % 16 == 0 && kOffRp % 16 == 0 && kOffWork % 16 == 0 && kOffDesc % 16 == 0, "align");
-static_assert((kRpCap * 4) % 16 == 0, "align");
-constexpr uint32_t kUnroll = 3;
+constexpr uint32_t align_up(uint32_t x, uint32_t a) {
+    return (x + a - 1) / a * a;
+}
+// shared-memory layout of one CTA for geometry variant V
+template <int V>
+struct Cfg {
+    static constexpr uint32_t kThreads = kTileGeom[V].threads;
+    static constexpr uint32_t kPool = kTileGeom[V].pool;
+    static constexpr uint32_t kMaxGen = kTileGeom[V].max_gen;
+    static constexpr uint32_t kCtasPerSm = kTileGeom[V].ctas_per_sm;
+    static constexpr uint32_t kColsCap = kPool + 24;   // 3 chunks, each <= ne + 6 after 16-byte alignment
+    static constexpr uint32_t kRpCap = kThreads + 8;   // per matrix, (nrows + 1) rounded up to 4
+    // gathered witness terms, later the per-entry products: two 16-byte planes so that 128-bit accesses of
+    // neighbouring lanes fall on distinct banks
+    static constexpr uint32_t kOffLo = 0;
+    static constexpr uint32_t kOffHi = kPool * 16;
+    static constexpr uint32_t kOffCols = kPool * 32;
+    static constexpr uint32_t kOffRp = kOffCols + kColsCap * 4;
+    static constexpr uint32_t kOffGval = align_up(kOffRp + 3 * kRpCap * 4, 32);
+    static constexpr uint32_t kOffGlist = kOffGval + kMaxGen * 32;
+    static constexpr uint32_t kOffDesc = align_up(kOffGlist + kMaxGen * 2, 16);
+    static constexpr uint32_t kBytes = align_up(kOffDesc + 64, 128);
+    static_assert(kOffCols % 16 == 0 && kOffRp % 16 == 0 && kOffGlist % 16 == 0 && (kRpCap * 4) % 16 == 0, "align");
+};
 
 __device__ __forceinline__ uint32_t round_up4(uint32_t x) {
     return (x + 3u) & ~3u;
 }
-}  // namespace tiled
-
-size_t r1cs_tiled_smem_bytes() {
-    return (size_t)tiled::kStageBytes * kTileStages;
+__device__ __forceinline__ uint32_t round_up8(uint32_t x) {
+    return (x + 7u) & ~7u;
+}
+// 2 x 16-byte asynchronous gather global -> shared (LDGSTS), no register staging
+__device__ __forceinline__ void cp_async_fr_planes(uint4* lo, uint4* hi, const fr_t* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lo)), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(hi)),
+                 "l"(reinterpret_cast<const uint8_t*>(gmem_src) + 16)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+__device__ __forceinline__ fr_t load_planes(const uint4* lo, const uint4* hi, uint32_t i) {
+    const uint4 a = lo[i], b = hi[i];
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void store_planes(uint4* lo, uint4* hi, uint32_t i, const fr_t& v) {
+    lo[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    hi[i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-template <class P, bool EMIT>
-__global__ void __launch_bounds__(kTiledThreads, kTiledCtasPerSm)
+// one thread: stage tile `tile` into `sb`, completion on `bar`
+template <int V>
+__device__ __forceinline__ void issue_tile_load(const DevR1cs& m, const Tile* __restrict__ tiles, uint32_t tile,
+                                                uint8_t* sb, uint64_t* bar) {
+    using C = Cfg<V>;
+    const Tile t = tiles[tile];
+    *reinterpret_cast<Tile*>(sb + C::kOffDesc) = t;
+    const uint32_t rp_bytes = round_up4(t.nrows + 1u) * 4u;
+    const uint32_t gl_bytes = round_up8(t.ng) * 2u;
+    uint32_t total = 3u * rp_bytes + gl_bytes + t.ng * 32u;
+    uint32_t cb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        cb[k] = t.ne[k] ? round_up4((t.e0[k] & 3u) + t.ne[k]) * 4u : 0u;
+        total += cb[k];
+    }
+    mbar_arrive_expect_tx(bar, total);
+    uint32_t coff = 0, goff = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (t.ne[k]) tma_load_1d(sb + C::kOffCols + (size_t)coff * 4u, m.m[k].col + (t.e0[k] & ~3u), cb[k], bar);
+        if (t.ngv[k])
+            tma_load_1d(sb + C::kOffGval + (size_t)goff * 32u, m.m[k].gval + t.gv0[k], t.ngv[k] * 32u, bar);
+        tma_load_1d(sb + C::kOffRp + (size_t)k * C::kRpCap * 4u, m.m[k].rowptr + t.row0, rp_bytes, bar);
+        coff += cb[k] / 4u;
+        goff += t.ngv[k];
+    }
+    if (gl_bytes) tma_load_1d(sb + C::kOffGlist, m.glist + t.g0, gl_bytes, bar);
+}
+}  // namespace tiled
+
+size_t r1cs_tiled_smem_bytes(int variant) {
+    return variant == 0 ? tiled::Cfg<0>::kBytes : tiled::Cfg<1>::kBytes;
+}
+
+template <class P, bool EMIT, int V>
+__global__ void __launch_bounds__(kTileGeom[V].threads, kTileGeom[V].ctas_per_sm)
     k_r1cs_tiled(DevR1cs m, const fr_t* __restrict__ w, const Tile* __restrict__ tiles, uint32_t n_tiles,
                  uint64_t row_base, unsigned long long* __restrict__ result, fr_t* __restrict__ Aw,
                  fr_t* __restrict__ Bw, fr_t* __restrict__ Cw) {
     using namespace tiled;
+    using C = Cfg<V>;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full_bar[kTileStages];
-    __shared__ __align__(8) uint64_t empty_bar[kTileStages];
-    __shared__ uint32_t s_nwork;
+    __shared__ __align__(8) uint64_t full_bar;
 
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < kTileStages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        s_nwork = 0;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
         mbar_fence_init();
     }
     __syncthreads();
+    if (tid == 0 && blockIdx.x < n_tiles) issue_tile_load<V>(m, tiles, blockIdx.x, smem, &full_bar);
 
-    if (threadIdx.x >= kConsumers) {
-        // ===== producer warp: one lane drives the TMA bulk copies =====
-        if (threadIdx.x == kConsumers) {
-            uint32_t it = 0;
-            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const uint32_t stage = it % kTileStages;
-                const uint32_t par = (it / kTileStages) & 1u;
-                mbar_wait(&empty_bar[stage], par ^ 1u);
-                uint8_t* sb = smem + (size_t)stage * kStageBytes;
-                const Tile t = tiles[tile];
-                *reinterpret_cast<Tile*>(sb + kOffDesc) = t;
-                const uint32_t rp_bytes = round_up4(t.nrows + 1u) * 4u;
-                uint32_t total = 3u * rp_bytes;
-                uint32_t cb[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    cb[k] = t.ne[k] ? round_up4((t.e0[k] & 3u) + t.ne[k]) * 4u : 0u;
-                    total += t.ne[k] * 32u + cb[k];
-                }
-                mbar_arrive_expect_tx(&full_bar[stage], total);
-                uint32_t vstart = 0, coff = 0;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (t.ne[k]) {
-                        tma_load_1d(sb + kOffVals + (size_t)vstart * 32u, m.m[k].val + t.e0[k], t.ne[k] * 32u,
-                                    &full_bar[stage]);
-                        tma_load_1d(sb + kOffCols + (size_t)coff * 4u, m.m[k].col + (t.e0[k] & ~3u), cb[k],
-                                    &full_bar[stage]);
-                    }
-                    tma_load_1d(sb + kOffRp + (size_t)k * kRpCap * 4u, m.m[k].rowptr + t.row0, rp_bytes,
-                                &full_bar[stage]);
-                    vstart += t.ne[k];
-                    coff += cb[k] / 4u;
-                }
-            }
-        }
-        return;
-    }
+    uint4* lo = reinterpret_cast<uint4*>(smem + C::kOffLo);
+    uint4* hi = reinterpret_cast<uint4*>(smem + C::kOffHi);
+    const uint32_t* cols = reinterpret_cast<const uint32_t*>(smem + C::kOffCols);
+    const uint32_t* rp = reinterpret_cast<const uint32_t*>(smem + C::kOffRp);
+    const fr_t* gval = reinterpret_cast<const fr_t*>(smem + C::kOffGval);
+    const uint16_t* glist = reinterpret_cast<const uint16_t*>(smem + C::kOffGlist);
 
-    // ===== consumers =====
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lane = tid & 31u;
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t stage = it % kTileStages;
-        const uint32_t par = (it / kTileStages) & 1u;
-        mbar_wait(&full_bar[stage], par);
-        uint8_t* sb = smem + (size_t)stage * kStageBytes;
-        fr_t* vals = reinterpret_cast<fr_t*>(sb + kOffVals);
-        const uint32_t* cols = reinterpret_cast<const uint32_t*>(sb + kOffCols);
-        const uint32_t* rp = reinterpret_cast<const uint32_t*>(sb + kOffRp);
-        uint16_t* work = reinterpret_cast<uint16_t*>(sb + kOffWork);
-        const Tile t = *reinterpret_cast<const Tile*>(sb + kOffDesc);
+        mbar_wait(&full_bar, it & 1u);
+        const Tile t = *reinterpret_cast<const Tile*>(smem + C::kOffDesc);
 
         const uint32_t nA = t.ne[0], nB = t.ne[1], nC = t.ne[2];
         const uint32_t nAB = nA + nB;
         const uint32_t E = nAB + nC;
-        // column index of pool entry idx:  cols[idx + cadj[M]]
+        // column word of pool entry idx:  cols[idx + cadj[M]]
         const uint32_t c0 = t.e0[0] & 3u;
         const uint32_t off1 = nA ? round_up4(c0 + nA) : 0u;
         const uint32_t c1 = off1 + (t.e0[1] & 3u);
         const uint32_t off2 = off1 + (nB ? round_up4((t.e0[1] & 3u) + nB) : 0u);
         const uint32_t c2 = off2 + (t.e0[2] & 3u);
-        const uint32_t cadjA = c0, cadjB = c1 - nA, cadjC = c2 - nAB;  // may wrap; used modulo 2^32
+        const uint32_t cadj[3] = {c0, c1 - nA, c2 - nAB};  // may wrap; used modulo 2^32
 
-        // ---- P1: thread per entry.  +-1 coefficients: replace the value by +-w[col].  Others: queue.
-        for (uint32_t base = 0; base < E; base += kConsumers * kUnroll) {
-            uint32_t idx[kUnroll], col[kUnroll];
-            bool plain[kUnroll], neg[kUnroll];
-#pragma unroll
-            for (uint32_t u = 0; u < kUnroll; ++u) {
-                idx[u] = base + u * kConsumers + tid;
-                const bool valid = idx[u] < E;
-                bool gen = false;
-                plain[u] = false;
-                neg[u] = false;
-                col[u] = 0;
-                if (valid) {
-                    const fr_t v = vals[idx[u]];
-                    const uint32_t adj = idx[u] < nA ? cadjA : (idx[u] < nAB ? cadjB : cadjC);
-                    col[u] = cols[idx[u] + adj];
-                    const bool one = fr_is_one<P>(v);
-                    neg[u] = fr_is_minus_one<P>(v);
-                    plain[u] = one || neg[u];
-                    gen = !plain[u];
-                }
-                const uint32_t bal = __ballot_sync(0xffffffffu, gen);
-                if (bal != 0u) {
-                    const uint32_t leader = (uint32_t)__ffs(bal) - 1u;
-                    uint32_t pos0 = 0;
-                    if (lane == leader) pos0 = atomicAdd(&s_nwork, (uint32_t)__popc(bal));
-                    pos0 = __shfl_sync(0xffffffffu, pos0, leader);
-                    if (gen) work[pos0 + __popc(bal & lanemask_lt())] = (uint16_t)idx[u];
-                }
-            }
-            fr_t x[kUnroll];
-#pragma unroll
-            for (uint32_t u = 0; u < kUnroll; ++u)
-                if (plain[u]) x[u] = w[col[u]];
-#pragma unroll
-            for (uint32_t u = 0; u < kUnroll; ++u)
-                if (plain[u]) vals[idx[u]] = neg[u] ? fr_neg<P>(x[u]) : x[u];
+        // ---- P1: gather the witness element of every entry, asynchronously, into the term planes
+        for (uint32_t e = tid; e < E; e += C::kThreads) {
+            const uint32_t c = cols[e + (e < nA ? cadj[0] : (e < nAB ? cadj[1] : cadj[2]))];
+            cp_async_fr_planes(lo + e, hi + e, w + (c & kColMask));
         }
-        named_bar_sync(1, kConsumers);
+        cp_async_wait_all();
+        __syncthreads();
 
-        // ---- P2: dense Montgomery products of the queued entries, one per lane
-        const uint32_t n_work = s_nwork;
-        for (uint32_t i = tid; i < n_work; i += kConsumers) {
-            const uint32_t e = work[i];
-            const uint32_t adj = e < nA ? cadjA : (e < nAB ? cadjB : cadjC);
-            const fr_t x = w[cols[e + adj]];
-            const fr_t v = vals[e];
-            vals[e] = fr_mul<P>(v, x);
+        // ---- P2: dense Montgomery products of the general entries, one per lane, in place
+        for (uint32_t j = tid; j < t.ng; j += C::kThreads) {
+            const uint32_t e = glist[j];
+            const fr_t v = gval[j];
+            const fr_t x = load_planes(lo, hi, e);
+            store_planes(lo, hi, e, fr_mul<P>(v, x));
         }
-        named_bar_sync(1, kConsumers);
-        if (tid == 0) s_nwork = 0;
+        __syncthreads();
 
-        // ---- P3: thread per row: sum the terms, test a*b == c
+        // ---- P3: thread per row: signed sum of the terms, test a*b == c
         bool bad = false;
         if (tid < t.nrows) {
             fr_t abc[3];
             uint32_t vstart = 0;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const uint32_t* rpk = rp + k * kRpCap;
+                const uint32_t* rpk = rp + k * C::kRpCap;
                 const uint32_t s = rpk[tid] - t.e0[k] + vstart;
                 const uint32_t e = rpk[tid + 1] - t.e0[k] + vstart;
                 fr_t acc = fr_zero<P>();
                 for (uint32_t j = s; j < e; ++j) {
-                    const fr_t term = vals[j];
-                    acc = fr_add<P>(acc, term);
+                    const fr_t term = load_planes(lo, hi, j);
+                    const uint32_t tag = cols[j + cadj[k]] >> 30;
+                    if (tag == kTagMinusOne) {
+                        acc = fr_sub<P>(acc, term);
+                    } else {
+                        acc = fr_add<P>(acc, term);
+                    }
                 }
                 abc[k] = acc;
                 vstart += t.ne[k];
@@ -308,11 +321,11 @@ __global__ void __launch_bounds__(kTiledThreads, kTiledCtasPerSm)
         const uint32_t bal = __ballot_sync(0xffffffffu, bad);
         if (bal != 0u && lane == 0u) report_bad_rows(result, bal, row_base + t.row0 + (tid & ~31u));
 
-        // the stage's shared memory was written through the generic proxy (P1/P2); order those writes
-        // before the TMA (async proxy) refill, then hand the stage back to the producer
+        // the staged arrays were read through the generic proxy; order that before the next TMA (async
+        // proxy) refill of the same bytes, then let one thread issue it
         fence_proxy_async_smem();
-        named_bar_sync(1, kConsumers);
-        if (tid == 0) mbar_arrive(&empty_bar[stage]);
+        __syncthreads();
+        if (tid == 0 && tile + gridDim.x < n_tiles) issue_tile_load<V>(m, tiles, tile + gridDim.x, smem, &full_bar);
     }
 }
 
@@ -375,35 +388,48 @@ cudaError_t launch_r1cs_rowwise(int field, const DevR1cs& m, const fr_t* w, uint
     return cudaGetLastError();
 }
 
-template <class P, bool EMIT>
+template <class P, bool EMIT, int V>
 static cudaError_t launch_tiled_impl(const DevR1cs& m, const fr_t* w, const Tile* d_tiles, uint32_t n_tiles,
                                      uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
                                      int sm_count, cudaStream_t s) {
-    const size_t smem = r1cs_tiled_smem_bytes();
+    const size_t smem = tiled::Cfg<V>::kBytes;
     {
-        cudaError_t e = cudaFuncSetAttribute(k_r1cs_tiled<P, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_r1cs_tiled<P, EMIT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
     }
-    unsigned grid = (unsigned)(sm_count * kTiledCtasPerSm);
+    unsigned grid = (unsigned)(sm_count * (int)kTileGeom[V].ctas_per_sm);
     if (grid > n_tiles) grid = n_tiles;
-    k_r1cs_tiled<P, EMIT><<<grid, kTiledThreads, smem, s>>>(m, w, d_tiles, n_tiles, row_base, d_result, Aw, Bw, Cw);
+    k_r1cs_tiled<P, EMIT, V><<<grid, kTileGeom[V].threads, smem, s>>>(m, w, d_tiles, n_tiles, row_base, d_result, Aw,
+                                                                       Bw, Cw);
     return cudaGetLastError();
 }
 
 cudaError_t launch_r1cs_tiled(int field, const DevR1cs& m, const fr_t* w, const Tile* d_tiles, uint32_t n_tiles,
                               uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
-                              int sm_count, cudaStream_t s) {
+                              int sm_count, int variant, cudaStream_t s) {
     if (n_tiles == 0) return cudaSuccess;
+    if (!m.tagged || !m.glist) return cudaErrorInvalidValue;
     const bool emit = Aw || Bw || Cw;
-    if (emit) {
-        ACG_DISPATCH_FIELD(field, return (launch_tiled_impl<P, true>(m, w, d_tiles, n_tiles, row_base, d_result, Aw,
-                                                                     Bw, Cw, sm_count, s)));
+#define ACG_TILED(EMITV, VAR)                                                                                     \
+    ACG_DISPATCH_FIELD(field, return (launch_tiled_impl<P, EMITV, VAR>(m, w, d_tiles, n_tiles, row_base, d_result, \
+                                                                       Aw, Bw, Cw, sm_count, s)))
+    if (variant == 1) {
+        if (emit) ACG_TILED(true, 1);
+        ACG_TILED(false, 1);
     } else {
-        ACG_DISPATCH_FIELD(field, return (launch_tiled_impl<P, false>(m, w, d_tiles, n_tiles, row_base, d_result, Aw,
-                                                                      Bw, Cw, sm_count, s)));
+        if (emit) ACG_TILED(true, 0);
+        ACG_TILED(false, 0);
     }
+#undef ACG_TILED
     return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_validate_csr(const uint32_t* rowptr, const uint32_t* col, uint32_t n_rows, uint64_t nnz,
+                                uint32_t n_cols, int* d_flag, cudaStream_t s) {
+    const uint64_t work = nnz > n_rows ? nnz : n_rows;
+    k_validate_csr<<<grid_for(work ? work : 1, 256, 148 * 8), 256, 0, s>>>(rowptr, col, n_rows, nnz, n_cols, d_flag);
+    return cudaGetLastError();
 }
 
 }  // namespace acg

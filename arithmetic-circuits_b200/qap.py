@@ -395,6 +395,9 @@ class Context:
     def set_check_kernel(self, which: int):
         _check(_lib.lib().acg_ctx_set_check_kernel(self._h, which), self)
 
+    def set_tiled_variant(self, variant: int):
+        _check(_lib.lib().acg_ctx_set_tiled_variant(self._h, variant), self)
+
     def last_timing(self) -> Dict[str, float]:
         t = AcgTiming()
         _check(_lib.lib().acg_last_timing(self._h, C.byref(t)), self)

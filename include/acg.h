@@ -81,6 +81,8 @@ const char* acg_last_error(const acg_ctx* ctx);
 int acg_ctx_create(int field_id, int device, acg_ctx** out);
 void acg_ctx_destroy(acg_ctx* ctx);
 int acg_ctx_set_check_kernel(acg_ctx* ctx, int which);
+/* Tiled kernel geometry (tuning): 0 = 128-row tiles, 7 CTAs per SM (default); 1 = 256-row tiles, 3 CTAs. */
+int acg_ctx_set_tiled_variant(acg_ctx* ctx, int variant);
 int acg_last_timing(const acg_ctx* ctx, acg_timing* out);
 /* Total launches of this library's kernels on this context since creation. */
 uint64_t acg_kernel_launch_count(const acg_ctx* ctx);

@@ -42,13 +42,26 @@ def test_field_ops_device(acg, ctxs, fid):
 
 
 # ------------------------------------------------------------------------------------------------ K2
+KERNELS = [("rowwise", 0), ("tiled", 0), ("tiled", 1)]   # (kernel, tiled geometry variant)
+
+
+def _select(acg, ctx, kernel, variant):
+    ctx.set_check_kernel(acg.CHECK_ROWWISE if kernel == "rowwise" else acg.CHECK_TILED)
+    ctx.set_tiled_variant(variant)
+
+
+def _reset(acg, ctx):
+    ctx.set_check_kernel(acg.CHECK_AUTO)
+    ctx.set_tiled_variant(0)
+
+
 def _both_kernels(acg, ctx, fn):
     out = []
-    for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
-        ctx.set_check_kernel(which)
+    for kernel, stages in KERNELS:
+        _select(acg, ctx, kernel, stages)
         out.append(fn())
-    ctx.set_check_kernel(acg.CHECK_AUTO)
-    assert out[0] == out[1], out
+    _reset(acg, ctx)
+    assert all(o == out[0] for o in out), out
     return out[0]
 
 
@@ -117,13 +130,14 @@ def test_mixed_circuits_gpu(acg, ctxs, idx):
     assert _both_kernels(acg, ctx, lambda: ctx.r1cs_check_host(g, w)) == (0, -1)
     assert list(_both_kernels(acg, ctx, lambda: ctx.r1cs_check_host(g, wb))) == case["bad_check"]
     m, dw = ctx.upload_r1cs(g), ctx.upload_witness(w)
-    for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
-        ctx.set_check_kernel(which)
+    assert _both_kernels(acg, ctx, lambda: ctx.r1cs_check(m, dw)) == (0, -1)
+    for kernel, stages in KERNELS:
+        _select(acg, ctx, kernel, stages)
         aw, bw, cw = ctx.r1cs_eval(m, dw)
         assert acg.from_limbs(aw) == unhex(case["Aw"])
         assert acg.from_limbs(bw) == unhex(case["Bw"])
         assert acg.from_limbs(cw) == unhex(case["Cw"])
-    ctx.set_check_kernel(acg.CHECK_AUTO)
+    _reset(acg, ctx)
     if "qap_delta_3_5_7" in case:
         q = case["qap_delta_3_5_7"]
         bufs, ok = ctx.qap_witness(m, dw, (3, 5, 7))
@@ -141,11 +155,12 @@ def test_synth_parity_small(acg, ctxs, fid, n, seed, dense):
     assert ref["n_violations"] == 0
     m, dw = ctx.upload_r1cs(g), ctx.upload_witness(w)
     assert m.algorithmic_bytes == sum(36 * k for k in g.nnz) + 3 * 4 * (n + 1) + 32 * g.n_cols + 8
-    for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
-        ctx.set_check_kernel(which)
+    for kernel, stages in KERNELS:
+        _select(acg, ctx, kernel, stages)
         assert ctx.r1cs_check(m, dw) == (0, -1)
         aw, bw, cw = ctx.r1cs_eval(m, dw)
         assert (aw == ref["Aw"]).all() and (bw == ref["Bw"]).all() and (cw == ref["Cw"]).all()
+    assert ctx.r1cs_check_host(g, w) == (0, -1)     # one-shot path (no preprocessing, untagged row-wise)
     # negative variants: SURVEY 8d (+1 on w[1025 + n/3]) and a few random single-limb flips
     rnd = random.Random(seed)
     for t in [1025 + n // 3] + [rnd.randrange(1, g.n_cols) for _ in range(3)]:
@@ -153,10 +168,11 @@ def test_synth_parity_small(acg, ctxs, fid, n, seed, dense):
         wb[t, rnd.randrange(3)] ^= np.uint64(1 << rnd.randrange(60))
         refb = oracle_check(fid, g, wb)
         dw.update(wb)
-        for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
-            ctx.set_check_kernel(which)
+        for kernel, stages in KERNELS:
+            _select(acg, ctx, kernel, stages)
             assert ctx.r1cs_check(m, dw) == (refb["n_violations"], refb["first_bad_row"])
-    ctx.set_check_kernel(acg.CHECK_AUTO)
+        assert ctx.r1cs_check_host(g, wb) == (refb["n_violations"], refb["first_bad_row"])
+    _reset(acg, ctx)
     if n <= 96:  # golden h through the reference-named call
         case = [c for c in golden("synth.json") if (c["field"], c["n"], c["seed"]) == (fid, n, seed)][0]
         dw.update(w)
@@ -197,12 +213,13 @@ def test_edge_shapes(acg, ctx_bn):
         wl = acg.to_limbs(w)
         ref = oracle_check(0, g, wl, True)
         m, dw = ctx_bn.upload_r1cs(g), ctx_bn.upload_witness(wl)
-        for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
-            ctx_bn.set_check_kernel(which)
+        for kernel, stages in KERNELS:
+            _select(acg, ctx_bn, kernel, stages)
             assert ctx_bn.r1cs_check(m, dw) == (ref["n_violations"], ref["first_bad_row"]), name
             aw, bw, cw = ctx_bn.r1cs_eval(m, dw)
             assert (aw == ref["Aw"]).all() and (bw == ref["Bw"]).all() and (cw == ref["Cw"]).all(), name
-        ctx_bn.set_check_kernel(acg.CHECK_AUTO)
+        _reset(acg, ctx_bn)
+        assert ctx_bn.r1cs_check_host(g, wl) == (ref["n_violations"], ref["first_bad_row"]), name
     # validation: column out of range, non-monotone rowptr, non-canonical coefficient / witness
     good = make_genqap(acg, 0, 1, 4, (3, 0, 0), O.CSR([0, 1], [1], [5]), O.CSR([0, 1], [2], [1]), O.CSR([0, 1], [3], [1]))
     assert ctx_bn.r1cs_check_host(good, acg.to_limbs([1, 2, 3, 30])) == (0, -1)
@@ -247,8 +264,8 @@ def test_full_size_properties(acg, ctx_bn):
     n = 1 << 20
     g, w = acg.synth_r1cs(0, n, 20260002)
     m, dw = ctx_bn.upload_r1cs(g), ctx_bn.upload_witness(w)
-    for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
-        ctx_bn.set_check_kernel(which)
+    for kernel, stages in KERNELS:
+        _select(acg, ctx_bn, kernel, stages)
         assert ctx_bn.r1cs_check(m, dw) == (0, -1)
     wb = w.copy()
     wb[1025 + n // 3, 0] += np.uint64(1)       # the SURVEY 8d negative variant
@@ -257,10 +274,11 @@ def test_full_size_properties(acg, ctx_bn):
     ref = oracle_check(0, g, wb, True, n_threads=8)
     assert ref["n_violations"] > 0
     dw.update(wb)
-    for which in (acg.CHECK_ROWWISE, acg.CHECK_TILED):
-        ctx_bn.set_check_kernel(which)
+    for kernel, stages in KERNELS:
+        _select(acg, ctx_bn, kernel, stages)
         assert ctx_bn.r1cs_check(m, dw) == (ref["n_violations"], ref["first_bad_row"])
-    ctx_bn.set_check_kernel(acg.CHECK_AUTO)
+    _reset(acg, ctx_bn)
+    assert ctx_bn.r1cs_check_host(g, wb) == (ref["n_violations"], ref["first_bad_row"])
     aw, bw, cw = ctx_bn.r1cs_eval(m, dw)
     assert (aw == ref["Aw"]).all() and (bw == ref["Bw"]).all() and (cw == ref["Cw"]).all()
 
