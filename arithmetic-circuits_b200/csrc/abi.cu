@@ -25,7 +25,8 @@ struct acg_ctx {
     int device = 0;
     int sm_count = 148;
     int check_kernel = ACG_CHECK_AUTO;
-    int tiled_variant = 0;  // index into kTileGeom
+    int tiled_variant = 0;  // index into kTileGeom, bound to a system at upload
+    int tiled_stages = 1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* d_result = nullptr;  // {n_violations, first_bad_row}
@@ -54,12 +55,13 @@ struct acg_r1cs {
     uint32_t* d_col[3] = {nullptr, nullptr, nullptr};
     fr_t* d_val[3] = {nullptr, nullptr, nullptr};
     DevR1cs dev{};
-    fr_t* d_gval[3] = {nullptr, nullptr, nullptr};  // general-coefficient values only (tiled kernel)
-    // tilings for both geometry variants of the tiled kernel (tiny: 64 bytes per tile)
-    Tile* d_tiles[2] = {nullptr, nullptr};
-    uint16_t* d_glist[2] = {nullptr, nullptr};
-    uint32_t n_tiles[2] = {0, 0};
-    std::vector<std::pair<uint32_t, uint32_t>> long_ranges[2];  // local row ranges too wide for a tile
+    // execution-ready tile stream of the tiled kernel (kernels.h), built for geometry `variant`
+    uint8_t* d_stream = nullptr;
+    uint32_t* d_stream_off = nullptr;
+    uint64_t stream_bytes = 0;
+    uint32_t n_tiles = 0;
+    int variant = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> long_ranges;  // local row ranges too wide for a tile
 };
 
 struct acg_vec {
@@ -190,11 +192,14 @@ int upload_canonical(acg_ctx* ctx, fr_t* d, const uint64_t* host, uint64_t n) {
 // Greedy tiling in groups of 4 rows (TMA needs 16-byte aligned row-pointer slices): a tile holds at most
 // geom.threads rows, geom.pool entries (A+B+C) and geom.max_gen general-coefficient entries.
 // gcum[k][r] = number of general entries of matrix k in local rows < r.
+struct HostTile {
+    uint32_t row0, nrows, e0[3], ne[3];
+};
 void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t* gcum[3], uint32_t n_local,
-                 std::vector<Tile>& tiles, std::vector<std::pair<uint32_t, uint32_t>>& long_ranges) {
+                 std::vector<HostTile>& tiles, std::vector<std::pair<uint32_t, uint32_t>>& long_ranges) {
     uint32_t r = 0;
     while (r < n_local) {
-        Tile t{};
+        HostTile t{};
         t.row0 = r;
         uint32_t g_base = 0;
         for (int k = 0; k < 3; ++k) {
@@ -222,11 +227,7 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
             continue;
         }
         t.nrows = end - r;
-        for (int k = 0; k < 3; ++k) {
-            t.ne[k] = rp[k][end] - t.e0[k];
-            t.gv0[k] = gcum[k][r];
-            t.ngv[k] = gcum[k][end] - gcum[k][r];
-        }
+        for (int k = 0; k < 3; ++k) t.ne[k] = rp[k][end] - t.e0[k];
         tiles.push_back(t);
         r = end;
     }
@@ -253,19 +254,17 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long 
     }
     const bool prof = 2 * (ctx->prof_used + 1) <= ctx->prof_ev.size();
     if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
-    const int v = ctx->tiled_variant;
-    DevR1cs dev = m->dev;
-    dev.glist = m->d_glist[v];
-    if (m->n_tiles[v]) {
-        CU(ctx, launch_r1cs_tiled(ctx->field, dev, w, m->d_tiles[v], m->n_tiles[v], m->row_begin, d_result, Aw, Bw, Cw,
-                                  ctx->sm_count, v, s));
+    if (m->n_tiles) {
+        DevTileStream ts{m->d_stream, m->d_stream_off, m->n_tiles, (uint32_t)m->variant};
+        CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin, d_result, Aw, Bw, Cw, ctx->sm_count,
+                                  ctx->tiled_stages, s));
         ++*launches;
     }
     if (prof) {
         CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], s));
         ++ctx->prof_used;
     }
-    for (const auto& lr : m->long_ranges[v]) {
+    for (const auto& lr : m->long_ranges) {
         CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, lr.first, lr.second, m->row_begin, d_result, Aw, Bw, Cw, s));
         ++*launches;
     }
@@ -380,6 +379,12 @@ int acg_ctx_set_tiled_variant(acg_ctx* ctx, int variant) {
     return ACG_OK;
 }
 
+int acg_ctx_set_tiled_stages(acg_ctx* ctx, int stages) {
+    if (!ctx || (stages != 1 && stages != 2)) return ACG_ERR_BAD_ARG;
+    ctx->tiled_stages = stages;
+    return ACG_OK;
+}
+
 int acg_last_timing(const acg_ctx* ctx, acg_timing* out) {
     if (!ctx || !out) return ACG_ERR_BAD_ARG;
     *out = ctx->timing;
@@ -453,11 +458,8 @@ void acg_r1cs_free(acg_r1cs* m) {
         cudaFree(m->d_col[k]);
         cudaFree(m->d_val[k]);
     }
-    for (int k = 0; k < 3; ++k) cudaFree(m->d_gval[k]);
-    for (int v = 0; v < 2; ++v) {
-        cudaFree(m->d_tiles[v]);
-        cudaFree(m->d_glist[v]);
-    }
+    cudaFree(m->d_stream);
+    cudaFree(m->d_stream_off);
     delete m;
 }
 
@@ -528,7 +530,6 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
 
     CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     uint32_t launches = 0;
-    std::vector<uint64_t> gen_vals[3];  // must outlive the asynchronous copies below
     CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
     for (int k = 0; k < 3; ++k) {
         const acg_csr* M = src[k];
@@ -551,59 +552,97 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
             CU(ctx, launch_to_mont(ctx->field, m->d_val[k], cnt, ctx->d_flag, ctx->stream));
             ++launches;
         }
-        // compact copy of the general-coefficient values, in entry order
-        const uint32_t n_gen = gcum[k][n_local];
-        gen_vals[k].resize(4ull * n_gen + 4);
-        {
-            uint64_t* dst = gen_vals[k].data();
-            for (uint64_t e = 0; e < cnt; ++e)
-                if ((tagged_col[k][e] >> 30) == kTagGeneral) {
-                    std::memcpy(dst, M->val + 4ull * (e0 + e), 32);
-                    dst += 4;
-                }
-        }
-        CU(ctx, cudaMalloc(&m->d_gval[k], ((size_t)n_gen + 1) * sizeof(fr_t)));
-        if (n_gen) {
-            CU(ctx, cudaMemcpyAsync(m->d_gval[k], gen_vals[k].data(), (size_t)n_gen * sizeof(fr_t),
-                                    cudaMemcpyHostToDevice, ctx->stream));
-            CU(ctx, launch_to_mont(ctx->field, m->d_gval[k], n_gen, ctx->d_flag, ctx->stream));
-            ++launches;
-        }
         m->dev.m[k].rowptr = m->d_rowptr[k];
         m->dev.m[k].col = m->d_col[k];
         m->dev.m[k].val = m->d_val[k];
-        m->dev.m[k].gval = m->d_gval[k];
     }
     // tiles and their static lists of general entries (pool indices, uint16)
     const uint32_t* rp[3] = {local_rp[0].data(), local_rp[1].data(), local_rp[2].data()};
     const uint32_t* gc[3] = {gcum[0].data(), gcum[1].data(), gcum[2].data()};
-    std::vector<Tile> tiles[2];
-    std::vector<uint16_t> glist[2];
-    for (int v = 0; v < 2; ++v) {
-        build_tiles(kTileGeom[v], rp, gc, n_local, tiles[v], m->long_ranges[v]);
-        for (Tile& t : tiles[v]) {
-            t.g0 = (uint32_t)glist[v].size();
-            uint32_t vstart = 0;
+    // ---- tile stream (see kernels.h): one self-contained blob per tile
+    m->variant = ctx->tiled_variant;
+    const TileGeometry geom = kTileGeom[m->variant];
+    std::vector<HostTile> tiles;
+    build_tiles(geom, rp, gc, n_local, tiles, m->long_ranges);
+    std::vector<uint8_t> stream;
+    std::vector<uint32_t> offs, gval_offs;  // 16-byte units
+    offs.reserve(tiles.size() + 1);
+    stream.reserve((size_t)n_local * 88 + 4096);
+    auto align16 = [&]() { stream.resize((stream.size() + 15) & ~(size_t)15, 0); };
+    auto put16 = [&](uint16_t v) {
+        stream.push_back((uint8_t)(v & 0xFF));
+        stream.push_back((uint8_t)(v >> 8));
+    };
+    for (const HostTile& t : tiles) {
+        align16();
+        const size_t base = stream.size();
+        offs.push_back((uint32_t)(base / 16));
+        stream.resize(base + sizeof(TileHeader), 0);
+        TileHeader h{};
+        h.row0 = t.row0;
+        h.nrows = t.nrows;
+        h.n_entries = t.ne[0] + t.ne[1] + t.ne[2];
+        // pool-relative row pointers: A rows, B rows, C rows, nrows + 1 each
+        h.off_rp = (uint32_t)(stream.size() - base);
+        uint32_t vstart = 0;
+        for (int k = 0; k < 3; ++k) {
+            for (uint32_t r = 0; r <= t.nrows; ++r) put16((uint16_t)(vstart + local_rp[k][t.row0 + r] - t.e0[k]));
+            vstart += t.ne[k];
+        }
+        align16();
+        h.off_cols = (uint32_t)(stream.size() - base);
+        for (int k = 0; k < 3; ++k) {
+            const uint8_t* src8 = reinterpret_cast<const uint8_t*>(tagged_col[k].data() + t.e0[k]);
+            stream.insert(stream.end(), src8, src8 + 4ull * t.ne[k]);
+        }
+        align16();
+        h.off_list = (uint32_t)(stream.size() - base);
+        for (uint32_t want : {kTagGeneral, kTagMinusOne}) {
+            vstart = 0;
             for (int k = 0; k < 3; ++k) {
                 for (uint32_t e = 0; e < t.ne[k]; ++e)
-                    if ((tagged_col[k][t.e0[k] + e] >> 30) == kTagGeneral) glist[v].push_back((uint16_t)(vstart + e));
+                    if ((tagged_col[k][t.e0[k] + e] >> 30) == want) {
+                        put16((uint16_t)(vstart + e));
+                        (want == kTagGeneral ? h.n_general : h.n_minus) += 1;
+                    }
                 vstart += t.ne[k];
             }
-            t.ng = (uint32_t)glist[v].size() - t.g0;
-            while (glist[v].size() % 8) glist[v].push_back(0);  // keep every slice 16-byte aligned
         }
-        for (int i = 0; i < 8; ++i) glist[v].push_back(0);
-        m->n_tiles[v] = (uint32_t)tiles[v].size();
-        if (m->n_tiles[v]) {
-            CU(ctx, cudaMalloc(&m->d_tiles[v], tiles[v].size() * sizeof(Tile)));
-            CU(ctx, cudaMemcpyAsync(m->d_tiles[v], tiles[v].data(), tiles[v].size() * sizeof(Tile),
-                                    cudaMemcpyHostToDevice, ctx->stream));
+        align16();
+        h.off_gval = (uint32_t)(stream.size() - base);
+        for (int k = 0; k < 3; ++k) {
+            const acg_csr* M = src[k];
+            const uint32_t g0 = M->rowptr[row_begin];
+            for (uint32_t e = 0; e < t.ne[k]; ++e)
+                if ((tagged_col[k][t.e0[k] + e] >> 30) == kTagGeneral) {
+                    gval_offs.push_back((uint32_t)(stream.size() / 16));
+                    const uint8_t* v8 = reinterpret_cast<const uint8_t*>(M->val + 4ull * (g0 + t.e0[k] + e));
+                    stream.insert(stream.end(), v8, v8 + 32);
+                }
         }
-        CU(ctx, cudaMalloc(&m->d_glist[v], glist[v].size() * sizeof(uint16_t)));
-        CU(ctx, cudaMemcpyAsync(m->d_glist[v], glist[v].data(), glist[v].size() * sizeof(uint16_t),
-                                cudaMemcpyHostToDevice, ctx->stream));
+        align16();
+        h.bytes = (uint32_t)(stream.size() - base);
+        std::memcpy(stream.data() + base, &h, sizeof h);
     }
-    m->dev.glist = m->d_glist[0];
+    align16();
+    offs.push_back((uint32_t)(stream.size() / 16));
+    if (stream.size() / 16 > 0xFFFFFFF0ull) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_r1cs_upload: tile stream too large");
+    m->n_tiles = (uint32_t)tiles.size();
+    m->stream_bytes = stream.size();
+    DevBuf d_goffs;
+    CU(ctx, cudaMalloc(&m->d_stream, stream.size() + 64));
+    CU(ctx, cudaMalloc(&m->d_stream_off, offs.size() * sizeof(uint32_t)));
+    CU(ctx, d_goffs.alloc(gval_offs.size() * sizeof(uint32_t)));
+    CU(ctx, cudaMemcpyAsync(m->d_stream, stream.data(), stream.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(m->d_stream_off, offs.data(), offs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                            ctx->stream));
+    if (!gval_offs.empty()) {
+        CU(ctx, cudaMemcpyAsync(d_goffs.p, gval_offs.data(), gval_offs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                ctx->stream));
+        CU(ctx, launch_to_mont_scattered(ctx->field, m->d_stream, d_goffs.as<uint32_t>(), gval_offs.size(), ctx->d_flag,
+                                         ctx->stream));
+        ++launches;
+    }
     m->dev.tagged = 1;
     CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -623,6 +662,8 @@ uint64_t acg_r1cs_algorithmic_bytes(const acg_r1cs* m) {
     for (int k = 0; k < 3; ++k) b += m->nnz[k] * 36ull + 4ull * (rows + 1);
     return b;
 }
+
+uint64_t acg_r1cs_stream_bytes(const acg_r1cs* m) { return m ? m->stream_bytes : 0; }
 
 void acg_vec_free(acg_vec* v) {
     if (!v) return;
@@ -765,7 +806,6 @@ int acg_r1cs_check_host(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const ac
     CU(ctx, cudaStreamSynchronize(s));
     if (*ctx->h_flag & 2) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_check_host: malformed CSR (rowptr / column index)");
     if (*ctx->h_flag & 1) return fail(ctx, ACG_ERR_NON_CANONICAL, "acg_r1cs_check_host: field element >= modulus");
-    dev.glist = nullptr;
     dev.tagged = 0;
     CU(ctx, launch_init_result(ctx->d_result, s));
     ++launches;

@@ -19,39 +19,55 @@ constexpr uint32_t kTagGeneral = 2u;
 struct DevCsr {
     const uint32_t* rowptr;  // shard-local rows + 1 entries, rebased to 0, padded by >= 8
     const uint32_t* col;     // padded by >= 8; tagged when DevR1cs::tagged
-    const fr_t* val;         // Montgomery form, one per entry (row-wise kernel)
-    const fr_t* gval;        // Montgomery form, general-coefficient entries only, in entry order (tiled kernel)
+    const fr_t* val;         // Montgomery form, one per entry
 };
 struct DevR1cs {
     DevCsr m[3];             // A, B, C
-    const uint16_t* glist;   // per-tile lists of general-coefficient entries (pool indices), or null
     uint32_t tagged;
 };
 
-// One unit of work of the tiled check kernel: rows [row0, row0+nrows), their entry ranges in A, B, C,
-// the ranges of their general-coefficient values, and the slice [g0, g0+ng) of the general-entry list.
-struct alignas(16) Tile {
-    uint32_t row0;
+// ---- tile stream (tiled kernel) -------------------------------------------------------------------
+// The sparsity pattern and the coefficients are static, so upload lays the system out as a stream of
+// self-contained, execution-ready tile blobs; the kernel stages one blob per tile with a single TMA
+// bulk copy.  Blob = header | u16 row pointers (pool-relative, A then B then C, nrows+1 each) |
+// tagged column words of the pool entries (A rows, then B rows, then C rows) | u16 work list (pool
+// indices of the general-coefficient entries, then of the -1 entries) | general-coefficient values
+// (Montgomery, in work-list order).  Every section starts 16-byte aligned.
+struct alignas(16) TileHeader {
+    uint32_t row0;       // first (shard-local) row
     uint32_t nrows;
-    uint32_t e0[3];
-    uint32_t ne[3];
-    uint32_t gv0[3];  // first general value of the tile in m[k].gval
-    uint32_t ngv[3];  // number of general values per matrix (sum == ng)
-    uint32_t g0;      // multiple of 8 (16-byte aligned uint16 slice)
-    uint32_t ng;
+    uint32_t n_entries;  // pool entries E = nA + nB + nC
+    uint32_t n_general;  // work list [0, n_general): multiply by gval[j]
+    uint32_t n_minus;    // work list [n_general, n_general + n_minus): negate
+    uint32_t off_rp;     // byte offsets inside the blob
+    uint32_t off_cols;
+    uint32_t off_list;
+    uint32_t off_gval;
+    uint32_t bytes;      // blob size (multiple of 16)
+    uint32_t pad[6];
 };
-static_assert(sizeof(Tile) == 64, "Tile must be 64 bytes");
+static_assert(sizeof(TileHeader) == 64, "TileHeader must be 64 bytes");
 
-// Tiled kernel geometry (see DESIGN.md "K2").  Two variants, chosen at upload time:
-//   variant 0: 128-thread CTAs, tiles of <= 128 rows / 640 entries / 176 general entries, 7 CTAs per SM
-//   variant 1: 256-thread CTAs, tiles of <= 256 rows / 1344 entries / 384 general entries, 3 CTAs per SM
+// Tiled kernel geometry (see DESIGN.md "K2"); the variant is bound when the system is uploaded.
+//   variant 0: 128-thread CTAs, tiles of <= 128 rows / 640 entries / 176 general entries
+//   variant 1: 256-thread CTAs, tiles of <= 256 rows / 1344 entries / 384 general entries
 struct TileGeometry {
     uint32_t threads;   // == max rows per tile
     uint32_t pool;      // A+B+C entries staged per tile
     uint32_t max_gen;   // general-coefficient entries per tile
-    uint32_t ctas_per_sm;
 };
-constexpr TileGeometry kTileGeom[2] = {{128, 640, 176, 7}, {256, 1344, 384, 3}};
+constexpr TileGeometry kTileGeom[2] = {{128, 640, 176}, {256, 1344, 384}};
+constexpr uint32_t tile_blob_capacity(const TileGeometry& g) {
+    return 64u + ((3u * (g.threads + 1u) * 2u + 15u) / 16u) * 16u + g.pool * 4u + ((g.pool * 2u + 15u) / 16u) * 16u +
+           g.max_gen * 32u;
+}
+
+struct DevTileStream {
+    const uint8_t* blobs;      // concatenated tile blobs
+    const uint32_t* offsets;   // n_tiles + 1 offsets in 16-byte units
+    uint32_t n_tiles;
+    uint32_t variant;
+};
 
 cudaError_t launch_to_mont(int field, fr_t* v, uint64_t n, int* d_bad_flag, cudaStream_t s);
 cudaError_t launch_from_mont(int field, fr_t* v, uint64_t n, cudaStream_t s);
@@ -62,11 +78,14 @@ cudaError_t launch_init_result(unsigned long long* d_result, cudaStream_t s);
 cudaError_t launch_r1cs_rowwise(int field, const DevR1cs& m, const fr_t* w, uint32_t row_lo, uint32_t row_hi,
                                 uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
                                 cudaStream_t s);
-// TMA-staged tile kernel over a list of tiles built at upload time for geometry `variant` (requires m.tagged).
-cudaError_t launch_r1cs_tiled(int field, const DevR1cs& m, const fr_t* w, const Tile* d_tiles, uint32_t n_tiles,
-                              uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
-                              int sm_count, int variant, cudaStream_t s);
-size_t r1cs_tiled_smem_bytes(int variant);
+// TMA-staged tile kernel over the tile stream.  stages: 1 = single blob buffer, 2 = the next tile's blob is
+// prefetched while the current tile computes.
+cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w, uint64_t row_base,
+                              unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count, int stages,
+                              cudaStream_t s);
+// general values inside the blobs: canonical -> Montgomery in place; offs[i] = byte offset / 16 of value i
+cudaError_t launch_to_mont_scattered(int field, uint8_t* blobs, const uint32_t* offs, uint64_t n, int* d_bad_flag,
+                                     cudaStream_t s);
 // structural validation on the device: rowptr monotone and ending at nnz, col < n_cols.  Sets *d_flag |= 2.
 cudaError_t launch_validate_csr(const uint32_t* rowptr, const uint32_t* col, uint32_t n_rows, uint64_t nnz,
                                 uint32_t n_cols, int* d_flag, cudaStream_t s);

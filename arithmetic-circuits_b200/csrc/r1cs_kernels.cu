@@ -143,34 +143,19 @@ namespace tiled {
 constexpr uint32_t align_up(uint32_t x, uint32_t a) {
     return (x + a - 1) / a * a;
 }
-// shared-memory layout of one CTA for geometry variant V
-template <int V>
+// shared-memory layout of one CTA: STAGES blob buffers, then the two 16-byte term planes
+template <int V, int STAGES>
 struct Cfg {
     static constexpr uint32_t kThreads = kTileGeom[V].threads;
     static constexpr uint32_t kPool = kTileGeom[V].pool;
-    static constexpr uint32_t kMaxGen = kTileGeom[V].max_gen;
-    static constexpr uint32_t kCtasPerSm = kTileGeom[V].ctas_per_sm;
-    static constexpr uint32_t kColsCap = kPool + 24;   // 3 chunks, each <= ne + 6 after 16-byte alignment
-    static constexpr uint32_t kRpCap = kThreads + 8;   // per matrix, (nrows + 1) rounded up to 4
-    // gathered witness terms, later the per-entry products: two 16-byte planes so that 128-bit accesses of
-    // neighbouring lanes fall on distinct banks
-    static constexpr uint32_t kOffLo = 0;
-    static constexpr uint32_t kOffHi = kPool * 16;
-    static constexpr uint32_t kOffCols = kPool * 32;
-    static constexpr uint32_t kOffRp = kOffCols + kColsCap * 4;
-    static constexpr uint32_t kOffGval = align_up(kOffRp + 3 * kRpCap * 4, 32);
-    static constexpr uint32_t kOffGlist = kOffGval + kMaxGen * 32;
-    static constexpr uint32_t kOffDesc = align_up(kOffGlist + kMaxGen * 2, 16);
-    static constexpr uint32_t kBytes = align_up(kOffDesc + 64, 128);
-    static_assert(kOffCols % 16 == 0 && kOffRp % 16 == 0 && kOffGlist % 16 == 0 && (kRpCap * 4) % 16 == 0, "align");
+    static constexpr uint32_t kBlobCap = align_up(tile_blob_capacity(kTileGeom[V]), 128);
+    static constexpr uint32_t kOffLo = kBlobCap * STAGES;
+    static constexpr uint32_t kOffHi = kOffLo + kPool * 16;
+    static constexpr uint32_t kBytes = kOffHi + kPool * 16;
+    // CTAs per SM that fit 227 KB of shared memory (1 KB per CTA is reserved by the system)
+    static constexpr uint32_t kCtasPerSm = (227u * 1024u) / (kBytes + 1024u + 64u);
 };
 
-__device__ __forceinline__ uint32_t round_up4(uint32_t x) {
-    return (x + 3u) & ~3u;
-}
-__device__ __forceinline__ uint32_t round_up8(uint32_t x) {
-    return (x + 7u) & ~7u;
-}
 // 2 x 16-byte asynchronous gather global -> shared (LDGSTS), no register staging
 __device__ __forceinline__ void cp_async_fr_planes(uint4* lo, uint4* hi, const fr_t* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lo)), "l"(gmem_src) : "memory");
@@ -192,140 +177,141 @@ __device__ __forceinline__ void store_planes(uint4* lo, uint4* hi, uint32_t i, c
     lo[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
     hi[i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
-
-// one thread: stage tile `tile` into `sb`, completion on `bar`
-template <int V>
-__device__ __forceinline__ void issue_tile_load(const DevR1cs& m, const Tile* __restrict__ tiles, uint32_t tile,
-                                                uint8_t* sb, uint64_t* bar) {
-    using C = Cfg<V>;
-    const Tile t = tiles[tile];
-    *reinterpret_cast<Tile*>(sb + C::kOffDesc) = t;
-    const uint32_t rp_bytes = round_up4(t.nrows + 1u) * 4u;
-    const uint32_t gl_bytes = round_up8(t.ng) * 2u;
-    uint32_t total = 3u * rp_bytes + gl_bytes + t.ng * 32u;
-    uint32_t cb[3];
+__device__ __forceinline__ fr_t load_fr16(const uint8_t* p) {  // 16-byte aligned shared-memory element
+    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+// p - x without the zero fix-up: the result is in (0, p] and only ever feeds fr_add, which accepts it
+template <class P>
+__device__ __forceinline__ fr_t neg_lazy(const fr_t& x) {
+    fr_t r;
+    r.l[0] = ptx::sub_cc(P::p(0), x.l[0]);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        cb[k] = t.ne[k] ? round_up4((t.e0[k] & 3u) + t.ne[k]) * 4u : 0u;
-        total += cb[k];
-    }
-    mbar_arrive_expect_tx(bar, total);
-    uint32_t coff = 0, goff = 0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (t.ne[k]) tma_load_1d(sb + C::kOffCols + (size_t)coff * 4u, m.m[k].col + (t.e0[k] & ~3u), cb[k], bar);
-        if (t.ngv[k])
-            tma_load_1d(sb + C::kOffGval + (size_t)goff * 32u, m.m[k].gval + t.gv0[k], t.ngv[k] * 32u, bar);
-        tma_load_1d(sb + C::kOffRp + (size_t)k * C::kRpCap * 4u, m.m[k].rowptr + t.row0, rp_bytes, bar);
-        coff += cb[k] / 4u;
-        goff += t.ngv[k];
-    }
-    if (gl_bytes) tma_load_1d(sb + C::kOffGlist, m.glist + t.g0, gl_bytes, bar);
+    for (int i = 1; i < 7; ++i) r.l[i] = ptx::subc_cc(P::p(i), x.l[i]);
+    r.l[7] = ptx::subc(P::p(7), x.l[7]);
+    return r;
+}
+// one thread: one bulk copy of the whole tile blob
+__device__ __forceinline__ void issue_blob_load(const DevTileStream& ts, uint32_t tile, uint8_t* dst, uint64_t* bar) {
+    const uint32_t o0 = ts.offsets[tile], o1 = ts.offsets[tile + 1];
+    const uint32_t bytes = (o1 - o0) * 16u;
+    mbar_arrive_expect_tx(bar, bytes);
+    tma_load_1d(dst, ts.blobs + (size_t)o0 * 16u, bytes, bar);
 }
 }  // namespace tiled
 
-size_t r1cs_tiled_smem_bytes(int variant) {
-    return variant == 0 ? tiled::Cfg<0>::kBytes : tiled::Cfg<1>::kBytes;
-}
-
-template <class P, bool EMIT, int V>
-__global__ void __launch_bounds__(kTileGeom[V].threads, kTileGeom[V].ctas_per_sm)
-    k_r1cs_tiled(DevR1cs m, const fr_t* __restrict__ w, const Tile* __restrict__ tiles, uint32_t n_tiles,
-                 uint64_t row_base, unsigned long long* __restrict__ result, fr_t* __restrict__ Aw,
-                 fr_t* __restrict__ Bw, fr_t* __restrict__ Cw) {
+template <class P, bool EMIT, int V, int STAGES>
+__global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V, STAGES>::kCtasPerSm)
+    k_r1cs_tiled(DevTileStream ts, const fr_t* __restrict__ w, uint64_t row_base,
+                 unsigned long long* __restrict__ result, fr_t* __restrict__ Aw, fr_t* __restrict__ Bw,
+                 fr_t* __restrict__ Cw) {
     using namespace tiled;
-    using C = Cfg<V>;
+    using C = Cfg<V, STAGES>;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full_bar;
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
+    const uint32_t n_tiles = ts.n_tiles;
     if (tid == 0) {
-        mbar_init(&full_bar, 1);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0 && blockIdx.x < n_tiles) issue_tile_load<V>(m, tiles, blockIdx.x, smem, &full_bar);
+    if (tid == 0 && blockIdx.x < n_tiles) issue_blob_load(ts, blockIdx.x, smem, &full_bar[0]);
 
     uint4* lo = reinterpret_cast<uint4*>(smem + C::kOffLo);
     uint4* hi = reinterpret_cast<uint4*>(smem + C::kOffHi);
-    const uint32_t* cols = reinterpret_cast<const uint32_t*>(smem + C::kOffCols);
-    const uint32_t* rp = reinterpret_cast<const uint32_t*>(smem + C::kOffRp);
-    const fr_t* gval = reinterpret_cast<const fr_t*>(smem + C::kOffGval);
-    const uint16_t* glist = reinterpret_cast<const uint16_t*>(smem + C::kOffGlist);
 
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(&full_bar, it & 1u);
-        const Tile t = *reinterpret_cast<const Tile*>(smem + C::kOffDesc);
+        const uint32_t stage = it % STAGES;
+        const uint8_t* blob = smem + (size_t)stage * C::kBlobCap;
+        if (STAGES == 2 && tid == 0 && tile + gridDim.x < n_tiles)  // prefetch: that buffer was released by the
+            issue_blob_load(ts, tile + gridDim.x,                   // barrier that ended the previous tile
+                            smem + (size_t)((it + 1) % STAGES) * C::kBlobCap, &full_bar[(it + 1) % STAGES]);
+        mbar_wait(&full_bar[stage], (it / STAGES) & 1u);
 
-        const uint32_t nA = t.ne[0], nB = t.ne[1], nC = t.ne[2];
-        const uint32_t nAB = nA + nB;
-        const uint32_t E = nAB + nC;
-        // column word of pool entry idx:  cols[idx + cadj[M]]
-        const uint32_t c0 = t.e0[0] & 3u;
-        const uint32_t off1 = nA ? round_up4(c0 + nA) : 0u;
-        const uint32_t c1 = off1 + (t.e0[1] & 3u);
-        const uint32_t off2 = off1 + (nB ? round_up4((t.e0[1] & 3u) + nB) : 0u);
-        const uint32_t c2 = off2 + (t.e0[2] & 3u);
-        const uint32_t cadj[3] = {c0, c1 - nA, c2 - nAB};  // may wrap; used modulo 2^32
+        const TileHeader h = *reinterpret_cast<const TileHeader*>(blob);
+        const uint32_t* cols = reinterpret_cast<const uint32_t*>(blob + h.off_cols);
+        const uint16_t* list = reinterpret_cast<const uint16_t*>(blob + h.off_list);
+        const uint8_t* gval = blob + h.off_gval;
 
         // ---- P1: gather the witness element of every entry, asynchronously, into the term planes
-        for (uint32_t e = tid; e < E; e += C::kThreads) {
-            const uint32_t c = cols[e + (e < nA ? cadj[0] : (e < nAB ? cadj[1] : cadj[2]))];
-            cp_async_fr_planes(lo + e, hi + e, w + (c & kColMask));
-        }
+        for (uint32_t e = tid; e < h.n_entries; e += C::kThreads)
+            cp_async_fr_planes(lo + e, hi + e, w + (cols[e] & kColMask));
         cp_async_wait_all();
         __syncthreads();
 
-        // ---- P2: dense Montgomery products of the general entries, one per lane, in place
-        for (uint32_t j = tid; j < t.ng; j += C::kThreads) {
-            const uint32_t e = glist[j];
-            const fr_t v = gval[j];
+        // ---- P2: dense work list, one entry per lane: general coefficients multiply, -1 coefficients negate
+        const uint32_t n_work = h.n_general + h.n_minus;
+        for (uint32_t j = tid; j < n_work; j += C::kThreads) {
+            const uint32_t e = list[j];
             const fr_t x = load_planes(lo, hi, e);
-            store_planes(lo, hi, e, fr_mul<P>(v, x));
+            if (j < h.n_general) {
+                store_planes(lo, hi, e, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), x));
+            } else {
+                store_planes(lo, hi, e, neg_lazy<P>(x));
+            }
         }
         __syncthreads();
 
-        // ---- P3: thread per row: signed sum of the terms, test a*b == c
+        // ---- P3: thread per row: three independent sums (A, B, C) advance together, then a*b == c
         bool bad = false;
-        if (tid < t.nrows) {
-            fr_t abc[3];
-            uint32_t vstart = 0;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const uint32_t* rpk = rp + k * C::kRpCap;
-                const uint32_t s = rpk[tid] - t.e0[k] + vstart;
-                const uint32_t e = rpk[tid + 1] - t.e0[k] + vstart;
-                fr_t acc = fr_zero<P>();
-                for (uint32_t j = s; j < e; ++j) {
-                    const fr_t term = load_planes(lo, hi, j);
-                    const uint32_t tag = cols[j + cadj[k]] >> 30;
-                    if (tag == kTagMinusOne) {
-                        acc = fr_sub<P>(acc, term);
-                    } else {
-                        acc = fr_add<P>(acc, term);
-                    }
-                }
-                abc[k] = acc;
-                vstart += t.ne[k];
+        if (tid < h.nrows) {
+            const uint16_t* rp = reinterpret_cast<const uint16_t*>(blob + h.off_rp);
+            const uint32_t stride = h.nrows + 1u;
+            uint32_t s0 = rp[tid], e0 = rp[tid + 1u];
+            uint32_t s1 = rp[stride + tid], e1 = rp[stride + tid + 1u];
+            uint32_t s2 = rp[2u * stride + tid], e2 = rp[2u * stride + tid + 1u];
+            fr_t a = fr_zero<P>(), b = fr_zero<P>(), c = fr_zero<P>();
+            while (s0 < e0 || s1 < e1 || s2 < e2) {
+                if (s0 < e0) a = fr_add<P>(a, load_planes(lo, hi, s0));
+                if (s1 < e1) b = fr_add<P>(b, load_planes(lo, hi, s1));
+                if (s2 < e2) c = fr_add<P>(c, load_planes(lo, hi, s2));
+                ++s0;
+                ++s1;
+                ++s2;
             }
             if (EMIT) {
-                const uint32_t row = t.row0 + tid;
-                if (Aw) Aw[row] = abc[0];
-                if (Bw) Bw[row] = abc[1];
-                if (Cw) Cw[row] = abc[2];
+                const uint32_t row = h.row0 + tid;
+                if (Aw) Aw[row] = a;
+                if (Bw) Bw[row] = b;
+                if (Cw) Cw[row] = c;
             }
-            bad = !fr_eq(fr_mul<P>(abc[0], abc[1]), abc[2]);
+            bad = !fr_eq(fr_mul<P>(a, b), c);
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, bad);
-        if (bal != 0u && lane == 0u) report_bad_rows(result, bal, row_base + t.row0 + (tid & ~31u));
+        if (bal != 0u && lane == 0u) report_bad_rows(result, bal, row_base + h.row0 + (tid & ~31u));
 
-        // the staged arrays were read through the generic proxy; order that before the next TMA (async
-        // proxy) refill of the same bytes, then let one thread issue it
+        // the blob was read through the generic proxy; order that before the next TMA (async proxy) refill
         fence_proxy_async_smem();
         __syncthreads();
-        if (tid == 0 && tile + gridDim.x < n_tiles) issue_tile_load<V>(m, tiles, tile + gridDim.x, smem, &full_bar);
+        if (STAGES == 1 && tid == 0 && tile + gridDim.x < n_tiles)
+            issue_blob_load(ts, tile + gridDim.x, smem, &full_bar[0]);
+    }
+}
+
+template <class P>
+__global__ void k_to_mont_scattered(uint8_t* __restrict__ blobs, const uint32_t* __restrict__ offs, uint64_t n,
+                                    int* __restrict__ bad_flag) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4* p = reinterpret_cast<uint4*>(blobs + (size_t)offs[i] * 16u);
+        const uint4 a = p[0], b = p[1];
+        fr_t x;
+        x.l[0] = a.x; x.l[1] = a.y; x.l[2] = a.z; x.l[3] = a.w;
+        x.l[4] = b.x; x.l[5] = b.y; x.l[6] = b.z; x.l[7] = b.w;
+        if (!fr_is_canonical<P>(x)) {
+            *bad_flag = 1;
+        } else {
+            const fr_t y = fr_to_mont<P>(x);
+            p[0] = make_uint4(y.l[0], y.l[1], y.l[2], y.l[3]);
+            p[1] = make_uint4(y.l[4], y.l[5], y.l[6], y.l[7]);
+        }
     }
 }
 
@@ -388,41 +374,54 @@ cudaError_t launch_r1cs_rowwise(int field, const DevR1cs& m, const fr_t* w, uint
     return cudaGetLastError();
 }
 
-template <class P, bool EMIT, int V>
-static cudaError_t launch_tiled_impl(const DevR1cs& m, const fr_t* w, const Tile* d_tiles, uint32_t n_tiles,
-                                     uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
-                                     int sm_count, cudaStream_t s) {
-    const size_t smem = tiled::Cfg<V>::kBytes;
+template <class P, bool EMIT, int V, int STAGES>
+static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uint64_t row_base,
+                                     unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count,
+                                     cudaStream_t s) {
+    using C = tiled::Cfg<V, STAGES>;
     {
-        cudaError_t e = cudaFuncSetAttribute(k_r1cs_tiled<P, EMIT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_r1cs_tiled<P, EMIT, V, STAGES>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kBytes);
         if (e != cudaSuccess) return e;
     }
-    unsigned grid = (unsigned)(sm_count * (int)kTileGeom[V].ctas_per_sm);
-    if (grid > n_tiles) grid = n_tiles;
-    k_r1cs_tiled<P, EMIT, V><<<grid, kTileGeom[V].threads, smem, s>>>(m, w, d_tiles, n_tiles, row_base, d_result, Aw,
-                                                                       Bw, Cw);
+    unsigned grid = (unsigned)(sm_count * (int)C::kCtasPerSm);
+    if (grid > ts.n_tiles) grid = ts.n_tiles;
+    k_r1cs_tiled<P, EMIT, V, STAGES><<<grid, kTileGeom[V].threads, C::kBytes, s>>>(ts, w, row_base, d_result, Aw, Bw,
+                                                                                   Cw);
     return cudaGetLastError();
 }
 
-cudaError_t launch_r1cs_tiled(int field, const DevR1cs& m, const fr_t* w, const Tile* d_tiles, uint32_t n_tiles,
-                              uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
-                              int sm_count, int variant, cudaStream_t s) {
-    if (n_tiles == 0) return cudaSuccess;
-    if (!m.tagged || !m.glist) return cudaErrorInvalidValue;
+cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w, uint64_t row_base,
+                              unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count, int stages,
+                              cudaStream_t s) {
+    if (ts.n_tiles == 0) return cudaSuccess;
     const bool emit = Aw || Bw || Cw;
-#define ACG_TILED(EMITV, VAR)                                                                                     \
-    ACG_DISPATCH_FIELD(field, return (launch_tiled_impl<P, EMITV, VAR>(m, w, d_tiles, n_tiles, row_base, d_result, \
-                                                                       Aw, Bw, Cw, sm_count, s)))
-    if (variant == 1) {
-        if (emit) ACG_TILED(true, 1);
-        ACG_TILED(false, 1);
+#define ACG_TILED(EMITV, VAR, STG)                                                                               \
+    ACG_DISPATCH_FIELD(field, return (launch_tiled_impl<P, EMITV, VAR, STG>(ts, w, row_base, d_result, Aw, Bw, Cw, \
+                                                                            sm_count, s)))
+#define ACG_TILED_VS(VAR, STG)        \
+    do {                              \
+        if (emit) ACG_TILED(true, VAR, STG); \
+        ACG_TILED(false, VAR, STG);   \
+    } while (0)
+    if (ts.variant == 1) {
+        if (stages == 2) ACG_TILED_VS(1, 2);
+        ACG_TILED_VS(1, 1);
     } else {
-        if (emit) ACG_TILED(true, 0);
-        ACG_TILED(false, 0);
+        if (stages == 2) ACG_TILED_VS(0, 2);
+        ACG_TILED_VS(0, 1);
     }
+#undef ACG_TILED_VS
 #undef ACG_TILED
     return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_to_mont_scattered(int field, uint8_t* blobs, const uint32_t* offs, uint64_t n, int* d_bad_flag,
+                                     cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    ACG_DISPATCH_FIELD(field,
+                       (k_to_mont_scattered<P><<<grid_for(n, 256, 148 * 16), 256, 0, s>>>(blobs, offs, n, d_bad_flag)));
+    return cudaGetLastError();
 }
 
 cudaError_t launch_validate_csr(const uint32_t* rowptr, const uint32_t* col, uint32_t n_rows, uint64_t nnz,

@@ -396,7 +396,11 @@ class Context:
         _check(_lib.lib().acg_ctx_set_check_kernel(self._h, which), self)
 
     def set_tiled_variant(self, variant: int):
+        """Tile geometry for systems uploaded AFTER this call (0: 128-row tiles, 1: 256-row tiles)."""
         _check(_lib.lib().acg_ctx_set_tiled_variant(self._h, variant), self)
+
+    def set_tiled_stages(self, stages: int):
+        _check(_lib.lib().acg_ctx_set_tiled_stages(self._h, stages), self)
 
     def last_timing(self) -> Dict[str, float]:
         t = AcgTiming()
@@ -519,6 +523,10 @@ class DeviceR1cs:
     @property
     def algorithmic_bytes(self) -> int:
         return _lib.lib().acg_r1cs_algorithmic_bytes(self._h)
+
+    @property
+    def stream_bytes(self) -> int:
+        return _lib.lib().acg_r1cs_stream_bytes(self._h)
 
 
 class DeviceVec:

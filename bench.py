@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--dense", action="store_true", help="all coefficients uniform (stress variant)")
     ap.add_argument("--kernel", default="tiled", choices=["tiled", "rowwise"])
     ap.add_argument("--variant", type=int, default=0, choices=[0, 1], help="tiled kernel geometry (0: 128-row tiles)")
+    ap.add_argument("--stages", type=int, default=1, choices=[1, 2], help="tiled kernel: 2 = prefetch next tile")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -209,6 +210,7 @@ def run_ours(args, rank, world, local_rank):
     ctx = acg.Context(field_id, local_rank)
     ctx.set_check_kernel(acg.CHECK_TILED if args.kernel == "tiled" else acg.CHECK_ROWWISE)
     ctx.set_tiled_variant(args.variant)
+    ctx.set_tiled_stages(args.stages)
     m = ctx.upload_r1cs(g)
     dw = ctx.upload_witness(w)
     algo_bytes = m.algorithmic_bytes
@@ -303,7 +305,7 @@ def run_ours(args, rank, world, local_rank):
             "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u256 (8x32-bit-limb Montgomery Fr, integer)", "data": "synthetic",
-            "config": {"workload": workload_name(args, world), "kernel": args.kernel, "tiled_variant": args.variant,
+            "config": {"workload": workload_name(args, world), "kernel": args.kernel, "tiled_variant": args.variant, "tiled_stages": args.stages,
                        "l2": "inputs streamed per step (%.0f MB CSR + %.0f MB witness per GPU) exceed the 126 MB L2; no explicit flush"
                              % ((algo_bytes - 32 * g.n_cols) / 1e6, 32 * g.n_cols / 1e6),
                        "parallelism": "rows sharded over %d rank(s), 1 all-reduce(sum) of the violation count per step" % world,
@@ -311,7 +313,8 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "peak_source": peak_src, "kernel": "k_r1cs_tiled" if args.kernel == "tiled" else "k_r1cs_rowwise",
-                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms_mean": k_ms,
+                         "algorithmic_bytes_per_launch": algo_bytes, "device_stream_bytes_per_launch": m.stream_bytes + 32 * g.n_cols,
+                         "kernel_ms_mean": k_ms,
                          "kernel_ms_min": min(kernel_ms) if kernel_ms else None},
             "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "call": "acg_r1cs_check_host",

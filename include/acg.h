@@ -81,8 +81,10 @@ const char* acg_last_error(const acg_ctx* ctx);
 int acg_ctx_create(int field_id, int device, acg_ctx** out);
 void acg_ctx_destroy(acg_ctx* ctx);
 int acg_ctx_set_check_kernel(acg_ctx* ctx, int which);
-/* Tiled kernel geometry (tuning): 0 = 128-row tiles, 7 CTAs per SM (default); 1 = 256-row tiles, 3 CTAs. */
+/* Tiled kernel tuning.  variant (bound to a system when it is uploaded): 0 = 128-row tiles (default),
+ * 1 = 256-row tiles.  stages: 1 = one tile buffer per CTA (default), 2 = prefetch the next tile's blob. */
 int acg_ctx_set_tiled_variant(acg_ctx* ctx, int variant);
+int acg_ctx_set_tiled_stages(acg_ctx* ctx, int stages);
 int acg_last_timing(const acg_ctx* ctx, acg_timing* out);
 /* Total launches of this library's kernels on this context since creation. */
 uint64_t acg_kernel_launch_count(const acg_ctx* ctx);
@@ -110,6 +112,9 @@ void acg_r1cs_free(acg_r1cs* m);
 /* Algorithmic bytes one check of this (shard of the) system reads: SURVEY.md 8(d) formula
  * sum_M [nnz_M*(32+4) + 4*(rows+1)] + 32*n_cols + 8. */
 uint64_t acg_r1cs_algorithmic_bytes(const acg_r1cs* m);
+/* Bytes of the device-side tile stream the tiled kernel actually reads per check (columns as tagged words,
+ * 16-bit row pointers, values of general coefficients only; +-1 coefficients are tags). */
+uint64_t acg_r1cs_stream_bytes(const acg_r1cs* m);
 
 /* w: n_cols canonical elements in qapSetToMap order (src/QAP.hs:605-620). */
 int acg_witness_upload(acg_ctx* ctx, const uint64_t* w, uint32_t n_cols, acg_vec** out);

@@ -20,19 +20,37 @@ def acg():
 
 
 @pytest.fixture(scope="session")
-def ctx_bn(acg):
+def _ctx_bn(acg):
     c = acg.Context(acg.BN254_FR, 0)
     yield c
     c.close()
 
 
 @pytest.fixture(scope="session")
-def ctx_bls(acg):
+def _ctx_bls(acg):
     c = acg.Context(acg.BLS12_381_FR, 0)
     yield c
     c.close()
 
 
-@pytest.fixture(scope="session")
+@pytest.fixture(params=[0, 1], ids=["tile128", "tile256"])
+def tile_variant(request):
+    """Every GPU test runs under both tile geometries of the tiled kernel (bound at upload time)."""
+    return request.param
+
+
+@pytest.fixture
+def ctx_bn(_ctx_bn, tile_variant):
+    _ctx_bn.set_tiled_variant(tile_variant)
+    return _ctx_bn
+
+
+@pytest.fixture
+def ctx_bls(_ctx_bls, tile_variant):
+    _ctx_bls.set_tiled_variant(tile_variant)
+    return _ctx_bls
+
+
+@pytest.fixture
 def ctxs(ctx_bn, ctx_bls):
     return {0: ctx_bn, 1: ctx_bls}
