@@ -374,7 +374,7 @@ int acg_ctx_set_check_kernel(acg_ctx* ctx, int which) {
 }
 
 int acg_ctx_set_tiled_variant(acg_ctx* ctx, int variant) {
-    if (!ctx || (variant != 0 && variant != 1)) return ACG_ERR_BAD_ARG;
+    if (!ctx || variant < 0 || variant >= kNumTileVariants) return ACG_ERR_BAD_ARG;
     ctx->tiled_variant = variant;
     return ACG_OK;
 }
@@ -567,11 +567,14 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     std::vector<uint8_t> stream;
     std::vector<uint32_t> offs, gval_offs;  // 16-byte units
     offs.reserve(tiles.size() + 1);
-    stream.reserve((size_t)n_local * 88 + 4096);
+    stream.reserve((size_t)n_local * 96 + 4096);
     auto align16 = [&]() { stream.resize((stream.size() + 15) & ~(size_t)15, 0); };
     auto put16 = [&](uint16_t v) {
         stream.push_back((uint8_t)(v & 0xFF));
         stream.push_back((uint8_t)(v >> 8));
+    };
+    auto put32 = [&](uint32_t v) {
+        for (int i = 0; i < 4; ++i) stream.push_back((uint8_t)(v >> (8 * i)));
     };
     for (const HostTile& t : tiles) {
         align16();
@@ -590,24 +593,22 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
             vstart += t.ne[k];
         }
         align16();
-        h.off_cols = (uint32_t)(stream.size() - base);
-        for (int k = 0; k < 3; ++k) {
-            const uint8_t* src8 = reinterpret_cast<const uint8_t*>(tagged_col[k].data() + t.e0[k]);
-            stream.insert(stream.end(), src8, src8 + 4ull * t.ne[k]);
-        }
-        align16();
-        h.off_list = (uint32_t)(stream.size() - base);
-        for (uint32_t want : {kTagGeneral, kTagMinusOne}) {
-            vstart = 0;
-            for (int k = 0; k < 3; ++k) {
-                for (uint32_t e = 0; e < t.ne[k]; ++e)
-                    if ((tagged_col[k][t.e0[k] + e] >> 30) == want) {
-                        put16((uint16_t)(vstart + e));
-                        (want == kTagGeneral ? h.n_general : h.n_minus) += 1;
-                    }
-                vstart += t.ne[k];
+        // entry words: +-1 entries keep their witness column, the j-th general entry carries j
+        h.off_words = (uint32_t)(stream.size() - base);
+        uint32_t j = 0;
+        for (int k = 0; k < 3; ++k)
+            for (uint32_t e = 0; e < t.ne[k]; ++e) {
+                const uint32_t word = tagged_col[k][t.e0[k] + e];
+                put32((word >> 30) == kTagGeneral ? ((kTagGeneral << 30) | j++) : word);
             }
-        }
+        h.n_general = j;
+        align16();
+        h.off_gcol = (uint32_t)(stream.size() - base);
+        for (int k = 0; k < 3; ++k)
+            for (uint32_t e = 0; e < t.ne[k]; ++e) {
+                const uint32_t word = tagged_col[k][t.e0[k] + e];
+                if ((word >> 30) == kTagGeneral) put32(word & kColMask);
+            }
         align16();
         h.off_gval = (uint32_t)(stream.size() - base);
         for (int k = 0; k < 3; ++k) {

@@ -29,37 +29,34 @@ struct DevR1cs {
 // ---- tile stream (tiled kernel) -------------------------------------------------------------------
 // The sparsity pattern and the coefficients are static, so upload lays the system out as a stream of
 // self-contained, execution-ready tile blobs; the kernel stages one blob per tile with a single TMA
-// bulk copy.  Blob = header | u16 row pointers (pool-relative, A then B then C, nrows+1 each) |
-// tagged column words of the pool entries (A rows, then B rows, then C rows) | u16 work list (pool
-// indices of the general-coefficient entries, then of the -1 entries) | general-coefficient values
-// (Montgomery, in work-list order).  Every section starts 16-byte aligned.
+// bulk copy.  Blob = header | u16 row pointers (pool-relative; A rows, B rows, C rows; nrows+1 each) |
+// entry words of the pool (A rows, then B rows, then C rows): tag<<30 | witness column for +-1
+// coefficients, tag<<30 | j for the j-th general-coefficient entry of the tile | u32 witness columns of
+// the general entries | their coefficient values (Montgomery).  Every section is 16-byte aligned.
 struct alignas(16) TileHeader {
     uint32_t row0;       // first (shard-local) row
     uint32_t nrows;
     uint32_t n_entries;  // pool entries E = nA + nB + nC
-    uint32_t n_general;  // work list [0, n_general): multiply by gval[j]
-    uint32_t n_minus;    // work list [n_general, n_general + n_minus): negate
+    uint32_t n_general;
     uint32_t off_rp;     // byte offsets inside the blob
-    uint32_t off_cols;
-    uint32_t off_list;
+    uint32_t off_words;
+    uint32_t off_gcol;
     uint32_t off_gval;
     uint32_t bytes;      // blob size (multiple of 16)
-    uint32_t pad[6];
+    uint32_t pad[7];
 };
 static_assert(sizeof(TileHeader) == 64, "TileHeader must be 64 bytes");
 
 // Tiled kernel geometry (see DESIGN.md "K2"); the variant is bound when the system is uploaded.
-//   variant 0: 128-thread CTAs, tiles of <= 128 rows / 640 entries / 176 general entries
-//   variant 1: 256-thread CTAs, tiles of <= 256 rows / 1344 entries / 384 general entries
 struct TileGeometry {
     uint32_t threads;   // == max rows per tile
-    uint32_t pool;      // A+B+C entries staged per tile
+    uint32_t pool;      // A+B+C entries per tile
     uint32_t max_gen;   // general-coefficient entries per tile
 };
-constexpr TileGeometry kTileGeom[2] = {{128, 640, 176}, {256, 1344, 384}};
+constexpr int kNumTileVariants = 4;
+constexpr TileGeometry kTileGeom[kNumTileVariants] = {{128, 768, 192}, {256, 1536, 384}, {64, 384, 96}, {32, 192, 64}};
 constexpr uint32_t tile_blob_capacity(const TileGeometry& g) {
-    return 64u + ((3u * (g.threads + 1u) * 2u + 15u) / 16u) * 16u + g.pool * 4u + ((g.pool * 2u + 15u) / 16u) * 16u +
-           g.max_gen * 32u;
+    return 64u + ((3u * (g.threads + 1u) * 2u + 15u) / 16u) * 16u + g.pool * 4u + g.max_gen * 4u + g.max_gen * 32u;
 }
 
 struct DevTileStream {

@@ -13,12 +13,16 @@
 //                           the tile's slices -- tagged columns and row pointers of A, B, C, the values
 //                           of the general-coefficient entries and their static index list -- into
 //                           shared memory; several CTAs per SM hide each other's load latency;
-//                    (P1)   thread per ENTRY: the witness element of every entry is gathered with
-//                           cp.async (LDGSTS, no register staging, all gathers of the tile in flight at
-//                           once) into two 16-byte planes (bank-conflict-free 128-bit accesses);
+//                    (P1)   the witness elements of the general-coefficient entries are gathered with
+//                           cp.async (LDGSTS, no register staging) into two 16-byte planes
+//                           (bank-conflict-free 128-bit accesses);
 //                    (P2)   one lane per general entry: the 256-bit Montgomery product, in place --
 //                           dense, no divergence between coefficient kinds;
-//                    (P3)   thread per row: signed sum of the row's terms, then the test a*b == c.
+//                    (P3)   thread per row: the three sums A.w, B.w, C.w advance together (independent
+//                           carry chains); +-1 terms are gathered from the witness straight into
+//                           registers, general terms come from the product planes; then a*b == c.
+//                    Shared memory holds only what is reused (blob + products), so occupancy is bounded
+//                    by registers, not by staging 32 bytes per entry.
 //                    The coefficient classification (+1 / -1 / general) lives in two tag bits of the
 //                    column word and is computed once at upload: the sparsity pattern is static, and the
 //                    32-byte encodings of +-1 never need to be re-read.  HBM traffic per check is one
@@ -143,17 +147,21 @@ namespace tiled {
 constexpr uint32_t align_up(uint32_t x, uint32_t a) {
     return (x + a - 1) / a * a;
 }
-// shared-memory layout of one CTA: STAGES blob buffers, then the two 16-byte term planes
+// shared-memory layout of one CTA: STAGES blob buffers, then the two 16-byte planes that hold the
+// products of the general-coefficient entries
 template <int V, int STAGES>
 struct Cfg {
     static constexpr uint32_t kThreads = kTileGeom[V].threads;
-    static constexpr uint32_t kPool = kTileGeom[V].pool;
+    static constexpr uint32_t kMaxGen = kTileGeom[V].max_gen;
     static constexpr uint32_t kBlobCap = align_up(tile_blob_capacity(kTileGeom[V]), 128);
     static constexpr uint32_t kOffLo = kBlobCap * STAGES;
-    static constexpr uint32_t kOffHi = kOffLo + kPool * 16;
-    static constexpr uint32_t kBytes = kOffHi + kPool * 16;
-    // CTAs per SM that fit 227 KB of shared memory (1 KB per CTA is reserved by the system)
-    static constexpr uint32_t kCtasPerSm = (227u * 1024u) / (kBytes + 1024u + 64u);
+    static constexpr uint32_t kOffHi = kOffLo + kMaxGen * 16;
+    static constexpr uint32_t kBytes = kOffHi + kMaxGen * 16;
+    // resident CTAs per SM: bounded by shared memory (227 KB, 1 KB per CTA reserved), by 64 registers per
+    // thread (1024 threads) and by the hardware limit of 32
+    static constexpr uint32_t kCtasBySmem = (227u * 1024u) / (kBytes + 1024u + 64u);
+    static constexpr uint32_t kCtasByRegs = 1024u / kThreads;
+    static constexpr uint32_t kCtasPerSm = kCtasBySmem < kCtasByRegs ? kCtasBySmem : kCtasByRegs;
 };
 
 // 2 x 16-byte asynchronous gather global -> shared (LDGSTS), no register staging
@@ -237,30 +245,22 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V, STAGES>::k
         mbar_wait(&full_bar[stage], (it / STAGES) & 1u);
 
         const TileHeader h = *reinterpret_cast<const TileHeader*>(blob);
-        const uint32_t* cols = reinterpret_cast<const uint32_t*>(blob + h.off_cols);
-        const uint16_t* list = reinterpret_cast<const uint16_t*>(blob + h.off_list);
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(blob + h.off_words);
+        const uint32_t* gcol = reinterpret_cast<const uint32_t*>(blob + h.off_gcol);
         const uint8_t* gval = blob + h.off_gval;
 
-        // ---- P1: gather the witness element of every entry, asynchronously, into the term planes
-        for (uint32_t e = tid; e < h.n_entries; e += C::kThreads)
-            cp_async_fr_planes(lo + e, hi + e, w + (cols[e] & kColMask));
+        // ---- P1: witness elements of the general-coefficient entries -> product planes, asynchronously
+        for (uint32_t j = tid; j < h.n_general; j += C::kThreads) cp_async_fr_planes(lo + j, hi + j, w + gcol[j]);
         cp_async_wait_all();
         __syncthreads();
 
-        // ---- P2: dense work list, one entry per lane: general coefficients multiply, -1 coefficients negate
-        const uint32_t n_work = h.n_general + h.n_minus;
-        for (uint32_t j = tid; j < n_work; j += C::kThreads) {
-            const uint32_t e = list[j];
-            const fr_t x = load_planes(lo, hi, e);
-            if (j < h.n_general) {
-                store_planes(lo, hi, e, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), x));
-            } else {
-                store_planes(lo, hi, e, neg_lazy<P>(x));
-            }
-        }
+        // ---- P2: dense 256-bit Montgomery products, one general entry per lane, in place
+        for (uint32_t j = tid; j < h.n_general; j += C::kThreads)
+            store_planes(lo, hi, j, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), load_planes(lo, hi, j)));
         __syncthreads();
 
-        // ---- P3: thread per row: three independent sums (A, B, C) advance together, then a*b == c
+        // ---- P3: thread per row: three independent sums (A, B, C) advance together; +-1 terms are gathered
+        //          straight from the witness into registers, general terms come from the product planes
         bool bad = false;
         if (tid < h.nrows) {
             const uint16_t* rp = reinterpret_cast<const uint16_t*>(blob + h.off_rp);
@@ -268,11 +268,22 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V, STAGES>::k
             uint32_t s0 = rp[tid], e0 = rp[tid + 1u];
             uint32_t s1 = rp[stride + tid], e1 = rp[stride + tid + 1u];
             uint32_t s2 = rp[2u * stride + tid], e2 = rp[2u * stride + tid + 1u];
+            auto term = [&](uint32_t idx) -> fr_t {
+                const uint32_t word = words[idx];
+                const uint32_t tag = word >> 30;
+                if (tag == kTagGeneral) return load_planes(lo, hi, word & kColMask);
+                const fr_t x = w[word & kColMask];
+                return tag == kTagMinusOne ? neg_lazy<P>(x) : x;
+            };
             fr_t a = fr_zero<P>(), b = fr_zero<P>(), c = fr_zero<P>();
             while (s0 < e0 || s1 < e1 || s2 < e2) {
-                if (s0 < e0) a = fr_add<P>(a, load_planes(lo, hi, s0));
-                if (s1 < e1) b = fr_add<P>(b, load_planes(lo, hi, s1));
-                if (s2 < e2) c = fr_add<P>(c, load_planes(lo, hi, s2));
+                fr_t ta, tb, tc;
+                if (s0 < e0) ta = term(s0);
+                if (s1 < e1) tb = term(s1);
+                if (s2 < e2) tc = term(s2);
+                if (s0 < e0) a = fr_add<P>(a, ta);
+                if (s1 < e1) b = fr_add<P>(b, tb);
+                if (s2 < e2) c = fr_add<P>(c, tc);
                 ++s0;
                 ++s1;
                 ++s2;
@@ -404,12 +415,23 @@ cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w,
         if (emit) ACG_TILED(true, VAR, STG); \
         ACG_TILED(false, VAR, STG);   \
     } while (0)
-    if (ts.variant == 1) {
-        if (stages == 2) ACG_TILED_VS(1, 2);
-        ACG_TILED_VS(1, 1);
-    } else {
-        if (stages == 2) ACG_TILED_VS(0, 2);
-        ACG_TILED_VS(0, 1);
+    switch (ts.variant) {
+        case 1:
+            if (stages == 2) ACG_TILED_VS(1, 2);
+            ACG_TILED_VS(1, 1);
+            break;
+        case 2:
+            if (stages == 2) ACG_TILED_VS(2, 2);
+            ACG_TILED_VS(2, 1);
+            break;
+        case 3:
+            if (stages == 2) ACG_TILED_VS(3, 2);
+            ACG_TILED_VS(3, 1);
+            break;
+        default:
+            if (stages == 2) ACG_TILED_VS(0, 2);
+            ACG_TILED_VS(0, 1);
+            break;
     }
 #undef ACG_TILED_VS
 #undef ACG_TILED

@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--field", default="bn254", choices=list(FIELD_IDS))
     ap.add_argument("--dense", action="store_true", help="all coefficients uniform (stress variant)")
     ap.add_argument("--kernel", default="tiled", choices=["tiled", "rowwise"])
-    ap.add_argument("--variant", type=int, default=0, choices=[0, 1], help="tiled kernel geometry (0: 128-row tiles)")
+    ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2, 3], help="tiled kernel geometry: rows per tile 128/256/64/32")
     ap.add_argument("--stages", type=int, default=1, choices=[1, 2], help="tiled kernel: 2 = prefetch next tile")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
