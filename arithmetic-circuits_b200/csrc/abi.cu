@@ -58,6 +58,7 @@ struct acg_r1cs {
     // execution-ready tile stream of the tiled kernel (kernels.h), built for geometry `variant`
     uint8_t* d_stream = nullptr;
     uint32_t* d_stream_off = nullptr;
+    uint2* d_windows = nullptr;
     uint64_t stream_bytes = 0;
     uint32_t n_tiles = 0;
     int variant = 0;
@@ -189,14 +190,21 @@ int upload_canonical(acg_ctx* ctx, fr_t* d, const uint64_t* host, uint64_t n) {
     return ACG_OK;
 }
 
-// Greedy tiling in groups of 4 rows (TMA needs 16-byte aligned row-pointer slices): a tile holds at most
-// geom.threads rows, geom.pool entries (A+B+C) and geom.max_gen general-coefficient entries.
-// gcum[k][r] = number of general entries of matrix k in local rows < r.
 struct HostTile {
-    uint32_t row0, nrows, e0[3], ne[3];
+    uint32_t row0, nrows, e0[3], ne[3], width[3];
 };
+// Greedy tiling in groups of 4 rows: a tile holds at most geom.threads rows and geom.max_gen
+// general-coefficient entries, and the sum of its three ELL widths (max row length per matrix) stays within
+// geom.max_slots.  Rows longer than kMaxEllWidth in any matrix (Split gates, src/QAP.hs:443-473) are left to
+// the row-wise kernel.  gcum[k][r] = number of general entries of matrix k in local rows < r.
 void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t* gcum[3], uint32_t n_local,
                  std::vector<HostTile>& tiles, std::vector<std::pair<uint32_t, uint32_t>>& long_ranges) {
+    auto add_long = [&](uint32_t a, uint32_t b) {
+        if (!long_ranges.empty() && long_ranges.back().second == a)
+            long_ranges.back().second = b;
+        else
+            long_ranges.emplace_back(a, b);
+    };
     uint32_t r = 0;
     while (r < n_local) {
         HostTile t{};
@@ -207,27 +215,41 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
             g_base += gcum[k][r];
         }
         uint32_t end = r;
+        uint32_t width[3] = {0, 0, 0};
+        bool hit_long = false;
         while (end < n_local && end - r < geom.threads) {
             const uint32_t g_end = std::min(end + 4u, n_local);
-            uint64_t tot = 0, gen = 0;
+            uint32_t nw[3] = {width[0], width[1], width[2]};
+            uint64_t gen = 0;
+            bool too_long = false;
             for (int k = 0; k < 3; ++k) {
-                tot += (uint64_t)rp[k][g_end] - t.e0[k];
+                for (uint32_t q = end; q < g_end; ++q) {
+                    const uint32_t len = rp[k][q + 1] - rp[k][q];
+                    if (len > kMaxEllWidth) too_long = true;
+                    nw[k] = std::max(nw[k], len);
+                }
                 gen += gcum[k][g_end];
             }
-            if (tot > (uint64_t)geom.pool || gen - g_base > (uint64_t)geom.max_gen) break;
+            if (too_long) {
+                hit_long = true;
+                break;
+            }
+            if (nw[0] + nw[1] + nw[2] > geom.max_slots || gen - g_base > (uint64_t)geom.max_gen) break;
+            for (int k = 0; k < 3; ++k) width[k] = nw[k];
             end = g_end;
         }
-        if (end == r) {  // a single 4-row group does not fit: the row-wise kernel handles it
+        if (end == r) {  // the next 4-row group cannot be tiled: the row-wise kernel handles it
+            (void)hit_long;
             const uint32_t g_end = std::min(r + 4u, n_local);
-            if (!long_ranges.empty() && long_ranges.back().second == r)
-                long_ranges.back().second = g_end;
-            else
-                long_ranges.emplace_back(r, g_end);
+            add_long(r, g_end);
             r = g_end;
             continue;
         }
         t.nrows = end - r;
-        for (int k = 0; k < 3; ++k) t.ne[k] = rp[k][end] - t.e0[k];
+        for (int k = 0; k < 3; ++k) {
+            t.ne[k] = rp[k][end] - t.e0[k];
+            t.width[k] = width[k];
+        }
         tiles.push_back(t);
         r = end;
     }
@@ -255,7 +277,7 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long 
     const bool prof = 2 * (ctx->prof_used + 1) <= ctx->prof_ev.size();
     if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
     if (m->n_tiles) {
-        DevTileStream ts{m->d_stream, m->d_stream_off, m->n_tiles, (uint32_t)m->variant};
+        DevTileStream ts{m->d_stream, m->d_stream_off, m->d_windows, m->n_tiles, (uint32_t)m->variant};
         CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin, d_result, Aw, Bw, Cw, ctx->sm_count,
                                   ctx->tiled_stages, s));
         ++*launches;
@@ -460,6 +482,7 @@ void acg_r1cs_free(acg_r1cs* m) {
     }
     cudaFree(m->d_stream);
     cudaFree(m->d_stream_off);
+    cudaFree(m->d_windows);
     delete m;
 }
 
@@ -559,7 +582,7 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     // tiles and their static lists of general entries (pool indices, uint16)
     const uint32_t* rp[3] = {local_rp[0].data(), local_rp[1].data(), local_rp[2].data()};
     const uint32_t* gc[3] = {gcum[0].data(), gcum[1].data(), gcum[2].data()};
-    // ---- tile stream (see kernels.h): one self-contained blob per tile
+    // ---- tile stream (see kernels.h): one self-contained blob per tile, entries in ELL order
     m->variant = ctx->tiled_variant;
     const TileGeometry geom = kTileGeom[m->variant];
     std::vector<HostTile> tiles;
@@ -569,14 +592,37 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     offs.reserve(tiles.size() + 1);
     stream.reserve((size_t)n_local * 96 + 4096);
     auto align16 = [&]() { stream.resize((stream.size() + 15) & ~(size_t)15, 0); };
-    auto put16 = [&](uint16_t v) {
-        stream.push_back((uint8_t)(v & 0xFF));
-        stream.push_back((uint8_t)(v >> 8));
-    };
     auto put32 = [&](uint32_t v) {
         for (int i = 0; i < 4; ++i) stream.push_back((uint8_t)(v >> (8 * i)));
     };
+    std::vector<uint32_t> gen_index;  // per tile: general ordinal of each (matrix, entry), row-major numbering
+    std::vector<uint2> windows;
+    std::vector<uint32_t> ref_cols;
+    windows.reserve(tiles.size());
     for (const HostTile& t : tiles) {
+        // witness window: the contiguous slice of geom.window elements that covers most references of the tile
+        ref_cols.clear();
+        for (int k = 0; k < 3; ++k)
+            for (uint32_t e = 0; e < t.ne[k]; ++e) ref_cols.push_back(tagged_col[k][t.e0[k] + e] & kColMask);
+        std::sort(ref_cols.begin(), ref_cols.end());
+        uint32_t win_n = std::min<uint32_t>(geom.window, n_cols), win_lo = 0;
+        {
+            size_t best = 0, lo_i = 0;
+            for (size_t hi_i = 0; hi_i < ref_cols.size(); ++hi_i) {
+                while (ref_cols[hi_i] - ref_cols[lo_i] >= win_n) ++lo_i;
+                if (hi_i - lo_i + 1 > best) {
+                    best = hi_i - lo_i + 1;
+                    win_lo = ref_cols[lo_i];
+                }
+            }
+            if (win_lo + win_n > n_cols) win_lo = n_cols - win_n;
+        }
+        windows.push_back(make_uint2(win_lo, win_n));
+        auto encode = [&](uint32_t word) -> uint32_t {  // tag | column  ->  tag | [window flag] | index
+            const uint32_t c = word & kColMask;
+            if (c >= win_lo && c - win_lo < win_n) return (word & 0xC0000000u) | kWinFlag | (c - win_lo);
+            return word;
+        };
         align16();
         const size_t base = stream.size();
         offs.push_back((uint32_t)(base / 16));
@@ -584,30 +630,50 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
         TileHeader h{};
         h.row0 = t.row0;
         h.nrows = t.nrows;
-        h.n_entries = t.ne[0] + t.ne[1] + t.ne[2];
-        // pool-relative row pointers: A rows, B rows, C rows, nrows + 1 each
-        h.off_rp = (uint32_t)(stream.size() - base);
-        uint32_t vstart = 0;
-        for (int k = 0; k < 3; ++k) {
-            for (uint32_t r = 0; r <= t.nrows; ++r) put16((uint16_t)(vstart + local_rp[k][t.row0 + r] - t.e0[k]));
-            vstart += t.ne[k];
-        }
-        align16();
-        // entry words: +-1 entries keep their witness column, the j-th general entry carries j
-        h.off_words = (uint32_t)(stream.size() - base);
-        uint32_t j = 0;
+        for (int k = 0; k < 3; ++k) h.width[k] = t.width[k];
+        h.win_lo = win_lo;
+        h.win_n = win_n;
+        // number the general entries of the tile (A rows, then B rows, then C rows, entry order)
+        uint32_t n_gen = 0;
         for (int k = 0; k < 3; ++k)
-            for (uint32_t e = 0; e < t.ne[k]; ++e) {
-                const uint32_t word = tagged_col[k][t.e0[k] + e];
-                put32((word >> 30) == kTagGeneral ? ((kTagGeneral << 30) | j++) : word);
+            for (uint32_t e = 0; e < t.ne[k]; ++e) n_gen += (tagged_col[k][t.e0[k] + e] >> 30) == kTagGeneral;
+        h.n_general = n_gen;
+        // entry words, slot-major
+        h.off_words = (uint32_t)(stream.size() - base);
+        uint32_t g_before = 0;  // generals of the matrices already emitted
+        for (int k = 0; k < 3; ++k) {
+            // general ordinal of the first entry of each row of this matrix
+            gen_index.assign((size_t)t.nrows + 1, 0);
+            uint32_t run = g_before;
+            for (uint32_t r = 0; r < t.nrows; ++r) {
+                gen_index[r] = run;
+                for (uint32_t e = local_rp[k][t.row0 + r]; e < local_rp[k][t.row0 + r + 1]; ++e)
+                    run += (tagged_col[k][e] >> 30) == kTagGeneral;
             }
-        h.n_general = j;
+            for (uint32_t j = 0; j < t.width[k]; ++j)
+                for (uint32_t r = 0; r < t.nrows; ++r) {
+                    const uint32_t s0 = local_rp[k][t.row0 + r], s1 = local_rp[k][t.row0 + r + 1];
+                    if (s0 + j >= s1) {
+                        put32((kTagPad << 30) | n_gen);
+                        continue;
+                    }
+                    const uint32_t word = tagged_col[k][s0 + j];
+                    if ((word >> 30) == kTagGeneral) {
+                        uint32_t ord = gen_index[r];
+                        for (uint32_t e = s0; e < s0 + j; ++e) ord += (tagged_col[k][e] >> 30) == kTagGeneral;
+                        put32((kTagGeneral << 30) | ord);
+                    } else {
+                        put32(encode(word));
+                    }
+                }
+            g_before = run;
+        }
         align16();
         h.off_gcol = (uint32_t)(stream.size() - base);
         for (int k = 0; k < 3; ++k)
             for (uint32_t e = 0; e < t.ne[k]; ++e) {
                 const uint32_t word = tagged_col[k][t.e0[k] + e];
-                if ((word >> 30) == kTagGeneral) put32(word & kColMask);
+                if ((word >> 30) == kTagGeneral) put32(encode(word & kColMask));
             }
         align16();
         h.off_gval = (uint32_t)(stream.size() - base);
@@ -633,6 +699,10 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     DevBuf d_goffs;
     CU(ctx, cudaMalloc(&m->d_stream, stream.size() + 64));
     CU(ctx, cudaMalloc(&m->d_stream_off, offs.size() * sizeof(uint32_t)));
+    CU(ctx, cudaMalloc(&m->d_windows, (windows.size() + 1) * sizeof(uint2)));
+    if (!windows.empty())
+        CU(ctx, cudaMemcpyAsync(m->d_windows, windows.data(), windows.size() * sizeof(uint2), cudaMemcpyHostToDevice,
+                                ctx->stream));
     CU(ctx, d_goffs.alloc(gval_offs.size() * sizeof(uint32_t)));
     CU(ctx, cudaMemcpyAsync(m->d_stream, stream.data(), stream.size(), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(m->d_stream_off, offs.data(), offs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,

@@ -11,7 +11,8 @@ namespace acg {
 // Column words carry a 2-bit coefficient tag in bits 31:30 when the system was preprocessed at upload
 // (DevR1cs::tagged): the sparsity pattern and the coefficients are static, so classifying them once is
 // free for every later check.
-constexpr uint32_t kColMask = 0x3FFFFFFFu;
+constexpr uint32_t kColMask = 0x1FFFFFFFu;   // witness columns are < 2^29
+constexpr uint32_t kWinFlag = 0x20000000u;   // tile stream only: the index is an offset into the tile's witness window
 constexpr uint32_t kTagPlusOne = 0u;   // coefficient == 1
 constexpr uint32_t kTagMinusOne = 1u;  // coefficient == r - 1
 constexpr uint32_t kTagGeneral = 2u;
@@ -29,39 +30,53 @@ struct DevR1cs {
 // ---- tile stream (tiled kernel) -------------------------------------------------------------------
 // The sparsity pattern and the coefficients are static, so upload lays the system out as a stream of
 // self-contained, execution-ready tile blobs; the kernel stages one blob per tile with a single TMA
-// bulk copy.  Blob = header | u16 row pointers (pool-relative; A rows, B rows, C rows; nrows+1 each) |
-// entry words of the pool (A rows, then B rows, then C rows): tag<<30 | witness column for +-1
-// coefficients, tag<<30 | j for the j-th general-coefficient entry of the tile | u32 witness columns of
-// the general entries | their coefficient values (Montgomery).  Every section is 16-byte aligned.
+// bulk copy, plus one more bulk copy of the tile's WITNESS WINDOW: the contiguous slice of w that most
+// of the tile's references fall into (for circuits built gate by gate: the wires defined just before /
+// by the tile's own rows).  Only references outside the window are gathered from global memory.
+// Blob = header | entry words in ELL (slot-major) order: for matrix A, then B, then C, for slot
+// j < width[k], for row r < nrows: one 32-bit word
+//        tag<<30 | [kWinFlag] | index    coefficient +1 (tag 0) or -1 (tag 1); index = witness column, or
+//                                        offset into the witness window when kWinFlag is set
+//        2<<30  | j                      j-th general-coefficient entry of the tile: its product slot
+//        3<<30  | n_general              padding (rows shorter than the tile's width): the zero slot
+//   | operand words of the general entries ([kWinFlag] | index) | their coefficient values (Montgomery).
+// Every section is 16-byte aligned.  Row r of the tile is handled by thread r, so slot-major order makes
+// every word read of a warp contiguous and the control flow of the row sums warp-uniform.
 struct alignas(16) TileHeader {
     uint32_t row0;       // first (shard-local) row
     uint32_t nrows;
-    uint32_t n_entries;  // pool entries E = nA + nB + nC
     uint32_t n_general;
-    uint32_t off_rp;     // byte offsets inside the blob
-    uint32_t off_words;
+    uint32_t width[3];   // ELL widths (max row length in the tile) of A, B, C
+    uint32_t off_words;  // byte offsets inside the blob
     uint32_t off_gcol;
     uint32_t off_gval;
     uint32_t bytes;      // blob size (multiple of 16)
-    uint32_t pad[7];
+    uint32_t win_lo;     // witness window [win_lo, win_lo + win_n)
+    uint32_t win_n;
+    uint32_t pad[4];
 };
 static_assert(sizeof(TileHeader) == 64, "TileHeader must be 64 bytes");
+constexpr uint32_t kTagPad = 3u;
 
 // Tiled kernel geometry (see DESIGN.md "K2"); the variant is bound when the system is uploaded.
 struct TileGeometry {
-    uint32_t threads;   // == max rows per tile
-    uint32_t pool;      // A+B+C entries per tile
-    uint32_t max_gen;   // general-coefficient entries per tile
+    uint32_t threads;    // == max rows per tile
+    uint32_t max_slots;  // sum of the three ELL widths (rows longer than kMaxEllWidth go to the row-wise kernel)
+    uint32_t max_gen;    // general-coefficient entries per tile
+    uint32_t window;     // witness elements staged per tile
 };
+constexpr uint32_t kMaxEllWidth = 8;
 constexpr int kNumTileVariants = 4;
-constexpr TileGeometry kTileGeom[kNumTileVariants] = {{128, 768, 192}, {256, 1536, 384}, {64, 384, 96}, {32, 192, 64}};
+constexpr TileGeometry kTileGeom[kNumTileVariants] = {
+    {128, 12, 192, 192}, {256, 12, 384, 320}, {64, 12, 96, 128}, {32, 12, 64, 96}};
 constexpr uint32_t tile_blob_capacity(const TileGeometry& g) {
-    return 64u + ((3u * (g.threads + 1u) * 2u + 15u) / 16u) * 16u + g.pool * 4u + g.max_gen * 4u + g.max_gen * 32u;
+    return 64u + g.threads * g.max_slots * 4u + g.max_gen * 4u + g.max_gen * 32u;
 }
 
 struct DevTileStream {
     const uint8_t* blobs;      // concatenated tile blobs
     const uint32_t* offsets;   // n_tiles + 1 offsets in 16-byte units
+    const uint2* windows;      // per tile {win_lo, win_n}
     uint32_t n_tiles;
     uint32_t variant;
 };

@@ -13,14 +13,14 @@
 //                           the tile's slices -- tagged columns and row pointers of A, B, C, the values
 //                           of the general-coefficient entries and their static index list -- into
 //                           shared memory; several CTAs per SM hide each other's load latency;
-//                    (P1)   the witness elements of the general-coefficient entries are gathered with
-//                           cp.async (LDGSTS, no register staging) into two 16-byte planes
-//                           (bank-conflict-free 128-bit accesses);
-//                    (P2)   one lane per general entry: the 256-bit Montgomery product, in place --
-//                           dense, no divergence between coefficient kinds;
-//                    (P3)   thread per row: the three sums A.w, B.w, C.w advance together (independent
-//                           carry chains); +-1 terms are gathered from the witness straight into
-//                           registers, general terms come from the product planes; then a*b == c.
+//                           plus a second bulk copy of the tile's WITNESS WINDOW, the contiguous slice of
+//                           w most references of the tile fall into;
+//                    (P2)   one lane per general entry: the 256-bit Montgomery product -- dense, no
+//                           divergence between coefficient kinds;
+//                    (P3)   thread per row over the tile's ELL (slot-major, padded) entry words: the three
+//                           sums A.w, B.w, C.w advance together with warp-uniform control flow; +-1 terms
+//                           are gathered from the witness straight into registers, general terms come
+//                           from the product planes (one generic-address load path); then a*b == c.
 //                    Shared memory holds only what is reused (blob + products), so occupancy is bounded
 //                    by registers, not by staging 32 bytes per entry.
 //                    The coefficient classification (+1 / -1 / general) lives in two tag bits of the
@@ -147,16 +147,17 @@ namespace tiled {
 constexpr uint32_t align_up(uint32_t x, uint32_t a) {
     return (x + a - 1) / a * a;
 }
-// shared-memory layout of one CTA: STAGES blob buffers, then the two 16-byte planes that hold the
-// products of the general-coefficient entries
+// shared-memory layout of one CTA: STAGES x (blob buffer + witness window), then the products of the
+// general-coefficient entries (+ the zero slot padding words point at)
 template <int V, int STAGES>
 struct Cfg {
     static constexpr uint32_t kThreads = kTileGeom[V].threads;
     static constexpr uint32_t kMaxGen = kTileGeom[V].max_gen;
     static constexpr uint32_t kBlobCap = align_up(tile_blob_capacity(kTileGeom[V]), 128);
-    static constexpr uint32_t kOffLo = kBlobCap * STAGES;
-    static constexpr uint32_t kOffHi = kOffLo + kMaxGen * 16;
-    static constexpr uint32_t kBytes = kOffHi + kMaxGen * 16;
+    static constexpr uint32_t kWinBytes = kTileGeom[V].window * 32;
+    static constexpr uint32_t kStageBytes = kBlobCap + kWinBytes;
+    static constexpr uint32_t kOffProd = kStageBytes * STAGES;
+    static constexpr uint32_t kBytes = kOffProd + (kMaxGen + 1) * 32;
     // resident CTAs per SM: bounded by shared memory (227 KB, 1 KB per CTA reserved), by 64 registers per
     // thread (1024 threads) and by the hardware limit of 32
     static constexpr uint32_t kCtasBySmem = (227u * 1024u) / (kBytes + 1024u + 64u);
@@ -202,12 +203,15 @@ __device__ __forceinline__ fr_t neg_lazy(const fr_t& x) {
     r.l[7] = ptx::subc(P::p(7), x.l[7]);
     return r;
 }
-// one thread: one bulk copy of the whole tile blob
-__device__ __forceinline__ void issue_blob_load(const DevTileStream& ts, uint32_t tile, uint8_t* dst, uint64_t* bar) {
+// one thread: bulk copies of the tile blob and of the tile's witness window
+__device__ __forceinline__ void issue_blob_load(const DevTileStream& ts, const fr_t* __restrict__ w, uint32_t tile,
+                                                uint8_t* dst, uint32_t blob_cap, uint64_t* bar) {
     const uint32_t o0 = ts.offsets[tile], o1 = ts.offsets[tile + 1];
     const uint32_t bytes = (o1 - o0) * 16u;
-    mbar_arrive_expect_tx(bar, bytes);
+    const uint2 win = ts.windows[tile];  // {win_lo, win_n}
+    mbar_arrive_expect_tx(bar, bytes + win.y * 32u);
     tma_load_1d(dst, ts.blobs + (size_t)o0 * 16u, bytes, bar);
+    if (win.y) tma_load_1d(dst + blob_cap, w + win.x, win.y * 32u, bar);
 }
 }  // namespace tiled
 
@@ -230,18 +234,19 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V, STAGES>::k
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0 && blockIdx.x < n_tiles) issue_blob_load(ts, blockIdx.x, smem, &full_bar[0]);
+    if (tid == 0 && blockIdx.x < n_tiles) issue_blob_load(ts, w, blockIdx.x, smem, C::kBlobCap, &full_bar[0]);
 
-    uint4* lo = reinterpret_cast<uint4*>(smem + C::kOffLo);
-    uint4* hi = reinterpret_cast<uint4*>(smem + C::kOffHi);
+    uint4* prod = reinterpret_cast<uint4*>(smem + C::kOffProd);  // 32-byte product slots
 
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t stage = it % STAGES;
-        const uint8_t* blob = smem + (size_t)stage * C::kBlobCap;
+        const uint8_t* blob = smem + (size_t)stage * C::kStageBytes;
+        const uint4* win = reinterpret_cast<const uint4*>(blob + C::kBlobCap);
         if (STAGES == 2 && tid == 0 && tile + gridDim.x < n_tiles)  // prefetch: that buffer was released by the
-            issue_blob_load(ts, tile + gridDim.x,                   // barrier that ended the previous tile
-                            smem + (size_t)((it + 1) % STAGES) * C::kBlobCap, &full_bar[(it + 1) % STAGES]);
+            issue_blob_load(ts, w, tile + gridDim.x,                // barrier that ended the previous tile
+                            smem + (size_t)((it + 1) % STAGES) * C::kStageBytes, C::kBlobCap,
+                            &full_bar[(it + 1) % STAGES]);
         mbar_wait(&full_bar[stage], (it / STAGES) & 1u);
 
         const TileHeader h = *reinterpret_cast<const TileHeader*>(blob);
@@ -249,44 +254,59 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V, STAGES>::k
         const uint32_t* gcol = reinterpret_cast<const uint32_t*>(blob + h.off_gcol);
         const uint8_t* gval = blob + h.off_gval;
 
-        // ---- P1: witness elements of the general-coefficient entries -> product planes, asynchronously
-        for (uint32_t j = tid; j < h.n_general; j += C::kThreads) cp_async_fr_planes(lo + j, hi + j, w + gcol[j]);
-        cp_async_wait_all();
+        // ---- P2: dense 256-bit Montgomery products, one general entry per lane: operand from the witness
+        //          window (shared memory) or one 256-bit global load
+        for (uint32_t j = tid; j < h.n_general; j += C::kThreads) {
+            const uint32_t gw = gcol[j];
+            const uint4* gsrc = reinterpret_cast<const uint4*>(w + (gw & kColMask));
+            const uint4* src = (gw & kWinFlag) ? win + 2u * (gw & kColMask) : gsrc;
+            const uint4 a4 = src[0], b4 = src[1];
+            fr_t x;
+            x.l[0] = a4.x; x.l[1] = a4.y; x.l[2] = a4.z; x.l[3] = a4.w;
+            x.l[4] = b4.x; x.l[5] = b4.y; x.l[6] = b4.z; x.l[7] = b4.w;
+            const fr_t pr = fr_mul<P>(load_fr16(gval + (size_t)j * 32u), x);
+            prod[2u * j] = make_uint4(pr.l[0], pr.l[1], pr.l[2], pr.l[3]);
+            prod[2u * j + 1u] = make_uint4(pr.l[4], pr.l[5], pr.l[6], pr.l[7]);
+        }
+        if (tid == 0) {  // the zero slot that padding words reference
+            prod[2u * h.n_general] = make_uint4(0u, 0u, 0u, 0u);
+            prod[2u * h.n_general + 1u] = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncthreads();
 
-        // ---- P2: dense 256-bit Montgomery products, one general entry per lane, in place
-        for (uint32_t j = tid; j < h.n_general; j += C::kThreads)
-            store_planes(lo, hi, j, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), load_planes(lo, hi, j)));
-        __syncthreads();
-
-        // ---- P3: thread per row: three independent sums (A, B, C) advance together; +-1 terms are gathered
-        //          straight from the witness into registers, general terms come from the product planes
+        // ---- P3: thread per row, warp-uniform: the sums A.w, B.w, C.w advance together slot by slot.  A term
+        //          is loaded through one generic address that points into the witness window or the product
+        //          slots (shared memory) or, for far references, into the witness in global memory; a -1
+        //          coefficient negates under a predicate.
         bool bad = false;
         if (tid < h.nrows) {
-            const uint16_t* rp = reinterpret_cast<const uint16_t*>(blob + h.off_rp);
-            const uint32_t stride = h.nrows + 1u;
-            uint32_t s0 = rp[tid], e0 = rp[tid + 1u];
-            uint32_t s1 = rp[stride + tid], e1 = rp[stride + tid + 1u];
-            uint32_t s2 = rp[2u * stride + tid], e2 = rp[2u * stride + tid + 1u];
-            auto term = [&](uint32_t idx) -> fr_t {
-                const uint32_t word = words[idx];
-                const uint32_t tag = word >> 30;
-                if (tag == kTagGeneral) return load_planes(lo, hi, word & kColMask);
-                const fr_t x = w[word & kColMask];
-                return tag == kTagMinusOne ? neg_lazy<P>(x) : x;
+            auto term = [&](uint32_t word) -> fr_t {
+                const uint32_t idx = word & kColMask;
+                const uint4* src = reinterpret_cast<const uint4*>(w + idx);
+                if (word & kWinFlag) src = win + 2u * idx;
+                if (word >> 31) src = prod + 2u * idx;  // tags 2 (general) and 3 (padding)
+                const uint4 a4 = src[0], b4 = src[1];
+                fr_t x;
+                x.l[0] = a4.x; x.l[1] = a4.y; x.l[2] = a4.z; x.l[3] = a4.w;
+                x.l[4] = b4.x; x.l[5] = b4.y; x.l[6] = b4.z; x.l[7] = b4.w;
+                if ((word >> 30) == kTagMinusOne) x = neg_lazy<P>(x);
+                return x;
             };
+            const uint32_t wA = h.width[0], wB = h.width[1], wC = h.width[2];
+            const uint32_t* pa = words + tid;
+            const uint32_t* pb = pa + wA * h.nrows;
+            const uint32_t* pc = pb + wB * h.nrows;
+            const uint32_t wmax = max(wA, max(wB, wC));
             fr_t a = fr_zero<P>(), b = fr_zero<P>(), c = fr_zero<P>();
-            while (s0 < e0 || s1 < e1 || s2 < e2) {
+            for (uint32_t j = 0; j < wmax; ++j) {  // trip count and the three predicates are warp-uniform
+                const bool ua = j < wA, ub = j < wB, uc = j < wC;
                 fr_t ta, tb, tc;
-                if (s0 < e0) ta = term(s0);
-                if (s1 < e1) tb = term(s1);
-                if (s2 < e2) tc = term(s2);
-                if (s0 < e0) a = fr_add<P>(a, ta);
-                if (s1 < e1) b = fr_add<P>(b, tb);
-                if (s2 < e2) c = fr_add<P>(c, tc);
-                ++s0;
-                ++s1;
-                ++s2;
+                if (ua) ta = term(pa[j * h.nrows]);
+                if (ub) tb = term(pb[j * h.nrows]);
+                if (uc) tc = term(pc[j * h.nrows]);
+                if (ua) a = fr_add<P>(a, ta);
+                if (ub) b = fr_add<P>(b, tb);
+                if (uc) c = fr_add<P>(c, tc);
             }
             if (EMIT) {
                 const uint32_t row = h.row0 + tid;
@@ -303,7 +323,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V, STAGES>::k
         fence_proxy_async_smem();
         __syncthreads();
         if (STAGES == 1 && tid == 0 && tile + gridDim.x < n_tiles)
-            issue_blob_load(ts, tile + gridDim.x, smem, &full_bar[0]);
+            issue_blob_load(ts, w, tile + gridDim.x, smem, C::kBlobCap, &full_bar[0]);
     }
 }
 

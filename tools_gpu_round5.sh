@@ -9,4 +9,4 @@ import sys,json
 j=json.loads(sys.stdin.read())
 print({k:j[k] for k in ('value','ms_per_step')}, 'roofline', round(j['roofline']['frac'],4), 'kernel_ms', round(j['roofline']['kernel_ms_mean'],4), 'stream MB', round(j['roofline']['device_stream_bytes_per_launch']/1e6,1))
 "; done
-echo "=== ncu v3"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_r1cs_tiled -s 3 -c 1 -o gpurun_out/prof_tiled_v6_var0 -f python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 --variant 0 > gpurun_out/ncu_full_a.log 2>&1; tail -1 gpurun_out/ncu_full_a.log
+echo "=== ncu v3"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_r1cs_tiled -s 3 -c 1 -o gpurun_out/prof_tiled_v8_var0 -f python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 --variant 0 > gpurun_out/ncu_full_a.log 2>&1; tail -1 gpurun_out/ncu_full_a.log
