@@ -298,6 +298,16 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peak, peak_src, sm_max = measured_peaks()
+        # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of this same command
+        # (profiles/r01_ncu_summary.json; never measured under the profiler here), only for the default workload
+        traffic = None
+        if args.log_rows == 20 and args.field == "bn254" and not args.dense and args.kernel == "tiled":
+            try:
+                with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as f:
+                    k2 = json.load(f)["k2_r1cs_tiled"][0]
+                traffic = (float(k2["dram__bytes_read.sum"]) + float(k2["dram__bytes_write.sum"])) * 1e6
+            except Exception:
+                traffic = None
         k_ms = statistics.mean(kernel_ms) if kernel_ms else float("nan")
         achieved = algo_bytes / (k_ms * 1e-3) / 1e9 if kernel_ms else None
         line = {
@@ -311,7 +321,7 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": "rows sharded over %d rank(s), 1 all-reduce(sum) of the violation count per step" % world,
                        "setup_s": {"generate": round(t_gen, 2)}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "k_r1cs_tiled" if args.kernel == "tiled" else "k_r1cs_rowwise",
                          "algorithmic_bytes_per_launch": algo_bytes, "device_stream_bytes_per_launch": m.stream_bytes + 32 * g.n_cols,
                          "kernel_ms_mean": k_ms,

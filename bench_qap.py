@@ -1,0 +1,103 @@
+#!/usr/bin/env python3
+"""Secondary measurements (not the driver's bench contract): BASELINE configs[2] -- the QAP build on one GPU.
+
+  * isolated 2^k-point Fr NTT, device resident (acg_ntt_device), CUDA events
+  * acg_qap_witness on S(2^k): R1CS eval + 3 iNTT + coset NTTs + quotient + iNTT  (kernel time of the call)
+  * the C oracle's NTT / coset quotient on the host cores beside it
+
+    python bench_qap.py [--log-n 22] [--field bn254] [--reps 5]
+Prints one JSON line per measurement."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--log-n", type=int, default=22)
+    ap.add_argument("--field", default="bn254", choices=["bn254", "bls12_381"])
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    import arithmetic_circuits_b200 as acg
+
+    fid = {"bn254": 0, "bls12_381": 1}[args.field]
+    n = 1 << args.log_n
+    ctx = acg.Context(fid, 0)
+    rng = np.random.default_rng(1)
+    v = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    v[:, 3] &= np.uint64((1 << 60) - 1)
+    dv = ctx.upload_witness(v)
+    stream = torch.cuda.current_stream()
+    L = acg._lib.lib()
+    import ctypes as C
+
+    def ntt_dev(inverse):
+        acg.qap._check(L.acg_ntt_device(ctx._h, dv._h, args.log_n, int(inverse), C.c_void_p(stream.cuda_stream)), ctx)
+
+    for inverse in (False, True):
+        for _ in range(2):
+            ntt_dev(inverse)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(args.reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ntt_dev(inverse)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        best = min(ms)
+        butterflies = (n // 2) * args.log_n
+        print(json.dumps({"what": "ntt_device", "field": args.field, "log_n": args.log_n, "inverse": inverse,
+                          "ms_best": best, "ms_all": ms, "points_per_s": n / (best * 1e-3),
+                          "modmul_per_s": butterflies / (best * 1e-3),
+                          "hbm_floor_ms_one_pass": 64 * n / 6548.2e9 * 1e3,
+                          "note": "natural->natural: DIF passes + bit-reversal permutation + copy"}), flush=True)
+
+    # QAP witness on the synthetic family
+    g, w = acg.synth_r1cs(fid, n, 20260003)
+    m, dw = ctx.upload_r1cs(g), ctx.upload_witness(w)
+    ctx.qap_witness(m, dw, want=("h",))  # warm-up: plans, coset tables
+    ks = []
+    for _ in range(max(2, args.reps // 2)):
+        t0 = time.perf_counter()
+        bufs, ok = ctx.qap_witness(m, dw, want=("h",))
+        wall = time.perf_counter() - t0
+        ks.append((ctx.last_timing()["kernel_ms"], wall * 1e3, ctx.last_timing()["kernel_launches"]))
+        assert ok
+    kbest = min(k[0] for k in ks)
+    print(json.dumps({"what": "qap_witness", "field": args.field, "log_n": args.log_n, "kernel_ms_best": kbest,
+                      "wall_ms_best": min(k[1] for k in ks), "kernel_launches": ks[0][2],
+                      "constraints_per_s_kernels": n / (kbest * 1e-3),
+                      "note": "R1CS eval + 3 iNTT + 3 coset NTT + quotient + iNTT; wall includes D2H of h (%.0f MB)" % (32 * (n + 1) / 1e6)}),
+          flush=True)
+    if not args.no_cpu:
+        from oracle import c_oracle as CO
+        CO.build()
+        th = CO.max_threads()
+        t0 = time.perf_counter()
+        CO.ntt(fid, v, True, th)
+        t_ntt = time.perf_counter() - t0
+        ref = CO.r1cs_eval_check(fid, g.n_rows, g.n_cols, *[(x[0], x[1], x[2]) for x in g.mats], w, True, th)
+        t0 = time.perf_counter()
+        a, b, c, h, okc = CO.qap_witness(fid, ref["Aw"], ref["Bw"], ref["Cw"], (0, 0, 0), th)
+        t_qap = time.perf_counter() - t0
+        same = bool((bufs["h"] == h).all())
+        print(json.dumps({"what": "cpu_oracle", "field": args.field, "log_n": args.log_n, "threads": th,
+                          "intt_ms": t_ntt * 1e3, "qap_witness_ms": t_qap * 1e3, "h_bit_exact_vs_gpu": same}), flush=True)
+        assert same and okc
+
+
+if __name__ == "__main__":
+    main()
