@@ -62,6 +62,13 @@ def workload_name(args, world):
         1 << args.log_rows)
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -157,7 +164,7 @@ def run_reference(args, rank, world):
     seed = SEEDS.get(args.log_rows, 20260000 + args.log_rows)
     # the bounded sample: rank 0's shard of the global system (all of it at N = 1)
     g, w = acg.synth_r1cs(field_id, total, seed, args.dense, rows=(0, n))
-    threads = CO.max_threads()
+    threads = host_threads()   # torchrun exports OMP_NUM_THREADS=1: ask for every host thread explicitly
     mats = [(m[0], m[1], m[2]) for m in g.mats]
     for _ in range(max(1, min(args.warmup, 3))):
         CO.r1cs_eval_check(field_id, g.n_rows, g.n_cols, *mats, w, False, threads)
@@ -301,7 +308,7 @@ def run_ours(args, rank, world, local_rank):
         # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of this same command
         # (profiles/r01_ncu_summary.json; never measured under the profiler here), only for the default workload
         traffic = None
-        if args.log_rows == 20 and args.field == "bn254" and not args.dense and args.kernel == "tiled":
+        if world == 1 and args.log_rows == 20 and args.field == "bn254" and not args.dense and args.kernel == "tiled":
             try:
                 with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as f:
                     k2 = json.load(f)["k2_r1cs_tiled"][0]
@@ -335,7 +342,7 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu_baseline:
             from oracle import c_oracle as CO
             CO.build()
-            threads = CO.max_threads()
+            threads = host_threads()
             v_all, times = cpu_check_throughput(g, w, field_id, threads, 6.0, 20)
             v_one, _ = cpu_check_throughput(g, w, field_id, 1, 4.0, 5)
             line["cpu_baseline"] = {"value": v_all, "unit": "constraints/s", "cores": threads, "kind": "port",
