@@ -33,7 +33,6 @@ PROTOTYPES = {
     "acg_ctx_destroy": (None, [vp]),
     "acg_ctx_set_check_kernel": (C.c_int, [vp, C.c_int]),
     "acg_ctx_set_tiled_variant": (C.c_int, [vp, C.c_int]),
-    "acg_ctx_set_tiled_stages": (C.c_int, [vp, C.c_int]),
     "acg_r1cs_stream_bytes": (C.c_uint64, [vp]),
     "acg_last_timing": (C.c_int, [vp, C.POINTER(AcgTiming)]),
     "acg_kernel_launch_count": (C.c_uint64, [vp]),

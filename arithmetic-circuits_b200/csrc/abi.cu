@@ -26,7 +26,6 @@ struct acg_ctx {
     int sm_count = 148;
     int check_kernel = ACG_CHECK_AUTO;
     int tiled_variant = 0;  // index into kTileGeom, bound to a system at upload
-    int tiled_stages = 1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* d_result = nullptr;  // {n_violations, first_bad_row}
@@ -278,8 +277,7 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long 
     if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
     if (m->n_tiles) {
         DevTileStream ts{m->d_stream, m->d_stream_off, m->d_windows, m->n_tiles, (uint32_t)m->variant};
-        CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin, d_result, Aw, Bw, Cw, ctx->sm_count,
-                                  ctx->tiled_stages, s));
+        CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin, d_result, Aw, Bw, Cw, ctx->sm_count, s));
         ++*launches;
     }
     if (prof) {
@@ -401,11 +399,6 @@ int acg_ctx_set_tiled_variant(acg_ctx* ctx, int variant) {
     return ACG_OK;
 }
 
-int acg_ctx_set_tiled_stages(acg_ctx* ctx, int stages) {
-    if (!ctx || (stages != 1 && stages != 2)) return ACG_ERR_BAD_ARG;
-    ctx->tiled_stages = stages;
-    return ACG_OK;
-}
 
 int acg_last_timing(const acg_ctx* ctx, acg_timing* out) {
     if (!ctx || !out) return ACG_ERR_BAD_ARG;
@@ -589,23 +582,31 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     build_tiles(geom, rp, gc, n_local, tiles, m->long_ranges);
     std::vector<uint8_t> stream;
     std::vector<uint32_t> offs, gval_offs;  // 16-byte units
-    offs.reserve(tiles.size() + 1);
+    std::vector<uint2> windows;
     stream.reserve((size_t)n_local * 96 + 4096);
     auto align16 = [&]() { stream.resize((stream.size() + 15) & ~(size_t)15, 0); };
+    auto put16 = [&](uint16_t v) {
+        stream.push_back((uint8_t)(v & 0xFF));
+        stream.push_back((uint8_t)(v >> 8));
+    };
     auto put32 = [&](uint32_t v) {
         for (int i = 0; i < 4; ++i) stream.push_back((uint8_t)(v >> (8 * i)));
     };
-    std::vector<uint32_t> gen_index;  // per tile: general ordinal of each (matrix, entry), row-major numbering
-    std::vector<uint2> windows;
-    std::vector<uint32_t> ref_cols;
-    windows.reserve(tiles.size());
-    for (const HostTile& t : tiles) {
+    const uint32_t kProd0 = geom.window + geom.max_far, kZero = tile_term_slots(geom) - 1u;
+    std::vector<uint32_t> ref_cols, far_cols;
+    // a tile whose distinct far references exceed the far slots is split in two (rows stay multiples of 4)
+    std::vector<HostTile> work(tiles.rbegin(), tiles.rend());
+    uint32_t n_tiles_out = 0;
+    while (!work.empty()) {
+        HostTile t = work.back();
+        work.pop_back();
         // witness window: the contiguous slice of geom.window elements that covers most references of the tile
         ref_cols.clear();
         for (int k = 0; k < 3; ++k)
             for (uint32_t e = 0; e < t.ne[k]; ++e) ref_cols.push_back(tagged_col[k][t.e0[k] + e] & kColMask);
         std::sort(ref_cols.begin(), ref_cols.end());
-        uint32_t win_n = std::min<uint32_t>(geom.window, n_cols), win_lo = 0;
+        const uint32_t win_n = std::min<uint32_t>(geom.window, n_cols);
+        uint32_t win_lo = 0;
         {
             size_t best = 0, lo_i = 0;
             for (size_t hi_i = 0; hi_i < ref_cols.size(); ++hi_i) {
@@ -617,36 +618,57 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
             }
             if (win_lo + win_n > n_cols) win_lo = n_cols - win_n;
         }
-        windows.push_back(make_uint2(win_lo, win_n));
-        auto encode = [&](uint32_t word) -> uint32_t {  // tag | column  ->  tag | [window flag] | index
-            const uint32_t c = word & kColMask;
-            if (c >= win_lo && c - win_lo < win_n) return (word & 0xC0000000u) | kWinFlag | (c - win_lo);
-            return word;
+        far_cols.clear();
+        for (uint32_t c : ref_cols)
+            if ((c < win_lo || c - win_lo >= win_n) && (far_cols.empty() || far_cols.back() != c)) far_cols.push_back(c);
+        if (far_cols.size() > geom.max_far && t.nrows > 4) {
+            const uint32_t half = ((t.nrows / 2 + 3) / 4) * 4;
+            HostTile lo_t{}, hi_t{};
+            lo_t.row0 = t.row0;
+            lo_t.nrows = half;
+            hi_t.row0 = t.row0 + half;
+            hi_t.nrows = t.nrows - half;
+            for (HostTile* q : {&lo_t, &hi_t})
+                for (int k = 0; k < 3; ++k) {
+                    q->e0[k] = rp[k][q->row0];
+                    q->ne[k] = rp[k][q->row0 + q->nrows] - q->e0[k];
+                    q->width[k] = 0;
+                    for (uint32_t r = q->row0; r < q->row0 + q->nrows; ++r)
+                        q->width[k] = std::max(q->width[k], rp[k][r + 1] - rp[k][r]);
+                }
+            work.push_back(hi_t);
+            work.push_back(lo_t);
+            continue;
+        }
+        if (far_cols.size() > geom.max_far) {  // 4 rows with more distinct far columns than slots: row-wise kernel
+            m->long_ranges.emplace_back(t.row0, t.row0 + t.nrows);
+            continue;
+        }
+        auto slot_of = [&](uint32_t c) -> uint32_t {  // witness column -> term slot
+            if (c >= win_lo && c - win_lo < win_n) return c - win_lo;
+            return geom.window + (uint32_t)(std::lower_bound(far_cols.begin(), far_cols.end(), c) - far_cols.begin());
         };
         align16();
         const size_t base = stream.size();
         offs.push_back((uint32_t)(base / 16));
+        windows.push_back(make_uint2(win_lo, win_n));
+        ++n_tiles_out;
         stream.resize(base + sizeof(TileHeader), 0);
         TileHeader h{};
         h.row0 = t.row0;
         h.nrows = t.nrows;
-        for (int k = 0; k < 3; ++k) h.width[k] = t.width[k];
         h.win_lo = win_lo;
         h.win_n = win_n;
-        // number the general entries of the tile (A rows, then B rows, then C rows, entry order)
-        uint32_t n_gen = 0;
-        for (int k = 0; k < 3; ++k)
-            for (uint32_t e = 0; e < t.ne[k]; ++e) n_gen += (tagged_col[k][t.e0[k] + e] >> 30) == kTagGeneral;
-        h.n_general = n_gen;
-        // entry words, slot-major
+        h.n_far = (uint32_t)far_cols.size();
+        for (int k = 0; k < 3; ++k) h.width[k] = t.width[k];
+        // entry words, slot-major; general entries are numbered A rows, then B rows, then C rows, entry order
         h.off_words = (uint32_t)(stream.size() - base);
-        uint32_t g_before = 0;  // generals of the matrices already emitted
+        uint32_t g_before = 0;
+        std::vector<uint32_t> gen_first((size_t)t.nrows + 1);
         for (int k = 0; k < 3; ++k) {
-            // general ordinal of the first entry of each row of this matrix
-            gen_index.assign((size_t)t.nrows + 1, 0);
             uint32_t run = g_before;
             for (uint32_t r = 0; r < t.nrows; ++r) {
-                gen_index[r] = run;
+                gen_first[r] = run;
                 for (uint32_t e = local_rp[k][t.row0 + r]; e < local_rp[k][t.row0 + r + 1]; ++e)
                     run += (tagged_col[k][e] >> 30) == kTagGeneral;
             }
@@ -654,26 +676,31 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
                 for (uint32_t r = 0; r < t.nrows; ++r) {
                     const uint32_t s0 = local_rp[k][t.row0 + r], s1 = local_rp[k][t.row0 + r + 1];
                     if (s0 + j >= s1) {
-                        put32((kTagPad << 30) | n_gen);
+                        put32(kZero);
                         continue;
                     }
                     const uint32_t word = tagged_col[k][s0 + j];
-                    if ((word >> 30) == kTagGeneral) {
-                        uint32_t ord = gen_index[r];
+                    const uint32_t tag = word >> 30;
+                    if (tag == kTagGeneral) {
+                        uint32_t ord = gen_first[r];
                         for (uint32_t e = s0; e < s0 + j; ++e) ord += (tagged_col[k][e] >> 30) == kTagGeneral;
-                        put32((kTagGeneral << 30) | ord);
+                        put32(kProd0 + ord);
                     } else {
-                        put32(encode(word));
+                        put32((tag == kTagMinusOne ? kTermSign : 0u) | slot_of(word & kColMask));
                     }
                 }
             g_before = run;
         }
+        h.n_general = g_before;
         align16();
-        h.off_gcol = (uint32_t)(stream.size() - base);
+        h.off_far = (uint32_t)(stream.size() - base);
+        for (uint32_t c : far_cols) put32(c);
+        align16();
+        h.off_gop = (uint32_t)(stream.size() - base);
         for (int k = 0; k < 3; ++k)
             for (uint32_t e = 0; e < t.ne[k]; ++e) {
                 const uint32_t word = tagged_col[k][t.e0[k] + e];
-                if ((word >> 30) == kTagGeneral) put32(encode(word & kColMask));
+                if ((word >> 30) == kTagGeneral) put16((uint16_t)slot_of(word & kColMask));
             }
         align16();
         h.off_gval = (uint32_t)(stream.size() - base);
@@ -691,10 +718,11 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
         h.bytes = (uint32_t)(stream.size() - base);
         std::memcpy(stream.data() + base, &h, sizeof h);
     }
+    std::sort(m->long_ranges.begin(), m->long_ranges.end());
     align16();
     offs.push_back((uint32_t)(stream.size() / 16));
     if (stream.size() / 16 > 0xFFFFFFF0ull) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_r1cs_upload: tile stream too large");
-    m->n_tiles = (uint32_t)tiles.size();
+    m->n_tiles = n_tiles_out;
     m->stream_bytes = stream.size();
     DevBuf d_goffs;
     CU(ctx, cudaMalloc(&m->d_stream, stream.size() + 64));

@@ -11,8 +11,7 @@ namespace acg {
 // Column words carry a 2-bit coefficient tag in bits 31:30 when the system was preprocessed at upload
 // (DevR1cs::tagged): the sparsity pattern and the coefficients are static, so classifying them once is
 // free for every later check.
-constexpr uint32_t kColMask = 0x1FFFFFFFu;   // witness columns are < 2^29
-constexpr uint32_t kWinFlag = 0x20000000u;   // tile stream only: the index is an offset into the tile's witness window
+constexpr uint32_t kColMask = 0x3FFFFFFFu;   // witness columns are < 2^30
 constexpr uint32_t kTagPlusOne = 0u;   // coefficient == 1
 constexpr uint32_t kTagMinusOne = 1u;  // coefficient == r - 1
 constexpr uint32_t kTagGeneral = 2u;
@@ -32,31 +31,37 @@ struct DevR1cs {
 // self-contained, execution-ready tile blobs; the kernel stages one blob per tile with a single TMA
 // bulk copy, plus one more bulk copy of the tile's WITNESS WINDOW: the contiguous slice of w that most
 // of the tile's references fall into (for circuits built gate by gate: the wires defined just before /
-// by the tile's own rows).  Only references outside the window are gathered from global memory.
+// by the tile's own rows).
+//
+// Inside the kernel every term of every row lives in ONE shared-memory array of 32-byte slots:
+//     [0, window)                         the witness window (TMA)
+//     [window, window + max_far)          "far" witness elements: the distinct columns outside the window,
+//                                         gathered once per tile
+//     [.., + max_gen)                     products coefficient * operand of the general-coefficient entries
+//     last slot                           zero (padding)
 // Blob = header | entry words in ELL (slot-major) order: for matrix A, then B, then C, for slot
-// j < width[k], for row r < nrows: one 32-bit word
-//        tag<<30 | [kWinFlag] | index    coefficient +1 (tag 0) or -1 (tag 1); index = witness column, or
-//                                        offset into the witness window when kWinFlag is set
-//        2<<30  | j                      j-th general-coefficient entry of the tile: its product slot
-//        3<<30  | n_general              padding (rows shorter than the tile's width): the zero slot
-//   | operand words of the general entries ([kWinFlag] | index) | their coefficient values (Montgomery).
+// j < width[k], for row r < nrows: one 32-bit word = sign<<31 | term slot (coefficient -1 sets the sign;
+// general entries point at their product slot, padding at the zero slot) | u32 witness columns of the far
+// slots | u16 operand slots of the general entries | their coefficient values (Montgomery).
 // Every section is 16-byte aligned.  Row r of the tile is handled by thread r, so slot-major order makes
 // every word read of a warp contiguous and the control flow of the row sums warp-uniform.
 struct alignas(16) TileHeader {
     uint32_t row0;       // first (shard-local) row
     uint32_t nrows;
     uint32_t n_general;
+    uint32_t n_far;
     uint32_t width[3];   // ELL widths (max row length in the tile) of A, B, C
     uint32_t off_words;  // byte offsets inside the blob
-    uint32_t off_gcol;
+    uint32_t off_far;
+    uint32_t off_gop;
     uint32_t off_gval;
     uint32_t bytes;      // blob size (multiple of 16)
     uint32_t win_lo;     // witness window [win_lo, win_lo + win_n)
     uint32_t win_n;
-    uint32_t pad[4];
+    uint32_t pad[2];
 };
 static_assert(sizeof(TileHeader) == 64, "TileHeader must be 64 bytes");
-constexpr uint32_t kTagPad = 3u;
+constexpr uint32_t kTermSign = 0x80000000u;
 
 // Tiled kernel geometry (see DESIGN.md "K2"); the variant is bound when the system is uploaded.
 struct TileGeometry {
@@ -64,13 +69,17 @@ struct TileGeometry {
     uint32_t max_slots;  // sum of the three ELL widths (rows longer than kMaxEllWidth go to the row-wise kernel)
     uint32_t max_gen;    // general-coefficient entries per tile
     uint32_t window;     // witness elements staged per tile
+    uint32_t max_far;    // distinct witness columns outside the window per tile
 };
 constexpr uint32_t kMaxEllWidth = 8;
 constexpr int kNumTileVariants = 4;
 constexpr TileGeometry kTileGeom[kNumTileVariants] = {
-    {128, 12, 192, 192}, {256, 12, 384, 320}, {64, 12, 96, 128}, {32, 12, 64, 96}};
+    {128, 12, 192, 192, 320}, {256, 12, 384, 320, 640}, {64, 12, 96, 128, 160}, {32, 12, 64, 96, 96}};
 constexpr uint32_t tile_blob_capacity(const TileGeometry& g) {
-    return 64u + g.threads * g.max_slots * 4u + g.max_gen * 4u + g.max_gen * 32u;
+    return 64u + g.threads * g.max_slots * 4u + g.max_far * 4u + ((g.max_gen * 2u + 15u) / 16u) * 16u + g.max_gen * 32u;
+}
+constexpr uint32_t tile_term_slots(const TileGeometry& g) {
+    return g.window + g.max_far + g.max_gen + 1u;
 }
 
 struct DevTileStream {
@@ -90,10 +99,9 @@ cudaError_t launch_init_result(unsigned long long* d_result, cudaStream_t s);
 cudaError_t launch_r1cs_rowwise(int field, const DevR1cs& m, const fr_t* w, uint32_t row_lo, uint32_t row_hi,
                                 uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
                                 cudaStream_t s);
-// TMA-staged tile kernel over the tile stream.  stages: 1 = single blob buffer, 2 = the next tile's blob is
-// prefetched while the current tile computes.
+// TMA-staged tile kernel over the tile stream.
 cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w, uint64_t row_base,
-                              unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count, int stages,
+                              unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count,
                               cudaStream_t s);
 // general values inside the blobs: canonical -> Montgomery in place; offs[i] = byte offset / 16 of value i
 cudaError_t launch_to_mont_scattered(int field, uint8_t* blobs, const uint32_t* offs, uint64_t n, int* d_bad_flag,

@@ -15,14 +15,15 @@
 //                           shared memory; several CTAs per SM hide each other's load latency;
 //                           plus a second bulk copy of the tile's WITNESS WINDOW, the contiguous slice of
 //                           w most references of the tile fall into;
+//                           every term then lives in one shared-memory array of 32-byte slots
+//                           (window | far elements | products | zero);
+//                    (P1)   the tile's distinct references outside the window ("far") are gathered once,
+//                           one 256-bit load each, into the far slots;
 //                    (P2)   one lane per general entry: the 256-bit Montgomery product -- dense, no
 //                           divergence between coefficient kinds;
 //                    (P3)   thread per row over the tile's ELL (slot-major, padded) entry words: the three
-//                           sums A.w, B.w, C.w advance together with warp-uniform control flow; +-1 terms
-//                           are gathered from the witness straight into registers, general terms come
-//                           from the product planes (one generic-address load path); then a*b == c.
-//                    Shared memory holds only what is reused (blob + products), so occupancy is bounded
-//                    by registers, not by staging 32 bytes per entry.
+//                           sums A.w, B.w, C.w advance together with warp-uniform control flow and touch
+//                           shared memory only (word = sign | term slot); then a*b == c.
 //                    The coefficient classification (+1 / -1 / general) lives in two tag bits of the
 //                    column word and is computed once at upload: the sparsity pattern is static, and the
 //                    32-byte encodings of +-1 never need to be re-read.  HBM traffic per check is one
@@ -147,44 +148,35 @@ namespace tiled {
 constexpr uint32_t align_up(uint32_t x, uint32_t a) {
     return (x + a - 1) / a * a;
 }
-// shared-memory layout of one CTA: STAGES x (blob buffer + witness window), then the products of the
-// general-coefficient entries (+ the zero slot padding words point at)
-template <int V, int STAGES>
+// shared-memory layout of one CTA: the tile blob, then the term array (window | far | products | zero)
+template <int V>
 struct Cfg {
     static constexpr uint32_t kThreads = kTileGeom[V].threads;
-    static constexpr uint32_t kMaxGen = kTileGeom[V].max_gen;
+    static constexpr uint32_t kWin = kTileGeom[V].window;
+    static constexpr uint32_t kFar0 = kWin;                              // first far slot
+    static constexpr uint32_t kProd0 = kWin + kTileGeom[V].max_far;      // first product slot
+    static constexpr uint32_t kZero = tile_term_slots(kTileGeom[V]) - 1u;  // the zero slot
     static constexpr uint32_t kBlobCap = align_up(tile_blob_capacity(kTileGeom[V]), 128);
-    static constexpr uint32_t kWinBytes = kTileGeom[V].window * 32;
-    static constexpr uint32_t kStageBytes = kBlobCap + kWinBytes;
-    static constexpr uint32_t kOffProd = kStageBytes * STAGES;
-    static constexpr uint32_t kBytes = kOffProd + (kMaxGen + 1) * 32;
-    // resident CTAs per SM: bounded by shared memory (227 KB, 1 KB per CTA reserved), by 64 registers per
-    // thread (1024 threads) and by the hardware limit of 32
+    static constexpr uint32_t kOffTerms = kBlobCap;
+    static constexpr uint32_t kBytes = kOffTerms + tile_term_slots(kTileGeom[V]) * 32;
+    // resident CTAs per SM: bounded by shared memory (227 KB, 1 KB per CTA reserved), by 96 registers per
+    // thread and by the hardware limit of 32
     static constexpr uint32_t kCtasBySmem = (227u * 1024u) / (kBytes + 1024u + 64u);
-    static constexpr uint32_t kCtasByRegs = 1024u / kThreads;
-    static constexpr uint32_t kCtasPerSm = kCtasBySmem < kCtasByRegs ? kCtasBySmem : kCtasByRegs;
+    static constexpr uint32_t kCtasByRegs = 65536u / (kThreads * 96u);
+    static constexpr uint32_t kCtasMin = kCtasBySmem < kCtasByRegs ? kCtasBySmem : kCtasByRegs;
+    static constexpr uint32_t kCtasPerSm = kCtasMin > 32u ? 32u : kCtasMin;
 };
 
-// 2 x 16-byte asynchronous gather global -> shared (LDGSTS), no register staging
-__device__ __forceinline__ void cp_async_fr_planes(uint4* lo, uint4* hi, const fr_t* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(lo)), "l"(gmem_src) : "memory");
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(hi)),
-                 "l"(reinterpret_cast<const uint8_t*>(gmem_src) + 16)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.wait_all;" ::: "memory");
-}
-__device__ __forceinline__ fr_t load_planes(const uint4* lo, const uint4* hi, uint32_t i) {
-    const uint4 a = lo[i], b = hi[i];
+__device__ __forceinline__ fr_t load_term(const uint4* terms, uint32_t slot) {
+    const uint4 a = terms[2u * slot], b = terms[2u * slot + 1u];
     fr_t r;
     r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
 }
-__device__ __forceinline__ void store_planes(uint4* lo, uint4* hi, uint32_t i, const fr_t& v) {
-    lo[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-    hi[i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+__device__ __forceinline__ void store_term(uint4* terms, uint32_t slot, const fr_t& v) {
+    terms[2u * slot] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    terms[2u * slot + 1u] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 __device__ __forceinline__ fr_t load_fr16(const uint8_t* p) {  // 16-byte aligned shared-memory element
     const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);
@@ -203,110 +195,129 @@ __device__ __forceinline__ fr_t neg_lazy(const fr_t& x) {
     r.l[7] = ptx::subc(P::p(7), x.l[7]);
     return r;
 }
-// one thread: bulk copies of the tile blob and of the tile's witness window
-__device__ __forceinline__ void issue_blob_load(const DevTileStream& ts, const fr_t* __restrict__ w, uint32_t tile,
-                                                uint8_t* dst, uint32_t blob_cap, uint64_t* bar) {
+// one thread: bulk copies of the tile blob and of the tile's witness window (into the first term slots)
+__device__ __forceinline__ void issue_tile_load(const DevTileStream& ts, const fr_t* __restrict__ w, uint32_t tile,
+                                                uint8_t* blob_dst, uint8_t* win_dst, uint64_t* bar) {
     const uint32_t o0 = ts.offsets[tile], o1 = ts.offsets[tile + 1];
     const uint32_t bytes = (o1 - o0) * 16u;
     const uint2 win = ts.windows[tile];  // {win_lo, win_n}
     mbar_arrive_expect_tx(bar, bytes + win.y * 32u);
-    tma_load_1d(dst, ts.blobs + (size_t)o0 * 16u, bytes, bar);
-    if (win.y) tma_load_1d(dst + blob_cap, w + win.x, win.y * 32u, bar);
+    tma_load_1d(blob_dst, ts.blobs + (size_t)o0 * 16u, bytes, bar);
+    if (win.y) tma_load_1d(win_dst, w + win.x, win.y * 32u, bar);
 }
 }  // namespace tiled
 
-template <class P, bool EMIT, int V, int STAGES>
-__global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V, STAGES>::kCtasPerSm)
+namespace tiled {
+// Sums of one row over the tile's ELL words (pa[j * nrows] = word of slot j): a = A-row . w, b, c likewise.
+// WA/WB/WC > 0: compile-time widths (fully unrolled, no predicates); 0: run-time widths wa/wb/wc.
+template <class P, int WA, int WB, int WC>
+__device__ __forceinline__ void row_sums(const uint4* terms, const uint32_t* pa, uint32_t nrows, uint32_t wa,
+                                         uint32_t wb, uint32_t wc, fr_t& a, fr_t& b, fr_t& c) {
+    auto term = [&](uint32_t word) -> fr_t {
+        fr_t x = load_term(terms, word & ~kTermSign);
+        if (word & kTermSign) x = neg_lazy<P>(x);
+        return x;
+    };
+    a = fr_zero<P>();
+    b = fr_zero<P>();
+    c = fr_zero<P>();
+    if (WA > 0) {
+        const uint32_t* pb = pa + WA * nrows;
+        const uint32_t* pc = pb + WB * nrows;
+        constexpr int WM = WA > WB ? (WA > WC ? WA : WC) : (WB > WC ? WB : WC);
+#pragma unroll
+        for (int j = 0; j < WM; ++j) {
+            fr_t ta, tb, tc;
+            if (j < WA) ta = term(pa[j * nrows]);
+            if (j < WB) tb = term(pb[j * nrows]);
+            if (j < WC) tc = term(pc[j * nrows]);
+            if (j < WA) a = fr_add<P>(a, ta);
+            if (j < WB) b = fr_add<P>(b, tb);
+            if (j < WC) c = fr_add<P>(c, tc);
+        }
+    } else {
+        const uint32_t* pb = pa + wa * nrows;
+        const uint32_t* pc = pb + wb * nrows;
+        const uint32_t wmax = max(wa, max(wb, wc));
+        for (uint32_t j = 0; j < wmax; ++j) {  // trip count and the three predicates are warp-uniform
+            const bool ua = j < wa, ub = j < wb, uc = j < wc;
+            fr_t ta, tb, tc;
+            if (ua) ta = term(pa[j * nrows]);
+            if (ub) tb = term(pb[j * nrows]);
+            if (uc) tc = term(pc[j * nrows]);
+            if (ua) a = fr_add<P>(a, ta);
+            if (ub) b = fr_add<P>(b, tb);
+            if (uc) c = fr_add<P>(c, tc);
+        }
+    }
+}
+}  // namespace tiled
+
+template <class P, bool EMIT, int V>
+__global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerSm)
     k_r1cs_tiled(DevTileStream ts, const fr_t* __restrict__ w, uint64_t row_base,
                  unsigned long long* __restrict__ result, fr_t* __restrict__ Aw, fr_t* __restrict__ Bw,
                  fr_t* __restrict__ Cw) {
     using namespace tiled;
-    using C = Cfg<V, STAGES>;
+    using C = Cfg<V>;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t full_bar;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t n_tiles = ts.n_tiles;
+    const uint8_t* blob = smem;
+    uint4* terms = reinterpret_cast<uint4*>(smem + C::kOffTerms);
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        mbar_init(&full_bar, 1);
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0 && blockIdx.x < n_tiles) issue_blob_load(ts, w, blockIdx.x, smem, C::kBlobCap, &full_bar[0]);
-
-    uint4* prod = reinterpret_cast<uint4*>(smem + C::kOffProd);  // 32-byte product slots
+    if (tid == 0 && blockIdx.x < n_tiles)
+        issue_tile_load(ts, w, blockIdx.x, smem, smem + C::kOffTerms, &full_bar);
 
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t stage = it % STAGES;
-        const uint8_t* blob = smem + (size_t)stage * C::kStageBytes;
-        const uint4* win = reinterpret_cast<const uint4*>(blob + C::kBlobCap);
-        if (STAGES == 2 && tid == 0 && tile + gridDim.x < n_tiles)  // prefetch: that buffer was released by the
-            issue_blob_load(ts, w, tile + gridDim.x,                // barrier that ended the previous tile
-                            smem + (size_t)((it + 1) % STAGES) * C::kStageBytes, C::kBlobCap,
-                            &full_bar[(it + 1) % STAGES]);
-        mbar_wait(&full_bar[stage], (it / STAGES) & 1u);
-
+        mbar_wait(&full_bar, it & 1u);
         const TileHeader h = *reinterpret_cast<const TileHeader*>(blob);
         const uint32_t* words = reinterpret_cast<const uint32_t*>(blob + h.off_words);
-        const uint32_t* gcol = reinterpret_cast<const uint32_t*>(blob + h.off_gcol);
+        const uint32_t* far = reinterpret_cast<const uint32_t*>(blob + h.off_far);
+        const uint16_t* gop = reinterpret_cast<const uint16_t*>(blob + h.off_gop);
         const uint8_t* gval = blob + h.off_gval;
 
-        // ---- P2: dense 256-bit Montgomery products, one general entry per lane: operand from the witness
-        //          window (shared memory) or one 256-bit global load
-        for (uint32_t j = tid; j < h.n_general; j += C::kThreads) {
-            const uint32_t gw = gcol[j];
-            const uint4* gsrc = reinterpret_cast<const uint4*>(w + (gw & kColMask));
-            const uint4* src = (gw & kWinFlag) ? win + 2u * (gw & kColMask) : gsrc;
-            const uint4 a4 = src[0], b4 = src[1];
-            fr_t x;
-            x.l[0] = a4.x; x.l[1] = a4.y; x.l[2] = a4.z; x.l[3] = a4.w;
-            x.l[4] = b4.x; x.l[5] = b4.y; x.l[6] = b4.z; x.l[7] = b4.w;
-            const fr_t pr = fr_mul<P>(load_fr16(gval + (size_t)j * 32u), x);
-            prod[2u * j] = make_uint4(pr.l[0], pr.l[1], pr.l[2], pr.l[3]);
-            prod[2u * j + 1u] = make_uint4(pr.l[4], pr.l[5], pr.l[6], pr.l[7]);
+        // ---- P1: the distinct far witness elements of the tile -> far slots (one 256-bit load each, all of a
+        //          thread's loads in flight together)
+        for (uint32_t f = tid; f < h.n_far; f += 3u * C::kThreads) {
+            const uint32_t f1 = f + C::kThreads, f2 = f + 2u * C::kThreads;
+            fr_t x0, x1, x2;
+            x0 = w[far[f]];
+            if (f1 < h.n_far) x1 = w[far[f1]];
+            if (f2 < h.n_far) x2 = w[far[f2]];
+            store_term(terms, C::kFar0 + f, x0);
+            if (f1 < h.n_far) store_term(terms, C::kFar0 + f1, x1);
+            if (f2 < h.n_far) store_term(terms, C::kFar0 + f2, x2);
         }
-        if (tid == 0) {  // the zero slot that padding words reference
-            prod[2u * h.n_general] = make_uint4(0u, 0u, 0u, 0u);
-            prod[2u * h.n_general + 1u] = make_uint4(0u, 0u, 0u, 0u);
-        }
+        if (tid == 0) store_term(terms, C::kZero, fr_zero<P>());
         __syncthreads();
 
-        // ---- P3: thread per row, warp-uniform: the sums A.w, B.w, C.w advance together slot by slot.  A term
-        //          is loaded through one generic address that points into the witness window or the product
-        //          slots (shared memory) or, for far references, into the witness in global memory; a -1
-        //          coefficient negates under a predicate.
+        // ---- P2: dense 256-bit Montgomery products, one general entry per lane (no divergence between
+        //          coefficient kinds): product slot <- coefficient * operand slot
+        for (uint32_t j = tid; j < h.n_general; j += C::kThreads)
+            store_term(terms, C::kProd0 + j, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), load_term(terms, gop[j])));
+        __syncthreads();
+
+        // ---- P3: thread per row, warp-uniform, shared memory only: the sums A.w, B.w, C.w advance together
+        //          slot by slot (three independent carry chains); a -1 coefficient negates under a predicate
         bool bad = false;
         if (tid < h.nrows) {
-            auto term = [&](uint32_t word) -> fr_t {
-                const uint32_t idx = word & kColMask;
-                const uint4* src = reinterpret_cast<const uint4*>(w + idx);
-                if (word & kWinFlag) src = win + 2u * idx;
-                if (word >> 31) src = prod + 2u * idx;  // tags 2 (general) and 3 (padding)
-                const uint4 a4 = src[0], b4 = src[1];
-                fr_t x;
-                x.l[0] = a4.x; x.l[1] = a4.y; x.l[2] = a4.z; x.l[3] = a4.w;
-                x.l[4] = b4.x; x.l[5] = b4.y; x.l[6] = b4.z; x.l[7] = b4.w;
-                if ((word >> 30) == kTagMinusOne) x = neg_lazy<P>(x);
-                return x;
-            };
             const uint32_t wA = h.width[0], wB = h.width[1], wC = h.width[2];
-            const uint32_t* pa = words + tid;
-            const uint32_t* pb = pa + wA * h.nrows;
-            const uint32_t* pc = pb + wB * h.nrows;
-            const uint32_t wmax = max(wA, max(wB, wC));
-            fr_t a = fr_zero<P>(), b = fr_zero<P>(), c = fr_zero<P>();
-            for (uint32_t j = 0; j < wmax; ++j) {  // trip count and the three predicates are warp-uniform
-                const bool ua = j < wA, ub = j < wB, uc = j < wC;
-                fr_t ta, tb, tc;
-                if (ua) ta = term(pa[j * h.nrows]);
-                if (ub) tb = term(pb[j * h.nrows]);
-                if (uc) tc = term(pc[j * h.nrows]);
-                if (ua) a = fr_add<P>(a, ta);
-                if (ub) b = fr_add<P>(b, tb);
-                if (uc) c = fr_add<P>(c, tc);
+            fr_t a, b, c;
+            if (wA == 3u && wB == 3u && wC == 1u) {  // the common shape: straight-line code, no predicates
+                row_sums<P, 3, 3, 1>(terms, words + tid, h.nrows, 3u, 3u, 1u, a, b, c);
+            } else if (wA == 2u && wB == 2u && wC == 1u) {
+                row_sums<P, 2, 2, 1>(terms, words + tid, h.nrows, 2u, 2u, 1u, a, b, c);
+            } else {
+                row_sums<P, 0, 0, 0>(terms, words + tid, h.nrows, wA, wB, wC, a, b, c);
             }
             if (EMIT) {
                 const uint32_t row = h.row0 + tid;
@@ -319,11 +330,12 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V, STAGES>::k
         const uint32_t bal = __ballot_sync(0xffffffffu, bad);
         if (bal != 0u && lane == 0u) report_bad_rows(result, bal, row_base + h.row0 + (tid & ~31u));
 
-        // the blob was read through the generic proxy; order that before the next TMA (async proxy) refill
+        // blob and window were read (and the term array written) through the generic proxy; order that before
+        // the next TMA (async proxy) refill of the same bytes
         fence_proxy_async_smem();
         __syncthreads();
-        if (STAGES == 1 && tid == 0 && tile + gridDim.x < n_tiles)
-            issue_blob_load(ts, w, tile + gridDim.x, smem, C::kBlobCap, &full_bar[0]);
+        if (tid == 0 && tile + gridDim.x < n_tiles)
+            issue_tile_load(ts, w, tile + gridDim.x, smem, smem + C::kOffTerms, &full_bar);
     }
 }
 
@@ -405,55 +417,42 @@ cudaError_t launch_r1cs_rowwise(int field, const DevR1cs& m, const fr_t* w, uint
     return cudaGetLastError();
 }
 
-template <class P, bool EMIT, int V, int STAGES>
+template <class P, bool EMIT, int V>
 static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uint64_t row_base,
                                      unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count,
                                      cudaStream_t s) {
-    using C = tiled::Cfg<V, STAGES>;
+    using C = tiled::Cfg<V>;
     {
-        cudaError_t e = cudaFuncSetAttribute(k_r1cs_tiled<P, EMIT, V, STAGES>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kBytes);
+        cudaError_t e = cudaFuncSetAttribute(k_r1cs_tiled<P, EMIT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)C::kBytes);
         if (e != cudaSuccess) return e;
     }
     unsigned grid = (unsigned)(sm_count * (int)C::kCtasPerSm);
     if (grid > ts.n_tiles) grid = ts.n_tiles;
-    k_r1cs_tiled<P, EMIT, V, STAGES><<<grid, kTileGeom[V].threads, C::kBytes, s>>>(ts, w, row_base, d_result, Aw, Bw,
-                                                                                   Cw);
+    k_r1cs_tiled<P, EMIT, V><<<grid, kTileGeom[V].threads, C::kBytes, s>>>(ts, w, row_base, d_result, Aw, Bw, Cw);
     return cudaGetLastError();
 }
 
 cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w, uint64_t row_base,
-                              unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count, int stages,
+                              unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count,
                               cudaStream_t s) {
     if (ts.n_tiles == 0) return cudaSuccess;
     const bool emit = Aw || Bw || Cw;
-#define ACG_TILED(EMITV, VAR, STG)                                                                               \
-    ACG_DISPATCH_FIELD(field, return (launch_tiled_impl<P, EMITV, VAR, STG>(ts, w, row_base, d_result, Aw, Bw, Cw, \
-                                                                            sm_count, s)))
-#define ACG_TILED_VS(VAR, STG)        \
-    do {                              \
-        if (emit) ACG_TILED(true, VAR, STG); \
-        ACG_TILED(false, VAR, STG);   \
+#define ACG_TILED(EMITV, VAR)                                                                                     \
+    ACG_DISPATCH_FIELD(field, return (launch_tiled_impl<P, EMITV, VAR>(ts, w, row_base, d_result, Aw, Bw, Cw, \
+                                                                       sm_count, s)))
+#define ACG_TILED_V(VAR)                \
+    do {                                \
+        if (emit) ACG_TILED(true, VAR); \
+        ACG_TILED(false, VAR);          \
     } while (0)
     switch (ts.variant) {
-        case 1:
-            if (stages == 2) ACG_TILED_VS(1, 2);
-            ACG_TILED_VS(1, 1);
-            break;
-        case 2:
-            if (stages == 2) ACG_TILED_VS(2, 2);
-            ACG_TILED_VS(2, 1);
-            break;
-        case 3:
-            if (stages == 2) ACG_TILED_VS(3, 2);
-            ACG_TILED_VS(3, 1);
-            break;
-        default:
-            if (stages == 2) ACG_TILED_VS(0, 2);
-            ACG_TILED_VS(0, 1);
-            break;
+        case 1: ACG_TILED_V(1); break;
+        case 2: ACG_TILED_V(2); break;
+        case 3: ACG_TILED_V(3); break;
+        default: ACG_TILED_V(0); break;
     }
-#undef ACG_TILED_VS
+#undef ACG_TILED_V
 #undef ACG_TILED
     return cudaErrorInvalidValue;
 }

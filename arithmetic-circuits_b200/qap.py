@@ -399,8 +399,6 @@ class Context:
         """Tile geometry for systems uploaded AFTER this call (0: 128-row tiles, 1: 256-row tiles)."""
         _check(_lib.lib().acg_ctx_set_tiled_variant(self._h, variant), self)
 
-    def set_tiled_stages(self, stages: int):
-        _check(_lib.lib().acg_ctx_set_tiled_stages(self._h, stages), self)
 
     def last_timing(self) -> Dict[str, float]:
         t = AcgTiming()

@@ -49,7 +49,6 @@ def parse_args():
     ap.add_argument("--dense", action="store_true", help="all coefficients uniform (stress variant)")
     ap.add_argument("--kernel", default="tiled", choices=["tiled", "rowwise"])
     ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2, 3], help="tiled kernel geometry: rows per tile 128/256/64/32")
-    ap.add_argument("--stages", type=int, default=1, choices=[1, 2], help="tiled kernel: 2 = prefetch next tile")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -217,7 +216,6 @@ def run_ours(args, rank, world, local_rank):
     ctx = acg.Context(field_id, local_rank)
     ctx.set_check_kernel(acg.CHECK_TILED if args.kernel == "tiled" else acg.CHECK_ROWWISE)
     ctx.set_tiled_variant(args.variant)
-    ctx.set_tiled_stages(args.stages)
     m = ctx.upload_r1cs(g)
     dw = ctx.upload_witness(w)
     algo_bytes = m.algorithmic_bytes
@@ -322,7 +320,7 @@ def run_ours(args, rank, world, local_rank):
             "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u256 (8x32-bit-limb Montgomery Fr, integer)", "data": "synthetic",
-            "config": {"workload": workload_name(args, world), "kernel": args.kernel, "tiled_variant": args.variant, "tiled_stages": args.stages,
+            "config": {"workload": workload_name(args, world), "kernel": args.kernel, "tiled_variant": args.variant,
                        "l2": "inputs streamed per step (%.0f MB CSR + %.0f MB witness per GPU) exceed the 126 MB L2; no explicit flush"
                              % ((algo_bytes - 32 * g.n_cols) / 1e6, 32 * g.n_cols / 1e6),
                        "parallelism": "rows sharded over %d rank(s), 1 all-reduce(sum) of the violation count per step" % world,

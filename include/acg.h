@@ -81,10 +81,9 @@ const char* acg_last_error(const acg_ctx* ctx);
 int acg_ctx_create(int field_id, int device, acg_ctx** out);
 void acg_ctx_destroy(acg_ctx* ctx);
 int acg_ctx_set_check_kernel(acg_ctx* ctx, int which);
-/* Tiled kernel tuning.  variant (bound to a system when it is uploaded): 0 = 128-row tiles (default),
- * 1 = 256-row tiles.  stages: 1 = one tile buffer per CTA (default), 2 = prefetch the next tile's blob. */
+/* Tiled kernel tuning: tile geometry, bound to a system when it is uploaded.  0 = 128-row tiles (default),
+ * 1 = 256, 2 = 64, 3 = 32 rows per tile. */
 int acg_ctx_set_tiled_variant(acg_ctx* ctx, int variant);
-int acg_ctx_set_tiled_stages(acg_ctx* ctx, int stages);
 int acg_last_timing(const acg_ctx* ctx, acg_timing* out);
 /* Total launches of this library's kernels on this context since creation. */
 uint64_t acg_kernel_launch_count(const acg_ctx* ctx);

@@ -42,17 +42,15 @@ def test_field_ops_device(acg, ctxs, fid):
 
 
 # ------------------------------------------------------------------------------------------------ K2
-KERNELS = [("rowwise", 1), ("tiled", 1), ("tiled", 2)]   # (kernel, tiled pipeline stages)
+KERNELS = [("rowwise", 0), ("tiled", 0)]   # the tile geometry comes from the `tile_variant` fixture (upload time)
 
 
-def _select(acg, ctx, kernel, stages):
+def _select(acg, ctx, kernel, _unused):
     ctx.set_check_kernel(acg.CHECK_ROWWISE if kernel == "rowwise" else acg.CHECK_TILED)
-    ctx.set_tiled_stages(stages)
 
 
 def _reset(acg, ctx):
     ctx.set_check_kernel(acg.CHECK_AUTO)
-    ctx.set_tiled_stages(1)
 
 
 def _both_kernels(acg, ctx, fn):
