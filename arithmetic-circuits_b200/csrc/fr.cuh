@@ -198,7 +198,7 @@ ACG_HD bool fr_is_canonical(const fr_t& a) {
     return borrow != 0;
 }
 
-// r = a + b mod p      (a, b < p)
+// r = a + b mod p      (a, b < p; for a, b <= p the result is in [0, p])
 template <class P>
 ACG_HD fr_t fr_add(const fr_t& a, const fr_t& b) {
     fr_t t, s;
@@ -304,7 +304,8 @@ ACG_HD fr_t fr_reduce_once(const uint32_t t[8]) {
     return r;
 }
 
-// Montgomery product a*b*2^-256 mod p.   a, b < p.
+// Montgomery product a*b*2^-256 mod p, result in [0, p).  a <= p (the vector operand: every round keeps
+// T < a + p); b is consumed limb by limb and may be ANY 256-bit value (an unreduced sum).
 template <class P>
 ACG_HD fr_t fr_mul(const fr_t& a, const fr_t& b) {
     uint32_t e0[9], o0[8], e1[9], o1[8];

@@ -11,7 +11,7 @@ static int binop(int op, const uint32_t* a, const uint32_t* b, uint32_t* o, uint
         fr_t x, y, z;
         std::memcpy(x.l, a + 8 * i, 32);
         std::memcpy(y.l, b + 8 * i, 32);
-        if (!fr_is_canonical<P>(x) || (op != 3 && op != 4 && op != 5 && !fr_is_canonical<P>(y))) return -2;
+        if (op < 7 && (!fr_is_canonical<P>(x) || (op != 3 && op != 4 && op != 5 && !fr_is_canonical<P>(y)))) return -2;
         switch (op) {
             case 0: z = fr_add<P>(x, y); break;
             case 1: z = fr_sub<P>(x, y); break;
@@ -20,6 +20,8 @@ static int binop(int op, const uint32_t* a, const uint32_t* b, uint32_t* o, uint
             case 4: z = fr_to_mont<P>(x); break;
             case 5: z = fr_neg<P>(x); break;
             case 6: z = fr_mul<P>(x, y); break;  // raw Montgomery product x*y/R
+            case 7: z = fr_mul<P>(x, y); break;  // x <= p, y any 256-bit value (unreduced row sum)
+            case 8: z = fr_add<P>(x, y); break;  // x, y <= p: result in [0, p]
             default: return -1;
         }
         std::memcpy(o + 8 * i, z.l, 32);

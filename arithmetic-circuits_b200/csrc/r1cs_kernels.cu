@@ -28,6 +28,9 @@
 //                    column word and is computed once at upload: the sparsity pattern is static, and the
 //                    32-byte encodings of +-1 never need to be re-read.  HBM traffic per check is one
 //                    pass over columns, row pointers and general values; the witness is gathered via L2.
+#include <cstdio>
+#include <cstdlib>
+
 #include "dev.cuh"
 #include "kernels.h"
 
@@ -208,52 +211,95 @@ __device__ __forceinline__ void issue_tile_load(const DevTileStream& ts, const f
 }  // namespace tiled
 
 namespace tiled {
-// Sums of one row over the tile's ELL words (pa[j * nrows] = word of slot j): a = A-row . w, b, c likewise.
-// WA/WB/WC > 0: compile-time widths (fully unrolled, no predicates); 0: run-time widths wa/wb/wc.
+template <class P>
+__device__ __forceinline__ fr_t signed_term(const uint4* terms, uint32_t word) {
+    fr_t x = load_term(terms, word & ~kTermSign);
+    if (word & kTermSign) x = neg_lazy<P>(x);
+    return x;  // <= p
+}
+// a + b with no reduction (the caller bounds the sum below 2^256)
+__device__ __forceinline__ fr_t add_wide(const fr_t& a, const fr_t& b) {
+    fr_t t;
+    t.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) t.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+    t.l[7] = ptx::addc(a.l[7], b.l[7]);
+    return t;
+}
+// how many values <= p add up below 2^256: 5 for BN254 Fr, 2 for BLS12-381 Fr
+template <class P>
+struct Lazy {
+    static constexpr int kTerms = (int)(0x100000000ull / ((uint64_t)P::p(7) + 1ull));
+};
+// One accumulation step of a row sum.  LAZY: the running value may stay unreduced (it ends as the scalar
+// operand of the Montgomery product, which accepts any 256-bit value); otherwise it stays <= p.
+template <class P, bool LAZY>
+__device__ __forceinline__ fr_t acc_step(const fr_t& acc, const fr_t& t) {
+    return LAZY ? add_wide(acc, t) : fr_add<P>(acc, t);  // fr_add maps [0, 2p] -> [0, p]
+}
+// Sums of one row over the tile's ELL words (pa[j * nrows] = word of slot j), compile-time widths >= 1:
+// straight-line, the three sums advance together slot by slot (three independent carry chains).
+//   a: A-row . w, possibly unreduced (< 2^256, congruent mod p);  b in [0, p];  c in [0, p)
 template <class P, int WA, int WB, int WC>
-__device__ __forceinline__ void row_sums(const uint4* terms, const uint32_t* pa, uint32_t nrows, uint32_t wa,
-                                         uint32_t wb, uint32_t wc, fr_t& a, fr_t& b, fr_t& c) {
-    auto term = [&](uint32_t word) -> fr_t {
-        fr_t x = load_term(terms, word & ~kTermSign);
-        if (word & kTermSign) x = neg_lazy<P>(x);
-        return x;
-    };
+__device__ __forceinline__ void row_sums_fixed(const uint4* terms, const uint32_t* pa, uint32_t nrows, fr_t& a,
+                                               fr_t& b, fr_t& c) {
+    const uint32_t* pb = pa + WA * nrows;
+    const uint32_t* pc = pb + WB * nrows;
+    constexpr int WM = WA > WB ? (WA > WC ? WA : WC) : (WB > WC ? WB : WC);
+    constexpr int L = Lazy<P>::kTerms;
+#pragma unroll
+    for (int j = 0; j < WM; ++j) {
+        fr_t ta, tb, tc;
+        if (j < WA) ta = signed_term<P>(terms, pa[j * nrows]);
+        if (j < WB) tb = signed_term<P>(terms, pb[j * nrows]);
+        if (j < WC) tc = signed_term<P>(terms, pc[j * nrows]);
+        if (j == 0) {
+            a = ta;
+            b = tb;
+            c = tc;
+        } else {
+            // the last L-1 steps of a may skip the reduction: value <= p * (1 + remaining steps) <= L * p
+            if (j < WA) a = (WA - j <= L - 1) ? acc_step<P, true>(a, ta) : acc_step<P, false>(a, ta);
+            if (j < WB) b = acc_step<P, false>(b, tb);
+            if (j < WC) c = acc_step<P, false>(c, tc);
+        }
+    }
+    c = fr_add<P>(c, fr_zero<P>());  // p (a negated zero) -> 0: c is compared, not multiplied
+}
+// Run-time widths.  a, b, c in [0, p).
+template <class P>
+__device__ __forceinline__ void row_sums_any(const uint4* terms, const uint32_t* pa, uint32_t nrows, uint32_t wa,
+                                             uint32_t wb, uint32_t wc, fr_t& a, fr_t& b, fr_t& c) {
     a = fr_zero<P>();
     b = fr_zero<P>();
     c = fr_zero<P>();
-    if (WA > 0) {
-        const uint32_t* pb = pa + WA * nrows;
-        const uint32_t* pc = pb + WB * nrows;
-        constexpr int WM = WA > WB ? (WA > WC ? WA : WC) : (WB > WC ? WB : WC);
-#pragma unroll
-        for (int j = 0; j < WM; ++j) {
-            fr_t ta, tb, tc;
-            if (j < WA) ta = term(pa[j * nrows]);
-            if (j < WB) tb = term(pb[j * nrows]);
-            if (j < WC) tc = term(pc[j * nrows]);
-            if (j < WA) a = fr_add<P>(a, ta);
-            if (j < WB) b = fr_add<P>(b, tb);
-            if (j < WC) c = fr_add<P>(c, tc);
-        }
-    } else {
-        const uint32_t* pb = pa + wa * nrows;
-        const uint32_t* pc = pb + wb * nrows;
-        const uint32_t wmax = max(wa, max(wb, wc));
-        for (uint32_t j = 0; j < wmax; ++j) {  // trip count and the three predicates are warp-uniform
-            const bool ua = j < wa, ub = j < wb, uc = j < wc;
-            fr_t ta, tb, tc;
-            if (ua) ta = term(pa[j * nrows]);
-            if (ub) tb = term(pb[j * nrows]);
-            if (uc) tc = term(pc[j * nrows]);
-            if (ua) a = fr_add<P>(a, ta);
-            if (ub) b = fr_add<P>(b, tb);
-            if (uc) c = fr_add<P>(c, tc);
-        }
+    const uint32_t* pb = pa + wa * nrows;
+    const uint32_t* pc = pb + wb * nrows;
+    const uint32_t wmax = max(wa, max(wb, wc));
+    for (uint32_t j = 0; j < wmax; ++j) {  // trip count and the three predicates are warp-uniform
+        const bool ua = j < wa, ub = j < wb, uc = j < wc;
+        fr_t ta, tb, tc;
+        if (ua) ta = signed_term<P>(terms, pa[j * nrows]);
+        if (ub) tb = signed_term<P>(terms, pb[j * nrows]);
+        if (uc) tc = signed_term<P>(terms, pc[j * nrows]);
+        if (ua) a = fr_add<P>(a, ta);
+        if (ub) b = fr_add<P>(b, tb);
+        if (uc) c = fr_add<P>(c, tc);
     }
+}
+// canonical representative of a value < 2^256 (EMIT path only)
+template <class P>
+__device__ __forceinline__ fr_t canonical(fr_t x) {
+#pragma unroll
+    for (int i = 0; i < Lazy<P>::kTerms; ++i) x = fr_add<P>(x, fr_zero<P>());
+    return x;
 }
 }  // namespace tiled
 
-template <class P, bool EMIT, int V>
+// phase cycle counters of the TIMING instantiation (a measurement aid, see tools/phase_timing.py)
+__device__ unsigned long long g_tiled_phase_cycles[2][8];
+
+template <class P, bool EMIT, int V, bool TIMING = false>
 __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerSm)
     k_r1cs_tiled(DevTileStream ts, const fr_t* __restrict__ w, uint64_t row_base,
                  unsigned long long* __restrict__ result, fr_t* __restrict__ Aw, fr_t* __restrict__ Bw,
@@ -262,10 +308,22 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     using C = Cfg<V>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar;
+    __shared__ unsigned long long ph[2][8];  // TIMING only: per-phase cycles seen by warp 0 and by the last warp
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t n_tiles = ts.n_tiles;
+    const bool rec = TIMING && (tid == 0u || tid == C::kThreads - 32u);
+    const uint32_t rw = tid == 0u ? 0u : 1u;
+    long long t_last = 0;
+    auto mark = [&](int k) {
+        if (TIMING && rec) {
+            const long long now = clock64();
+            ph[rw][k] += (unsigned long long)(now - t_last);
+            t_last = now;
+        }
+    };
+    if (TIMING && tid < 16u) ph[tid >> 3][tid & 7u] = 0ull;
     const uint8_t* blob = smem;
     uint4* terms = reinterpret_cast<uint4*>(smem + C::kOffTerms);
     if (tid == 0) {
@@ -277,8 +335,10 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         issue_tile_load(ts, w, blockIdx.x, smem, smem + C::kOffTerms, &full_bar);
 
     uint32_t it = 0;
+    if (TIMING) t_last = clock64();
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         mbar_wait(&full_bar, it & 1u);
+        mark(0);
         const TileHeader h = *reinterpret_cast<const TileHeader*>(blob);
         const uint32_t* words = reinterpret_cast<const uint32_t*>(blob + h.off_words);
         const uint32_t* far = reinterpret_cast<const uint32_t*>(blob + h.off_far);
@@ -298,13 +358,17 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
             if (f2 < h.n_far) store_term(terms, C::kFar0 + f2, x2);
         }
         if (tid == 0) store_term(terms, C::kZero, fr_zero<P>());
+        mark(1);
         __syncthreads();
+        mark(2);
 
         // ---- P2: dense 256-bit Montgomery products, one general entry per lane (no divergence between
         //          coefficient kinds): product slot <- coefficient * operand slot
         for (uint32_t j = tid; j < h.n_general; j += C::kThreads)
             store_term(terms, C::kProd0 + j, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), load_term(terms, gop[j])));
+        mark(3);
         __syncthreads();
+        mark(4);
 
         // ---- P3: thread per row, warp-uniform, shared memory only: the sums A.w, B.w, C.w advance together
         //          slot by slot (three independent carry chains); a -1 coefficient negates under a predicate
@@ -313,29 +377,37 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
             const uint32_t wA = h.width[0], wB = h.width[1], wC = h.width[2];
             fr_t a, b, c;
             if (wA == 3u && wB == 3u && wC == 1u) {  // the common shape: straight-line code, no predicates
-                row_sums<P, 3, 3, 1>(terms, words + tid, h.nrows, 3u, 3u, 1u, a, b, c);
+                row_sums_fixed<P, 3, 3, 1>(terms, words + tid, h.nrows, a, b, c);
             } else if (wA == 2u && wB == 2u && wC == 1u) {
-                row_sums<P, 2, 2, 1>(terms, words + tid, h.nrows, 2u, 2u, 1u, a, b, c);
+                row_sums_fixed<P, 2, 2, 1>(terms, words + tid, h.nrows, a, b, c);
             } else {
-                row_sums<P, 0, 0, 0>(terms, words + tid, h.nrows, wA, wB, wC, a, b, c);
+                row_sums_any<P>(terms, words + tid, h.nrows, wA, wB, wC, a, b, c);
             }
             if (EMIT) {
+                a = canonical<P>(a);
+                b = fr_add<P>(b, fr_zero<P>());
                 const uint32_t row = h.row0 + tid;
                 if (Aw) Aw[row] = a;
                 if (Bw) Bw[row] = b;
                 if (Cw) Cw[row] = c;
             }
-            bad = !fr_eq(fr_mul<P>(a, b), c);
+            bad = !fr_eq(fr_mul<P>(b, a), c);  // b (<= p) is the vector operand, a the limb-wise scalar
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, bad);
         if (bal != 0u && lane == 0u) report_bad_rows(result, bal, row_base + h.row0 + (tid & ~31u));
 
         // blob and window were read (and the term array written) through the generic proxy; order that before
         // the next TMA (async proxy) refill of the same bytes
+        mark(5);
         fence_proxy_async_smem();
         __syncthreads();
+        mark(6);
         if (tid == 0 && tile + gridDim.x < n_tiles)
             issue_tile_load(ts, w, tile + gridDim.x, smem, smem + C::kOffTerms, &full_bar);
+    }
+    if (TIMING && rec) {
+        for (int k = 0; k < 7; ++k) atomicAdd(&g_tiled_phase_cycles[rw][k], ph[rw][k]);
+        atomicAdd(&g_tiled_phase_cycles[rw][7], (unsigned long long)it);
     }
 }
 
@@ -429,6 +501,33 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
     }
     unsigned grid = (unsigned)(sm_count * (int)C::kCtasPerSm);
     if (grid > ts.n_tiles) grid = ts.n_tiles;
+    if (V == 0 && !EMIT) {  // ACG_TILED_TIMING=1: run the instrumented instantiation and print its counters
+        static const bool timing = getenv("ACG_TILED_TIMING") != nullptr;
+        if (timing) {
+            cudaFuncSetAttribute(k_r1cs_tiled<P, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)C::kBytes);
+            unsigned long long z[2][8] = {};
+            cudaMemcpyToSymbolAsync(g_tiled_phase_cycles, z, sizeof z, 0, cudaMemcpyHostToDevice, s);
+            k_r1cs_tiled<P, false, 0, true><<<grid, kTileGeom[0].threads, C::kBytes, s>>>(ts, w, row_base, d_result,
+                                                                                          Aw, Bw, Cw);
+            cudaMemcpyFromSymbolAsync(z, g_tiled_phase_cycles, sizeof z, 0, cudaMemcpyDeviceToHost, s);
+            cudaStreamSynchronize(s);
+            static int printed = 0;
+            if (printed++ < 3) {
+                static const char* nm[7] = {"tma_wait", "p1", "bar1", "p2", "bar2", "p3", "bar3"};
+                for (int wsel = 0; wsel < 2; ++wsel) {
+                    fprintf(stderr, "[phase cycles/tile, %s] tiles=%llu:", wsel ? "last warp" : "warp 0", z[wsel][7]);
+                    unsigned long long tot = 0;
+                    for (int k = 0; k < 7; ++k) {
+                        fprintf(stderr, " %s=%.0f", nm[k], (double)z[wsel][k] / (double)z[wsel][7]);
+                        tot += z[wsel][k];
+                    }
+                    fprintf(stderr, " total=%.0f\n", (double)tot / (double)z[wsel][7]);
+                }
+            }
+            return cudaGetLastError();
+        }
+    }
     k_r1cs_tiled<P, EMIT, V><<<grid, kTileGeom[V].threads, C::kBytes, s>>>(ts, w, row_base, d_result, Aw, Bw, Cw);
     return cudaGetLastError();
 }

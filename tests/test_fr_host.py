@@ -51,6 +51,14 @@ def test_device_field_algorithms_on_host(hostlib, acg, F):
     assert _run(hostlib, acg, fid, 6, xs, ys) == [(x * y * Rinv) % r for x, y in zip(xs, ys)]
     assert _run(hostlib, acg, fid, 4, xs, ys) == [(x * R) % r for x in xs]
     assert _run(hostlib, acg, fid, 5, xs, ys) == [(-x) % r for x in xs]
+    # operand contract the tiled kernel's lazy row sums rely on: vector operand <= p, scalar operand any
+    # 256-bit value; fr_add on [0, p] inputs stays in [0, p]
+    lim = R - 1
+    wide = [rnd.randrange(R) for _ in range(3000)] + [lim, lim - 1, r, 2 * r, R - r, 0] * 3
+    vec = [rnd.randrange(r) for _ in range(3000)] + [r, r - 1, 0, r, 1, r] * 3
+    assert _run(hostlib, acg, fid, 7, vec, wide) == [(x * y * Rinv) % r for x, y in zip(vec, wide)]
+    got = _run(hostlib, acg, fid, 8, vec, [r] * len(vec))
+    assert all(g % r == v % r and g <= r for g, v in zip(got, vec))
     inv_in = xs[:50] + edge
     assert _run(hostlib, acg, fid, 3, inv_in, inv_in) == [pow(x, -1, r) if x else 0 for x in inv_in]
 
