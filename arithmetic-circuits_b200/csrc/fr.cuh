@@ -269,9 +269,25 @@ ACG_HD void mont_round(uint32_t nev[9], uint32_t nod[8], const uint32_t ev[9], c
     nev[7] = ptx::madc_hi_cc(a[6], bi, FIRST ? 0u : od[7]);
     nev[8] = ptx::addc(0u, 0u);
 
-    const uint32_t m = nev[0] * P::NINV32;
-    nod[0] = ptx::mad_lo_cc(P::p(1), m, nod[0]);
-    nod[1] = ptx::madc_hi_cc(P::p(1), m, nod[1]);
+    // m = -T * p^-1 mod 2^32.  BLS12-381 Fr has p0 = 1, p1 = 2^32 - 1 and -p^-1 = -1 (mod 2^32): m and the
+    // products m*p0, m*p1 then come from adds on the ALU pipe instead of the quarter-rate 32x32->64 multiplier
+    // (measured +4% on the tiled check).  The analogous rewrite for BN254 Fr (p0 = 2^32 - 2^28 + 1) was
+    // measured 5% SLOWER: four dependent ALU operations replace one multiply on the cross-round critical path.
+    uint32_t m;
+    if constexpr (P::NINV32 == 0xffffffffu)
+        m = 0u - nev[0];
+    else
+        m = nev[0] * P::NINV32;
+
+    if constexpr (P::p(1) == 0xffffffffu) {  // m * (2^32 - 1) = (m << 32) - m
+        const uint32_t lo = ptx::sub_cc(0u, m);
+        const uint32_t hi = ptx::subc(m, 0u);
+        nod[0] = ptx::add_cc(nod[0], lo);
+        nod[1] = ptx::addc_cc(nod[1], hi);
+    } else {
+        nod[0] = ptx::mad_lo_cc(P::p(1), m, nod[0]);
+        nod[1] = ptx::madc_hi_cc(P::p(1), m, nod[1]);
+    }
     nod[2] = ptx::madc_lo_cc(P::p(3), m, nod[2]);
     nod[3] = ptx::madc_hi_cc(P::p(3), m, nod[3]);
     nod[4] = ptx::madc_lo_cc(P::p(5), m, nod[4]);
@@ -279,8 +295,13 @@ ACG_HD void mont_round(uint32_t nev[9], uint32_t nod[8], const uint32_t ev[9], c
     nod[6] = ptx::madc_lo_cc(P::p(7), m, nod[6]);
     nod[7] = ptx::madc_hi(P::p(7), m, nod[7]);
 
-    nev[0] = ptx::mad_lo_cc(P::p(0), m, nev[0]);   // == 0
-    nev[1] = ptx::madc_hi_cc(P::p(0), m, nev[1]);
+    if constexpr (P::p(0) == 1u) {  // m * 1: the low word cancels nev[0] (carry iff nev[0] != 0)
+        nev[0] = ptx::add_cc(nev[0], m);
+        nev[1] = ptx::addc_cc(nev[1], 0u);
+    } else {
+        nev[0] = ptx::mad_lo_cc(P::p(0), m, nev[0]);   // == 0
+        nev[1] = ptx::madc_hi_cc(P::p(0), m, nev[1]);
+    }
     nev[2] = ptx::madc_lo_cc(P::p(2), m, nev[2]);
     nev[3] = ptx::madc_hi_cc(P::p(2), m, nev[3]);
     nev[4] = ptx::madc_lo_cc(P::p(4), m, nev[4]);
