@@ -22,7 +22,7 @@ CPP_SOURCES = ["host/circuit.cpp", "host/synth.cpp"]
 HEADERS = ["fr.cuh", "fr_constants.inc", "dev.cuh", "kernels.h", "host/fr_host.hpp", "host/circuit.hpp",
            "../../include/acg.h"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"] + os.environ.get("ACG_NVCC_EXTRA", "").split()
 
 
 def _newer(target: str, deps) -> bool:

@@ -56,9 +56,10 @@ struct acg_r1cs {
     DevR1cs dev{};
     // execution-ready tile stream of the tiled kernel (kernels.h), built for geometry `variant`
     uint8_t* d_stream = nullptr;
-    uint32_t* d_stream_off = nullptr;
-    uint2* d_windows = nullptr;
+    TileMeta* d_meta = nullptr;
+    uint32_t* d_far_cols = nullptr;
     uint64_t stream_bytes = 0;
+    uint64_t blob_bytes = 0;  // of d_stream
     uint32_t n_tiles = 0;
     int variant = 0;
     std::vector<std::pair<uint32_t, uint32_t>> long_ranges;  // local row ranges too wide for a tile
@@ -196,8 +197,9 @@ struct HostTile {
 // general-coefficient entries, and the sum of its three ELL widths (max row length per matrix) stays within
 // geom.max_slots.  Rows longer than kMaxEllWidth in any matrix (Split gates, src/QAP.hs:443-473) are left to
 // the row-wise kernel.  gcum[k][r] = number of general entries of matrix k in local rows < r.
-void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t* gcum[3], uint32_t n_local,
-                 std::vector<HostTile>& tiles, std::vector<std::pair<uint32_t, uint32_t>>& long_ranges) {
+void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t* gcum[3], const uint32_t* ccum[3],
+                 uint32_t n_local, std::vector<HostTile>& tiles,
+                 std::vector<std::pair<uint32_t, uint32_t>>& long_ranges) {
     auto add_long = [&](uint32_t a, uint32_t b) {
         if (!long_ranges.empty() && long_ranges.back().second == a)
             long_ranges.back().second = b;
@@ -208,10 +210,11 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
     while (r < n_local) {
         HostTile t{};
         t.row0 = r;
-        uint32_t g_base = 0;
+        uint32_t g_base = 0, c_base = 0;
         for (int k = 0; k < 3; ++k) {
             t.e0[k] = rp[k][r];
             g_base += gcum[k][r];
+            c_base += ccum[k][r];
         }
         uint32_t end = r;
         uint32_t width[3] = {0, 0, 0};
@@ -219,7 +222,7 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
         while (end < n_local && end - r < geom.threads) {
             const uint32_t g_end = std::min(end + 4u, n_local);
             uint32_t nw[3] = {width[0], width[1], width[2]};
-            uint64_t gen = 0;
+            uint64_t gen = 0, cst = 0;
             bool too_long = false;
             for (int k = 0; k < 3; ++k) {
                 for (uint32_t q = end; q < g_end; ++q) {
@@ -228,12 +231,19 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
                     nw[k] = std::max(nw[k], len);
                 }
                 gen += gcum[k][g_end];
+                cst += ccum[k][g_end];
             }
             if (too_long) {
                 hit_long = true;
                 break;
             }
-            if (nw[0] + nw[1] + nw[2] > geom.max_slots || gen - g_base > (uint64_t)geom.max_gen) break;
+            // products needed: general entries off column 0.  One full round of the product phase (one entry
+            // per thread) beats one round and a bit: past half a tile of rows, stop at `threads` products.
+            const uint64_t prods = (gen - g_base) - (cst - c_base);
+            if (nw[0] + nw[1] + nw[2] > geom.max_slots || prods > (uint64_t)geom.max_gen ||
+                cst - c_base > (uint64_t)geom.max_const)
+                break;
+            if (prods > (uint64_t)geom.threads && end - r >= geom.threads / 2u) break;
             for (int k = 0; k < 3; ++k) width[k] = nw[k];
             end = g_end;
         }
@@ -276,7 +286,8 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long 
     const bool prof = 2 * (ctx->prof_used + 1) <= ctx->prof_ev.size();
     if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
     if (m->n_tiles) {
-        DevTileStream ts{m->d_stream, m->d_stream_off, m->d_windows, m->n_tiles, (uint32_t)m->variant};
+        DevTileStream ts{m->d_stream, m->d_meta, m->d_far_cols, m->n_tiles, (uint32_t)m->variant,
+                         (uint32_t)(m->blob_bytes / 16), m->n_cols};
         CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin, d_result, Aw, Bw, Cw, ctx->sm_count, s));
         ++*launches;
     }
@@ -474,8 +485,8 @@ void acg_r1cs_free(acg_r1cs* m) {
         cudaFree(m->d_val[k]);
     }
     cudaFree(m->d_stream);
-    cudaFree(m->d_stream_off);
-    cudaFree(m->d_windows);
+    cudaFree(m->d_meta);
+    cudaFree(m->d_far_cols);
     delete m;
 }
 
@@ -495,7 +506,7 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     std::memcpy(minus_one, modulus, 32);
     minus_one[0] -= 1;  // r is odd
     // host pass over the uploaded slice: structural validation, coefficient tags, per-row general counts
-    std::vector<uint32_t> local_rp[3], tagged_col[3], gcum[3];
+    std::vector<uint32_t> local_rp[3], tagged_col[3], gcum[3], ccum[3];  // ccum: general entries on column 0
     for (int k = 0; k < 3; ++k) {
         const acg_csr* M = src[k];
         if (!M->rowptr || (M->nnz && (!M->col || !M->val)) || M->nnz > 0xFFFFFFF0ull)
@@ -508,11 +519,13 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
         if (e1 > M->nnz) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: rowptr exceeds nnz");
         local_rp[k].resize((size_t)n_local + 1);
         gcum[k].resize((size_t)n_local + 1);
+        ccum[k].resize((size_t)n_local + 1);
         tagged_col[k].resize((size_t)(e1 - e0));
-        uint32_t bad = 0, gen = 0;
+        uint32_t bad = 0, gen = 0, cst = 0;
         for (uint32_t r = 0; r < n_local; ++r) {
             local_rp[k][r] = M->rowptr[row_begin + r] - e0;
             gcum[k][r] = gen;
+            ccum[k][r] = cst;
             for (uint32_t e = M->rowptr[row_begin + r]; e < M->rowptr[row_begin + r + 1]; ++e) {
                 const uint32_t c = M->col[e];
                 bad |= (c >= n_cols);
@@ -523,11 +536,13 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
                 else if (v[0] == minus_one[0] && v[1] == minus_one[1] && v[2] == minus_one[2] && v[3] == minus_one[3])
                     tag = kTagMinusOne;
                 gen += (tag == kTagGeneral);
+                cst += (tag == kTagGeneral && c == 0u);
                 tagged_col[k][e - e0] = (c & kColMask) | (tag << 30);
             }
         }
         local_rp[k][n_local] = e1 - e0;
         gcum[k][n_local] = gen;
+        ccum[k][n_local] = cst;
         if (bad) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: column index >= n_cols");
     }
     acg_r1cs* m = new (std::nothrow) acg_r1cs();
@@ -575,14 +590,16 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     // tiles and their static lists of general entries (pool indices, uint16)
     const uint32_t* rp[3] = {local_rp[0].data(), local_rp[1].data(), local_rp[2].data()};
     const uint32_t* gc[3] = {gcum[0].data(), gcum[1].data(), gcum[2].data()};
+    const uint32_t* cc[3] = {ccum[0].data(), ccum[1].data(), ccum[2].data()};
     // ---- tile stream (see kernels.h): one self-contained blob per tile, entries in ELL order
     m->variant = ctx->tiled_variant;
     const TileGeometry geom = kTileGeom[m->variant];
     std::vector<HostTile> tiles;
-    build_tiles(geom, rp, gc, n_local, tiles, m->long_ranges);
+    build_tiles(geom, rp, gc, cc, n_local, tiles, m->long_ranges);
     std::vector<uint8_t> stream;
-    std::vector<uint32_t> offs, gval_offs;  // 16-byte units
-    std::vector<uint2> windows;
+    std::vector<uint32_t> gval_offs;  // 16-byte units
+    std::vector<TileMeta> metas;
+    std::vector<uint32_t> far_all;
     stream.reserve((size_t)n_local * 96 + 4096);
     auto align16 = [&]() { stream.resize((stream.size() + 15) & ~(size_t)15, 0); };
     auto put16 = [&](uint16_t v) {
@@ -596,7 +613,12 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     std::vector<uint32_t> ref_cols, far_cols;
     // a tile whose distinct far references exceed the far slots is split in two (rows stay multiples of 4)
     std::vector<HostTile> work(tiles.rbegin(), tiles.rend());
-    uint32_t n_tiles_out = 0;
+    struct FinalTile {
+        HostTile t;
+        uint32_t win_lo, win_n, far_off, n_far;
+    };
+    std::vector<FinalTile> final_tiles;
+    // ---- pass 1: window and far columns of every tile (splitting tiles with too many far columns)
     while (!work.empty()) {
         HostTile t = work.back();
         work.pop_back();
@@ -644,97 +666,139 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
             m->long_ranges.emplace_back(t.row0, t.row0 + t.nrows);
             continue;
         }
+        FinalTile ft{};
+        ft.t = t;
+        ft.win_lo = win_lo;
+        ft.win_n = win_n;
+        ft.far_off = (uint32_t)far_all.size();
+        ft.n_far = (uint32_t)far_cols.size();
+        far_all.insert(far_all.end(), far_cols.begin(), far_cols.end());
+        final_tiles.push_back(ft);
+    }
+    // ---- pass 2: emit the blobs.  Blob i also carries what the kernel needs to start tile i + 1 while blob i is
+    //      still the only one in shared memory: its far witness columns and, in the header, its size and window.
+    std::vector<size_t> bases;
+    for (size_t ti = 0; ti < final_tiles.size(); ++ti) {
+        const FinalTile& ft = final_tiles[ti];
+        const HostTile& t = ft.t;
+        const uint32_t win_lo = ft.win_lo, win_n = ft.win_n;
+        const uint32_t* far_b = far_all.data() + ft.far_off;
+        const uint32_t* far_e = far_b + ft.n_far;
         auto slot_of = [&](uint32_t c) -> uint32_t {  // witness column -> term slot
             if (c >= win_lo && c - win_lo < win_n) return c - win_lo;
-            return geom.window + (uint32_t)(std::lower_bound(far_cols.begin(), far_cols.end(), c) - far_cols.begin());
+            return geom.window + (uint32_t)(std::lower_bound(far_b, far_e, c) - far_b);
         };
         align16();
         const size_t base = stream.size();
-        offs.push_back((uint32_t)(base / 16));
-        windows.push_back(make_uint2(win_lo, win_n));
-        ++n_tiles_out;
+        bases.push_back(base);
+        TileMeta tm{};
+        tm.blob_off16 = (uint32_t)(base / 16);
+        tm.win_lo = win_lo;
+        tm.win_n = win_n;
+        tm.far_off = ft.far_off;
+        tm.n_far = ft.n_far;
         stream.resize(base + sizeof(TileHeader), 0);
         TileHeader h{};
         h.row0 = t.row0;
         h.nrows = t.nrows;
-        h.win_lo = win_lo;
-        h.win_n = win_n;
-        h.n_far = (uint32_t)far_cols.size();
         for (int k = 0; k < 3; ++k) h.width[k] = t.width[k];
-        // entry words, slot-major; general entries are numbered A rows, then B rows, then C rows, entry order
-        h.off_words = (uint32_t)(stream.size() - base);
-        uint32_t g_before = 0;
-        std::vector<uint32_t> gen_first((size_t)t.nrows + 1);
+        if (ti + 1 < final_tiles.size()) {
+            const FinalTile& nx = final_tiles[ti + 1];
+            h.next_win_lo = nx.win_lo;
+            h.next_win_n = nx.win_n;
+            h.next_n_far = nx.n_far;
+        }
+        // general entries, numbered A rows, then B rows, then C rows, entry order -- separately for the ones that
+        // need a product (gid >= 0: product index) and the ones on column 0 (gid < 0: ~index among those)
+        std::vector<int32_t> gid[3];
+        uint32_t n_prod = 0, n_const = 0;
         for (int k = 0; k < 3; ++k) {
-            uint32_t run = g_before;
-            for (uint32_t r = 0; r < t.nrows; ++r) {
-                gen_first[r] = run;
-                for (uint32_t e = local_rp[k][t.row0 + r]; e < local_rp[k][t.row0 + r + 1]; ++e)
-                    run += (tagged_col[k][e] >> 30) == kTagGeneral;
+            gid[k].assign(t.ne[k], 0);
+            for (uint32_t e = 0; e < t.ne[k]; ++e) {
+                const uint32_t word = tagged_col[k][t.e0[k] + e];
+                if ((word >> 30) != kTagGeneral) continue;
+                gid[k][e] = (word & kColMask) == 0u ? ~(int32_t)(n_const++) : (int32_t)(n_prod++);
             }
+        }
+        h.n_general = n_prod;
+        h.n_const = n_const;
+        // layout (offsets from the blob start; the blob lands at shared-memory offset 0)
+        auto up = [](uint32_t x, uint32_t a) { return (x + a - 1) / a * a; };
+        h.off_words = (uint32_t)sizeof(TileHeader);
+        h.off_next_far = up(h.off_words + (t.width[0] + t.width[1] + t.width[2]) * t.nrows * 4u, 16);
+        h.off_gop = up(h.off_next_far + h.next_n_far * 4u, 16);
+        h.off_gval = up(h.off_gop + n_prod * 2u, 32);
+        const uint32_t term_base = tile_terms_offset(geom) / 32u;  // 32-byte units from the start of shared memory
+        // entry words, slot-major
+        for (int k = 0; k < 3; ++k)
             for (uint32_t j = 0; j < t.width[k]; ++j)
                 for (uint32_t r = 0; r < t.nrows; ++r) {
                     const uint32_t s0 = local_rp[k][t.row0 + r], s1 = local_rp[k][t.row0 + r + 1];
                     if (s0 + j >= s1) {
-                        put32(kZero);
+                        put32(term_base + kZero);
                         continue;
                     }
                     const uint32_t word = tagged_col[k][s0 + j];
                     const uint32_t tag = word >> 30;
                     if (tag == kTagGeneral) {
-                        uint32_t ord = gen_first[r];
-                        for (uint32_t e = s0; e < s0 + j; ++e) ord += (tagged_col[k][e] >> 30) == kTagGeneral;
-                        put32(kProd0 + ord);
+                        const int32_t g = gid[k][s0 + j - t.e0[k]];
+                        put32(g >= 0 ? term_base + kProd0 + (uint32_t)g
+                                     : h.off_gval / 32u + n_prod + (uint32_t)(~g));
                     } else {
-                        put32((tag == kTagMinusOne ? kTermSign : 0u) | slot_of(word & kColMask));
+                        put32((tag == kTagMinusOne ? kTermSign : 0u) | (term_base + slot_of(word & kColMask)));
                     }
                 }
-            g_before = run;
-        }
-        h.n_general = g_before;
-        align16();
-        h.off_far = (uint32_t)(stream.size() - base);
-        for (uint32_t c : far_cols) put32(c);
-        align16();
-        h.off_gop = (uint32_t)(stream.size() - base);
+        stream.resize(base + h.off_next_far, 0);
+        for (uint32_t f = 0; f < h.next_n_far; ++f) put32(far_all[final_tiles[ti + 1].far_off + f]);
+        stream.resize(base + h.off_gop, 0);
         for (int k = 0; k < 3; ++k)
             for (uint32_t e = 0; e < t.ne[k]; ++e) {
                 const uint32_t word = tagged_col[k][t.e0[k] + e];
-                if ((word >> 30) == kTagGeneral) put16((uint16_t)slot_of(word & kColMask));
+                if ((word >> 30) == kTagGeneral && gid[k][e] >= 0)
+                    put16((uint16_t)(term_base + slot_of(word & kColMask)));
             }
-        align16();
-        h.off_gval = (uint32_t)(stream.size() - base);
+        stream.resize(base + h.off_gval + (size_t)(n_prod + n_const) * 32u, 0);
         for (int k = 0; k < 3; ++k) {
             const acg_csr* M = src[k];
             const uint32_t g0 = M->rowptr[row_begin];
             for (uint32_t e = 0; e < t.ne[k]; ++e)
                 if ((tagged_col[k][t.e0[k] + e] >> 30) == kTagGeneral) {
-                    gval_offs.push_back((uint32_t)(stream.size() / 16));
-                    const uint8_t* v8 = reinterpret_cast<const uint8_t*>(M->val + 4ull * (g0 + t.e0[k] + e));
-                    stream.insert(stream.end(), v8, v8 + 32);
+                    const int32_t g = gid[k][e];
+                    const size_t at = base + h.off_gval + (size_t)(g >= 0 ? (uint32_t)g : n_prod + (uint32_t)(~g)) * 32u;
+                    gval_offs.push_back((uint32_t)(at / 16));
+                    std::memcpy(stream.data() + at, M->val + 4ull * (g0 + t.e0[k] + e), 32);
                 }
         }
         align16();
         h.bytes = (uint32_t)(stream.size() - base);
         std::memcpy(stream.data() + base, &h, sizeof h);
+        tm.blob_bytes = h.bytes;
+        metas.push_back(tm);
     }
+    for (size_t ti = 0; ti + 1 < metas.size(); ++ti) {  // next_bytes: known once the next blob is laid out
+        const uint32_t nb = metas[ti + 1].blob_bytes;
+        std::memcpy(stream.data() + bases[ti] + offsetof(TileHeader, next_bytes), &nb, sizeof nb);
+    }
+    const uint32_t n_tiles_out = (uint32_t)metas.size();
     std::sort(m->long_ranges.begin(), m->long_ranges.end());
     align16();
-    offs.push_back((uint32_t)(stream.size() / 16));
     if (stream.size() / 16 > 0xFFFFFFF0ull) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_r1cs_upload: tile stream too large");
     m->n_tiles = n_tiles_out;
-    m->stream_bytes = stream.size();
+    // what one check streams from HBM besides the witness: blobs, tile records, far column lists
+    m->blob_bytes = stream.size();
+    m->stream_bytes = stream.size() + metas.size() * sizeof(TileMeta) + far_all.size() * sizeof(uint32_t);
     DevBuf d_goffs;
     CU(ctx, cudaMalloc(&m->d_stream, stream.size() + 64));
-    CU(ctx, cudaMalloc(&m->d_stream_off, offs.size() * sizeof(uint32_t)));
-    CU(ctx, cudaMalloc(&m->d_windows, (windows.size() + 1) * sizeof(uint2)));
-    if (!windows.empty())
-        CU(ctx, cudaMemcpyAsync(m->d_windows, windows.data(), windows.size() * sizeof(uint2), cudaMemcpyHostToDevice,
+    CU(ctx, cudaMalloc(&m->d_meta, (metas.size() + 1) * sizeof(TileMeta)));
+    CU(ctx, cudaMalloc(&m->d_far_cols, (far_all.size() + 4) * sizeof(uint32_t)));
+    if (!metas.empty())
+        CU(ctx, cudaMemcpyAsync(m->d_meta, metas.data(), metas.size() * sizeof(TileMeta), cudaMemcpyHostToDevice,
                                 ctx->stream));
+    if (!far_all.empty())
+        CU(ctx, cudaMemcpyAsync(m->d_far_cols, far_all.data(), far_all.size() * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, d_goffs.alloc(gval_offs.size() * sizeof(uint32_t)));
     CU(ctx, cudaMemcpyAsync(m->d_stream, stream.data(), stream.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(m->d_stream_off, offs.data(), offs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                            ctx->stream));
     if (!gval_offs.empty()) {
         CU(ctx, cudaMemcpyAsync(d_goffs.p, gval_offs.data(), gval_offs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                 ctx->stream));

@@ -47,6 +47,36 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// Same copy for data that is read exactly once per pass (the tile stream): L2 evict-first, so that the stream
+// does not push the witness -- which every tile re-reads through windows and far gathers -- out of L2.
+#ifndef ACG_STREAM_EVICT_FIRST
+#define ACG_STREAM_EVICT_FIRST 1
+#endif
+__device__ __forceinline__ void tma_load_1d_stream(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+#if ACG_STREAM_EVICT_FIRST
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+#else
+    tma_load_1d(smem_dst, gmem_src, bytes, bar);
+#endif
+}
+// pull [p, p + bytes) towards L2 (bytes % 16 == 0, p 16-byte aligned); no completion to wait for
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// one witness element (32 bytes) through the read-only path
+__device__ __forceinline__ fr_t ld_witness(const fr_t* p) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
 // order this thread's generic-proxy shared-memory accesses before later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -346,6 +346,41 @@ ACG_HD fr_t fr_mul(const fr_t& a, const fr_t& b) {
     t[7] = ptx::addc(o1[7], e1[8]);
     return fr_reduce_once<P>(t);
 }
+// Two independent Montgomery products with their rounds alternating in program order: every carry chain is
+// self-contained (it starts without carry-in and ends without carry-out), so the interleaving is legal at the
+// PTX level, and ptxas -- which renames the carry flag into predicates -- overlaps the two dependency chains.
+// For latency-bound callers that have two products to do (the second one costs much less than a full product).
+template <class P>
+ACG_HD void fr_mul2(fr_t& r0, fr_t& r1, const fr_t& a0, const fr_t& b0, const fr_t& a1, const fr_t& b1) {
+    uint32_t e0[9], o0[8], e1[9], o1[8], f0[9], g0[8], f1[9], g1[8];
+    mont_round<P, true>(e0, o0, e0, o0, a0.l, b0.l[0]);
+    mont_round<P, true>(f0, g0, f0, g0, a1.l, b1.l[0]);
+    mont_round<P, false>(e1, o1, e0, o0, a0.l, b0.l[1]);
+    mont_round<P, false>(f1, g1, f0, g0, a1.l, b1.l[1]);
+    mont_round<P, false>(e0, o0, e1, o1, a0.l, b0.l[2]);
+    mont_round<P, false>(f0, g0, f1, g1, a1.l, b1.l[2]);
+    mont_round<P, false>(e1, o1, e0, o0, a0.l, b0.l[3]);
+    mont_round<P, false>(f1, g1, f0, g0, a1.l, b1.l[3]);
+    mont_round<P, false>(e0, o0, e1, o1, a0.l, b0.l[4]);
+    mont_round<P, false>(f0, g0, f1, g1, a1.l, b1.l[4]);
+    mont_round<P, false>(e1, o1, e0, o0, a0.l, b0.l[5]);
+    mont_round<P, false>(f1, g1, f0, g0, a1.l, b1.l[5]);
+    mont_round<P, false>(e0, o0, e1, o1, a0.l, b0.l[6]);
+    mont_round<P, false>(f0, g0, f1, g1, a1.l, b1.l[6]);
+    mont_round<P, false>(e1, o1, e0, o0, a0.l, b0.l[7]);
+    mont_round<P, false>(f1, g1, f0, g0, a1.l, b1.l[7]);
+    uint32_t t[8], u[8];
+    t[0] = ptx::add_cc(o1[0], e1[1]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) t[i] = ptx::addc_cc(o1[i], e1[i + 1]);
+    t[7] = ptx::addc(o1[7], e1[8]);
+    u[0] = ptx::add_cc(g1[0], f1[1]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) u[i] = ptx::addc_cc(g1[i], f1[i + 1]);
+    u[7] = ptx::addc(g1[7], f1[8]);
+    r0 = fr_reduce_once<P>(t);
+    r1 = fr_reduce_once<P>(u);
+}
 template <class P>
 ACG_HD fr_t fr_sqr(const fr_t& a) {
     return fr_mul<P>(a, a);

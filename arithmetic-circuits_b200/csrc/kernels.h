@@ -40,25 +40,37 @@ struct DevR1cs {
 //     [.., + max_gen)                     products coefficient * operand of the general-coefficient entries
 //     last slot                           zero (padding)
 // Blob = header | entry words in ELL (slot-major) order: for matrix A, then B, then C, for slot
-// j < width[k], for row r < nrows: one 32-bit word = sign<<31 | term slot (coefficient -1 sets the sign;
-// general entries point at their product slot, padding at the zero slot) | u32 witness columns of the far
-// slots | u16 operand slots of the general entries | their coefficient values (Montgomery).
-// Every section is 16-byte aligned.  Row r of the tile is handled by thread r, so slot-major order makes
+// j < width[k], for row r < nrows: one 32-bit word = sign<<31 | term address in 32-byte units from the start
+// of shared memory (coefficient -1 sets the sign; general entries point at their product slot, padding at the
+// zero slot) | u32 far witness columns of the next tile | u16 operand addresses of the general entries | their
+// coefficient values (Montgomery; 32-byte aligned in shared memory), followed by the coefficient values of
+// the general entries ON COLUMN 0.  Column 0 is the constant wire of the reference (w[0] = 1 by construction:
+// initialQapSet, src/QAP.hs:591-595; qapSetToMap puts it at index 0, :605-620), so coefficient * w[0] is the
+// coefficient itself: the entry word of such an entry points at the coefficient inside the blob and no product
+// is computed.  The kernel checks w[0] == 1 at run time and, if a caller passes something else, multiplies
+// these coefficients by w[0] in place first -- the result is the same for every witness.
+// Every section is 16-byte aligned.
+// A CTA walks a CONTIGUOUS run of tiles, so the stream is linear per CTA.  What the kernel must know before
+// a blob is in shared memory travels one blob earlier: blob i carries the far witness columns of tile i + 1
+// and, in its header, that tile's blob size and window.  With them the CTA issues the bulk copies of tile
+// i + 1 and gathers its far witness elements the moment tile i is done, without a dependent global read.
+// Only the first tile of a run is described from outside (TileMeta, DevTileStream::far_cols).  Row r of the tile is handled by thread r, so slot-major order makes
 // every word read of a warp contiguous and the control flow of the row sums warp-uniform.
 struct alignas(16) TileHeader {
-    uint32_t row0;       // first (shard-local) row
+    uint32_t row0;          // first (shard-local) row
     uint32_t nrows;
     uint32_t n_general;
-    uint32_t n_far;
-    uint32_t width[3];   // ELL widths (max row length in the tile) of A, B, C
-    uint32_t off_words;  // byte offsets inside the blob
-    uint32_t off_far;
+    uint32_t bytes;         // blob size (multiple of 16)
+    uint32_t width[3];      // ELL widths (max row length in the tile) of A, B, C
+    uint32_t off_words;     // byte offsets inside the blob
     uint32_t off_gop;
     uint32_t off_gval;
-    uint32_t bytes;      // blob size (multiple of 16)
-    uint32_t win_lo;     // witness window [win_lo, win_lo + win_n)
-    uint32_t win_n;
-    uint32_t pad[2];
+    uint32_t off_next_far;  // u32 far witness columns of the NEXT tile of the stream
+    uint32_t next_n_far;    // .. and what else is needed to start loading it: its far count,
+    uint32_t next_bytes;    //    blob size (it starts where this blob ends)
+    uint32_t next_win_lo;   //    and witness window [next_win_lo, next_win_lo + next_win_n)
+    uint32_t next_win_n;
+    uint32_t n_const;       // general entries on column 0 (values follow the n_general product coefficients)
 };
 static_assert(sizeof(TileHeader) == 64, "TileHeader must be 64 bytes");
 constexpr uint32_t kTermSign = 0x80000000u;
@@ -67,27 +79,47 @@ constexpr uint32_t kTermSign = 0x80000000u;
 struct TileGeometry {
     uint32_t threads;    // == max rows per tile
     uint32_t max_slots;  // sum of the three ELL widths (rows longer than kMaxEllWidth go to the row-wise kernel)
-    uint32_t max_gen;    // general-coefficient entries per tile
+    uint32_t max_gen;    // general-coefficient entries per tile that need a product (column != 0)
     uint32_t window;     // witness elements staged per tile
     uint32_t max_far;    // distinct witness columns outside the window per tile
+    uint32_t max_const;  // general-coefficient entries per tile on column 0 (the constant wire)
 };
 constexpr uint32_t kMaxEllWidth = 8;
 constexpr int kNumTileVariants = 4;
 constexpr TileGeometry kTileGeom[kNumTileVariants] = {
-    {128, 12, 192, 192, 320}, {256, 12, 384, 320, 640}, {64, 12, 96, 128, 160}, {32, 12, 64, 96, 96}};
+    {128, 10, 160, 192, 288, 96}, {256, 10, 320, 320, 576, 192}, {64, 10, 96, 128, 160, 64}, {32, 10, 64, 96, 96, 32}};
 constexpr uint32_t tile_blob_capacity(const TileGeometry& g) {
-    return 64u + g.threads * g.max_slots * 4u + g.max_far * 4u + ((g.max_gen * 2u + 15u) / 16u) * 16u + g.max_gen * 32u;
+    return 64u + g.threads * g.max_slots * 4u + g.max_far * 4u + ((g.max_gen * 2u + 15u) / 16u) * 16u + 16u +
+           (g.max_gen + g.max_const) * 32u;
 }
+// shared-memory offset of the term array (the blob sits at offset 0); entry words and operand words address
+// 32-byte units from the start of shared memory, so that a word can also point INTO the blob (see below)
+constexpr uint32_t tile_terms_offset(const TileGeometry& g) {
+    return (tile_blob_capacity(g) + 127u) / 128u * 128u;
+}
+// far gathers per thread (the far witness columns of a tile are gathered tid, tid + threads, ...)
+constexpr uint32_t kFarPerThread = 3;
 constexpr uint32_t tile_term_slots(const TileGeometry& g) {
     return g.window + g.max_far + g.max_gen + 1u;
 }
 
+struct alignas(32) TileMeta {
+    uint32_t blob_off16;  // blob offset in 16-byte units
+    uint32_t blob_bytes;  // multiple of 16
+    uint32_t win_lo;      // witness window [win_lo, win_lo + win_n)
+    uint32_t win_n;
+    uint32_t far_off;     // first entry of the tile in DevTileStream::far_cols
+    uint32_t n_far;
+    uint32_t pad[2];
+};
 struct DevTileStream {
-    const uint8_t* blobs;      // concatenated tile blobs
-    const uint32_t* offsets;   // n_tiles + 1 offsets in 16-byte units
-    const uint2* windows;      // per tile {win_lo, win_n}
+    const uint8_t* blobs;       // concatenated tile blobs
+    const TileMeta* meta;       // n_tiles records
+    const uint32_t* far_cols;   // witness columns of the far slots, tile after tile
     uint32_t n_tiles;
     uint32_t variant;
+    uint32_t blobs_len16;       // length of `blobs` in 16-byte units
+    uint32_t n_cols;            // witness length
 };
 
 cudaError_t launch_to_mont(int field, fr_t* v, uint64_t n, int* d_bad_flag, cudaStream_t s);

@@ -147,6 +147,12 @@ __global__ void k_validate_csr(const uint32_t* __restrict__ rowptr, const uint32
 // ------------------------------------------------------------------------------------------------
 // tiled kernel
 // ------------------------------------------------------------------------------------------------
+#ifndef ACG_K2_ILP2
+#define ACG_K2_ILP2 0
+#endif
+#ifndef ACG_K2_REGS
+#define ACG_K2_REGS 96u
+#endif
 namespace tiled {
 constexpr uint32_t align_up(uint32_t x, uint32_t a) {
     return (x + a - 1) / a * a;
@@ -159,13 +165,12 @@ struct Cfg {
     static constexpr uint32_t kFar0 = kWin;                              // first far slot
     static constexpr uint32_t kProd0 = kWin + kTileGeom[V].max_far;      // first product slot
     static constexpr uint32_t kZero = tile_term_slots(kTileGeom[V]) - 1u;  // the zero slot
-    static constexpr uint32_t kBlobCap = align_up(tile_blob_capacity(kTileGeom[V]), 128);
-    static constexpr uint32_t kOffTerms = kBlobCap;
+    static constexpr uint32_t kOffTerms = tile_terms_offset(kTileGeom[V]);
     static constexpr uint32_t kBytes = kOffTerms + tile_term_slots(kTileGeom[V]) * 32;
     // resident CTAs per SM: bounded by shared memory (227 KB, 1 KB per CTA reserved), by 96 registers per
     // thread and by the hardware limit of 32
     static constexpr uint32_t kCtasBySmem = (227u * 1024u) / (kBytes + 1024u + 64u);
-    static constexpr uint32_t kCtasByRegs = 65536u / (kThreads * 96u);
+    static constexpr uint32_t kCtasByRegs = 65536u / (kThreads * ACG_K2_REGS);
     static constexpr uint32_t kCtasMin = kCtasBySmem < kCtasByRegs ? kCtasBySmem : kCtasByRegs;
     static constexpr uint32_t kCtasPerSm = kCtasMin > 32u ? 32u : kCtasMin;
 };
@@ -198,15 +203,23 @@ __device__ __forceinline__ fr_t neg_lazy(const fr_t& x) {
     r.l[7] = ptx::subc(P::p(7), x.l[7]);
     return r;
 }
-// one thread: bulk copies of the tile blob and of the tile's witness window (into the first term slots)
-__device__ __forceinline__ void issue_tile_load(const DevTileStream& ts, const fr_t* __restrict__ w, uint32_t tile,
+// one thread: bulk copies of a tile blob and of the tile's witness window (into the first term slots)
+__device__ __forceinline__ void issue_tile_load(const DevTileStream& ts, const fr_t* __restrict__ w, uint32_t blob_off16,
+                                                uint32_t blob_bytes, uint32_t win_lo, uint32_t win_n,
                                                 uint8_t* blob_dst, uint8_t* win_dst, uint64_t* bar) {
-    const uint32_t o0 = ts.offsets[tile], o1 = ts.offsets[tile + 1];
-    const uint32_t bytes = (o1 - o0) * 16u;
-    const uint2 win = ts.windows[tile];  // {win_lo, win_n}
-    mbar_arrive_expect_tx(bar, bytes + win.y * 32u);
-    tma_load_1d(blob_dst, ts.blobs + (size_t)o0 * 16u, bytes, bar);
-    if (win.y) tma_load_1d(win_dst, w + win.x, win.y * 32u, bar);
+    mbar_arrive_expect_tx(bar, blob_bytes + win_n * 32u);
+    tma_load_1d_stream(blob_dst, ts.blobs + (size_t)blob_off16 * 16u, blob_bytes, bar);
+    if (win_n) tma_load_1d(win_dst, w + win_lo, win_n * 32u, bar);
+}
+// one thread: pull what most likely comes after the tile being loaded towards L2 -- the stream is linear per
+// CTA and windows of successive tiles are (for circuits built gate by gate) successive slices of w, so the
+// guess "as much again, right behind" is good; a wrong guess only wastes a prefetch
+__device__ __forceinline__ void prefetch_behind(const DevTileStream& ts, const fr_t* __restrict__ w, uint32_t blob_off16,
+                                                uint32_t blob_bytes, uint32_t win_lo, uint32_t win_n) {
+    const uint32_t o = blob_off16 + blob_bytes / 16u;
+    if (o < ts.blobs_len16) prefetch_l2_bulk(ts.blobs + (size_t)o * 16u, min(blob_bytes, (ts.blobs_len16 - o) * 16u));
+    const uint32_t c = win_lo + win_n;
+    if (c < ts.n_cols) prefetch_l2_bulk(w + c, min(win_n, ts.n_cols - c) * 32u);
 }
 }  // namespace tiled
 
@@ -296,9 +309,14 @@ __device__ __forceinline__ fr_t canonical(fr_t x) {
 }
 }  // namespace tiled
 
-// phase cycle counters of the TIMING instantiation (a measurement aid, see tools/phase_timing.py)
+// phase cycle counters of the TIMING instantiation (a measurement aid: ACG_TILED_TIMING=1)
 __device__ unsigned long long g_tiled_phase_cycles[2][8];
 
+// One CTA walks a contiguous run of tiles.  While tile i computes, the blob and window of tile i + 1 are already
+// in (or on their way to) L2 (cp.async.bulk.prefetch.L2 issued a tile earlier); the moment P3 of tile i is done
+// the CTA issues the bulk copies of tile i + 1 and -- with the far witness columns that blob i carried --
+// gathers its far witness elements, all loads of a thread in flight together and overlapping the bulk copies.
+// Memory latency per tile is one L2 round trip instead of a DRAM bulk copy followed by a dependent gather.
 template <class P, bool EMIT, int V, bool TIMING = false>
 __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerSm)
     k_r1cs_tiled(DevTileStream ts, const fr_t* __restrict__ w, uint64_t row_base,
@@ -306,13 +324,13 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
                  fr_t* __restrict__ Cw) {
     using namespace tiled;
     using C = Cfg<V>;
+    static_assert(kTileGeom[V].max_far <= kFarPerThread * C::kThreads, "far slots exceed the per-thread gathers");
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar;
     __shared__ unsigned long long ph[2][8];  // TIMING only: per-phase cycles seen by warp 0 and by the last warp
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
-    const uint32_t n_tiles = ts.n_tiles;
     const bool rec = TIMING && (tid == 0u || tid == C::kThreads - 32u);
     const uint32_t rw = tid == 0u ? 0u : 1u;
     long long t_last = 0;
@@ -324,51 +342,89 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         }
     };
     if (TIMING && tid < 16u) ph[tid >> 3][tid & 7u] = 0ull;
-    const uint8_t* blob = smem;
+    uint8_t* blob = smem;
     uint4* terms = reinterpret_cast<uint4*>(smem + C::kOffTerms);
-    if (tid == 0) {
-        mbar_init(&full_bar, 1);
-        mbar_fence_init();
+    const uint4* smem4 = reinterpret_cast<const uint4*>(smem);  // entry / operand words address 32-byte units from here
+    // column 0 is the constant wire: w[0] == 1 for every witness the reference builds, and then a general
+    // coefficient on column 0 is its own product (kernels.h); anything else takes the multiply-in-place path
+    const bool w0_is_one = fr_is_one<P>(ld_witness(w));
+    // this CTA's run of tiles
+    const uint32_t t_begin = (uint32_t)((uint64_t)blockIdx.x * ts.n_tiles / gridDim.x);
+    const uint32_t t_end = (uint32_t)((uint64_t)(blockIdx.x + 1u) * ts.n_tiles / gridDim.x);
+    if (t_begin >= t_end) return;
+    // gather this thread's far witness elements (far slot f = tid + k * threads) : all loads, then the stores
+    auto gather_far = [&](uint32_t n_far, const uint32_t (&idx)[kFarPerThread]) {
+        fr_t x[kFarPerThread];
+#pragma unroll
+        for (uint32_t k = 0; k < kFarPerThread; ++k)
+            if (tid + k * C::kThreads < n_far) x[k] = ld_witness(w + idx[k]);
+#pragma unroll
+        for (uint32_t k = 0; k < kFarPerThread; ++k)
+            if (tid + k * C::kThreads < n_far) store_term(terms, C::kFar0 + tid + k * C::kThreads, x[k]);
+    };
+
+    uint32_t next_off16;  // where the next blob starts (thread 0)
+    {
+        const TileMeta tm = ts.meta[t_begin];  // the first tile of the run is described from outside
+        if (tid == 0) {
+            mbar_init(&full_bar, 1);
+            mbar_fence_init();
+            store_term(terms, C::kZero, fr_zero<P>());
+            issue_tile_load(ts, w, tm.blob_off16, tm.blob_bytes, tm.win_lo, tm.win_n, smem, smem + C::kOffTerms,
+                            &full_bar);
+            prefetch_behind(ts, w, tm.blob_off16, tm.blob_bytes, tm.win_lo, tm.win_n);
+        }
+        next_off16 = tm.blob_off16 + tm.blob_bytes / 16u;
+        uint32_t idx[kFarPerThread];
+#pragma unroll
+        for (uint32_t k = 0; k < kFarPerThread; ++k) {
+            const uint32_t f = tid + k * C::kThreads;
+            idx[k] = f < tm.n_far ? ts.far_cols[tm.far_off + f] : 0u;
+        }
+        gather_far(tm.n_far, idx);
     }
-    __syncthreads();
-    if (tid == 0 && blockIdx.x < n_tiles)
-        issue_tile_load(ts, w, blockIdx.x, smem, smem + C::kOffTerms, &full_bar);
+    __syncthreads();  // mbarrier initialised before anyone waits on it
 
     uint32_t it = 0;
     if (TIMING) t_last = clock64();
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t tile = t_begin; tile < t_end; ++tile, ++it) {
         mbar_wait(&full_bar, it & 1u);
         mark(0);
+        __syncthreads();  // far slots written by every thread
+        mark(1);
         const TileHeader h = *reinterpret_cast<const TileHeader*>(blob);
         const uint32_t* words = reinterpret_cast<const uint32_t*>(blob + h.off_words);
-        const uint32_t* far = reinterpret_cast<const uint32_t*>(blob + h.off_far);
         const uint16_t* gop = reinterpret_cast<const uint16_t*>(blob + h.off_gop);
-        const uint8_t* gval = blob + h.off_gval;
-
-        // ---- P1: the distinct far witness elements of the tile -> far slots (one 256-bit load each, all of a
-        //          thread's loads in flight together)
-        for (uint32_t f = tid; f < h.n_far; f += 3u * C::kThreads) {
-            const uint32_t f1 = f + C::kThreads, f2 = f + 2u * C::kThreads;
-            fr_t x0, x1, x2;
-            x0 = w[far[f]];
-            if (f1 < h.n_far) x1 = w[far[f1]];
-            if (f2 < h.n_far) x2 = w[far[f2]];
-            store_term(terms, C::kFar0 + f, x0);
-            if (f1 < h.n_far) store_term(terms, C::kFar0 + f1, x1);
-            if (f2 < h.n_far) store_term(terms, C::kFar0 + f2, x2);
-        }
-        if (tid == 0) store_term(terms, C::kZero, fr_zero<P>());
-        mark(1);
-        __syncthreads();
-        mark(2);
+        uint8_t* gval = blob + h.off_gval;
 
         // ---- P2: dense 256-bit Montgomery products, one general entry per lane (no divergence between
         //          coefficient kinds): product slot <- coefficient * operand slot
+#if ACG_K2_ILP2
+        //          a lane that has two entries interleaves the two products (fr_mul2)
+        for (uint32_t j = tid; j < h.n_general; j += 2u * C::kThreads) {
+            const uint32_t j1 = j + C::kThreads;
+            if (j1 < h.n_general) {
+                fr_t r0, r1;
+                fr_mul2<P>(r0, r1, load_fr16(gval + (size_t)j * 32u), load_term(smem4, gop[j]),
+                           load_fr16(gval + (size_t)j1 * 32u), load_term(smem4, gop[j1]));
+                store_term(terms, C::kProd0 + j, r0);
+                store_term(terms, C::kProd0 + j1, r1);
+            } else {
+                store_term(terms, C::kProd0 + j, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), load_term(smem4, gop[j])));
+            }
+        }
+#else
         for (uint32_t j = tid; j < h.n_general; j += C::kThreads)
-            store_term(terms, C::kProd0 + j, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), load_term(terms, gop[j])));
-        mark(3);
+            store_term(terms, C::kProd0 + j, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), load_term(smem4, gop[j])));
+#endif
+        if (!w0_is_one) {  // not a witness of the reference: coefficient * w[0] in place, inside the blob
+            const fr_t w0 = ld_witness(w);
+            for (uint32_t j = h.n_general + tid; j < h.n_general + h.n_const; j += C::kThreads)
+                store_term(reinterpret_cast<uint4*>(gval), j, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), w0));
+        }
+        mark(2);
         __syncthreads();
-        mark(4);
+        mark(3);
 
         // ---- P3: thread per row, warp-uniform, shared memory only: the sums A.w, B.w, C.w advance together
         //          slot by slot (three independent carry chains); a -1 coefficient negates under a predicate
@@ -377,11 +433,11 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
             const uint32_t wA = h.width[0], wB = h.width[1], wC = h.width[2];
             fr_t a, b, c;
             if (wA == 3u && wB == 3u && wC == 1u) {  // the common shape: straight-line code, no predicates
-                row_sums_fixed<P, 3, 3, 1>(terms, words + tid, h.nrows, a, b, c);
+                row_sums_fixed<P, 3, 3, 1>(smem4, words + tid, h.nrows, a, b, c);
             } else if (wA == 2u && wB == 2u && wC == 1u) {
-                row_sums_fixed<P, 2, 2, 1>(terms, words + tid, h.nrows, a, b, c);
+                row_sums_fixed<P, 2, 2, 1>(smem4, words + tid, h.nrows, a, b, c);
             } else {
-                row_sums_any<P>(terms, words + tid, h.nrows, wA, wB, wC, a, b, c);
+                row_sums_any<P>(smem4, words + tid, h.nrows, wA, wB, wC, a, b, c);
             }
             if (EMIT) {
                 a = canonical<P>(a);
@@ -395,15 +451,32 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, bad);
         if (bal != 0u && lane == 0u) report_bad_rows(result, bal, row_base + h.row0 + (tid & ~31u));
+        mark(4);
+        if (tile + 1u == t_end) break;
 
+        // ---- refill: the far witness columns of the next tile leave the blob before it is overwritten
+        uint32_t idx[kFarPerThread];
+        {
+            const uint32_t* nfar = reinterpret_cast<const uint32_t*>(blob + h.off_next_far);
+#pragma unroll
+            for (uint32_t k = 0; k < kFarPerThread; ++k) {
+                const uint32_t f = tid + k * C::kThreads;
+                idx[k] = f < h.next_n_far ? nfar[f] : 0u;
+            }
+        }
         // blob and window were read (and the term array written) through the generic proxy; order that before
-        // the next TMA (async proxy) refill of the same bytes
-        mark(5);
+        // the TMA (async proxy) refill of the same bytes
         fence_proxy_async_smem();
         __syncthreads();
+        mark(5);
+        if (tid == 0) {
+            issue_tile_load(ts, w, next_off16, h.next_bytes, h.next_win_lo, h.next_win_n, smem, smem + C::kOffTerms,
+                            &full_bar);
+            prefetch_behind(ts, w, next_off16, h.next_bytes, h.next_win_lo, h.next_win_n);
+        }
+        next_off16 += h.next_bytes / 16u;
+        gather_far(h.next_n_far, idx);
         mark(6);
-        if (tid == 0 && tile + gridDim.x < n_tiles)
-            issue_tile_load(ts, w, tile + gridDim.x, smem, smem + C::kOffTerms, &full_bar);
     }
     if (TIMING && rec) {
         for (int k = 0; k < 7; ++k) atomicAdd(&g_tiled_phase_cycles[rw][k], ph[rw][k]);
@@ -494,12 +567,19 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
                                      unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count,
                                      cudaStream_t s) {
     using C = tiled::Cfg<V>;
+    // ACG_K2_CTAS_PER_SM=k (a measurement aid): pad the dynamic shared memory so that only k CTAs fit on an SM
+    static const int limit_ctas = getenv("ACG_K2_CTAS_PER_SM") ? atoi(getenv("ACG_K2_CTAS_PER_SM")) : 0;
+    unsigned smem_bytes = C::kBytes, ctas = C::kCtasPerSm;
+    if (limit_ctas > 0 && (unsigned)limit_ctas < ctas) {
+        ctas = (unsigned)limit_ctas;
+        smem_bytes = (227u * 1024u) / ctas - 1024u - 256u;
+    }
     {
         cudaError_t e = cudaFuncSetAttribute(k_r1cs_tiled<P, EMIT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)C::kBytes);
+                                             (int)smem_bytes);
         if (e != cudaSuccess) return e;
     }
-    unsigned grid = (unsigned)(sm_count * (int)C::kCtasPerSm);
+    unsigned grid = (unsigned)sm_count * ctas;
     if (grid > ts.n_tiles) grid = ts.n_tiles;
     if (V == 0 && !EMIT) {  // ACG_TILED_TIMING=1: run the instrumented instantiation and print its counters
         static const bool timing = getenv("ACG_TILED_TIMING") != nullptr;
@@ -514,7 +594,7 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
             cudaStreamSynchronize(s);
             static int printed = 0;
             if (printed++ < 3) {
-                static const char* nm[7] = {"tma_wait", "p1", "bar1", "p2", "bar2", "p3", "bar3"};
+                static const char* nm[7] = {"tma_wait", "bar1", "p2", "bar2", "p3", "bar3", "refill"};
                 for (int wsel = 0; wsel < 2; ++wsel) {
                     fprintf(stderr, "[phase cycles/tile, %s] tiles=%llu:", wsel ? "last warp" : "warp 0", z[wsel][7]);
                     unsigned long long tot = 0;
@@ -528,7 +608,7 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
             return cudaGetLastError();
         }
     }
-    k_r1cs_tiled<P, EMIT, V><<<grid, kTileGeom[V].threads, C::kBytes, s>>>(ts, w, row_base, d_result, Aw, Bw, Cw);
+    k_r1cs_tiled<P, EMIT, V><<<grid, kTileGeom[V].threads, smem_bytes, s>>>(ts, w, row_base, d_result, Aw, Bw, Cw);
     return cudaGetLastError();
 }
 

@@ -281,6 +281,36 @@ def test_full_size_properties(acg, ctx_bn):
     assert (aw == ref["Aw"]).all() and (bw == ref["Bw"]).all() and (cw == ref["Cw"]).all()
 
 
+@pytest.mark.parametrize("fid", [0, 1])
+def test_constant_wire_not_one(acg, ctxs, fid):
+    """The tiled kernel folds general coefficients on column 0 (the reference's constant wire, w[0] = 1) into
+    ready-made terms.  A caller may still pass any w[0]: the result must match the oracle for w[0] = 0, 2, r - 1
+    and for a random element (counts, first bad row and the emitted A.w / B.w / C.w vectors)."""
+    ctx = ctxs[fid]
+    n = 3000
+    g, w = acg.synth_r1cs(fid, n, 777 + fid)
+    m, dw = ctx.upload_r1cs(g), ctx.upload_witness(w)
+    rng = np.random.default_rng(5)
+    rnd = rng.integers(0, 1 << 63, size=4, dtype=np.uint64)
+    rnd[3] &= np.uint64((1 << 60) - 1)
+    r_minus_1 = acg.to_limbs([acg.field_constants(fid)["modulus"] - 1])[0]
+    for w0 in (np.array([0, 0, 0, 0], dtype=np.uint64), np.array([2, 0, 0, 0], dtype=np.uint64), r_minus_1, rnd):
+        wb = w.copy()
+        wb[0] = w0
+        ref = oracle_check(fid, g, wb, True)
+        assert ref["n_violations"] > 0
+        dw.update(wb)
+        for kernel, stages in KERNELS:
+            _select(acg, ctx, kernel, stages)
+            assert ctx.r1cs_check(m, dw) == (ref["n_violations"], ref["first_bad_row"])
+            aw, bw, cw = ctx.r1cs_eval(m, dw)
+            assert (aw == ref["Aw"]).all() and (bw == ref["Bw"]).all() and (cw == ref["Cw"]).all()
+    dw.update(w)
+    _select(acg, ctx, "tiled", 0)
+    assert ctx.r1cs_check(m, dw) == (0, -1)
+    _reset(acg, ctx)
+
+
 # ------------------------------------------------------------------------------------------------ K3 / K4
 def test_ntt_golden(acg, ctxs):
     for case in golden("ntt.json"):
