@@ -197,8 +197,8 @@ struct HostTile {
 // general-coefficient entries, and the sum of its three ELL widths (max row length per matrix) stays within
 // geom.max_slots.  Rows longer than kMaxEllWidth in any matrix (Split gates, src/QAP.hs:443-473) are left to
 // the row-wise kernel.  gcum[k][r] = number of general entries of matrix k in local rows < r.
-void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t* gcum[3], const uint32_t* ccum[3],
-                 uint32_t n_local, std::vector<HostTile>& tiles,
+void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t* gcum[3],
+                 const uint32_t* ccum[3], uint32_t n_local, std::vector<HostTile>& tiles,
                  std::vector<std::pair<uint32_t, uint32_t>>& long_ranges) {
     auto add_long = [&](uint32_t a, uint32_t b) {
         if (!long_ranges.empty() && long_ranges.back().second == a)
@@ -217,9 +217,10 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
             c_base += ccum[k][r];
         }
         uint32_t end = r;
+        const uint32_t row_cap = geom.threads;
         uint32_t width[3] = {0, 0, 0};
         bool hit_long = false;
-        while (end < n_local && end - r < geom.threads) {
+        while (end < n_local && end - r < row_cap) {
             const uint32_t g_end = std::min(end + 4u, n_local);
             uint32_t nw[3] = {width[0], width[1], width[2]};
             uint64_t gen = 0, cst = 0;
@@ -243,7 +244,7 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
             if (nw[0] + nw[1] + nw[2] > geom.max_slots || prods > (uint64_t)geom.max_gen ||
                 cst - c_base > (uint64_t)geom.max_const)
                 break;
-            if (prods > (uint64_t)geom.threads && end - r >= geom.threads / 2u) break;
+            if (prods > (uint64_t)geom.threads && end - r >= row_cap / 2u) break;
             for (int k = 0; k < 3; ++k) width[k] = nw[k];
             end = g_end;
         }
@@ -533,8 +534,9 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
                 uint32_t tag = kTagGeneral;
                 if (v[0] == 1 && (v[1] | v[2] | v[3]) == 0)
                     tag = kTagPlusOne;
-                else if (v[0] == minus_one[0] && v[1] == minus_one[1] && v[2] == minus_one[2] && v[3] == minus_one[3])
-                    tag = kTagMinusOne;
+                else if (k != 2 && v[0] == minus_one[0] && v[1] == minus_one[1] && v[2] == minus_one[2] &&
+                         v[3] == minus_one[3])
+                    tag = kTagMinusOne;  // (a -1 in C stays general: C.w is compared, so its terms are never negated)
                 gen += (tag == kTagGeneral);
                 cst += (tag == kTagGeneral && c == 0u);
                 tagged_col[k][e - e0] = (c & kColMask) | (tag << 30);
@@ -609,7 +611,7 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     auto put32 = [&](uint32_t v) {
         for (int i = 0; i < 4; ++i) stream.push_back((uint8_t)(v >> (8 * i)));
     };
-    const uint32_t kProd0 = geom.window + geom.max_far, kZero = tile_term_slots(geom) - 1u;
+    const uint32_t kProd0 = tile_prod_slot0(geom), kZero = tile_term_slots(geom) - 1u;
     std::vector<uint32_t> ref_cols, far_cols;
     // a tile whose distinct far references exceed the far slots is split in two (rows stay multiples of 4)
     std::vector<HostTile> work(tiles.rbegin(), tiles.rend());
@@ -686,7 +688,7 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
         const uint32_t* far_e = far_b + ft.n_far;
         auto slot_of = [&](uint32_t c) -> uint32_t {  // witness column -> term slot
             if (c >= win_lo && c - win_lo < win_n) return c - win_lo;
-            return geom.window + (uint32_t)(std::lower_bound(far_b, far_e, c) - far_b);
+            return tile_far_slot0(geom, (uint32_t)ti) + (uint32_t)(std::lower_bound(far_b, far_e, c) - far_b);
         };
         align16();
         const size_t base = stream.size();

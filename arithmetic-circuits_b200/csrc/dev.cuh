@@ -69,6 +69,45 @@ __device__ __forceinline__ void tma_load_1d_stream(void* smem_dst, const void* g
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// the same for read-once data: the prefetched lines are marked evict-first
+#ifndef ACG_PREFETCH_EVICT_FIRST
+#define ACG_PREFETCH_EVICT_FIRST 0
+#endif
+__device__ __forceinline__ void prefetch_l2_bulk_stream(const void* p, uint32_t bytes) {
+#if ACG_PREFETCH_EVICT_FIRST
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol)
+                 : "memory");
+#else
+    prefetch_l2_bulk(p, bytes);
+#endif
+}
+// bulk copy of witness data (re-read by many tiles): L2 evict-last
+#ifndef ACG_WITNESS_EVICT_LAST
+#define ACG_WITNESS_EVICT_LAST 0
+#endif
+__device__ __forceinline__ void tma_load_1d_keep(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+#if ACG_WITNESS_EVICT_LAST
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+#else
+    tma_load_1d(smem_dst, gmem_src, bytes, bar);
+#endif
+}
+// 16-byte asynchronous global -> shared copy that bypasses L1 (SASS LDGSTS.BYPASS), and the wait for all of this
+// thread's copies
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
 // one witness element (32 bytes) through the read-only path
 __device__ __forceinline__ fr_t ld_witness(const fr_t* p) {
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);

@@ -35,8 +35,8 @@ struct DevR1cs {
 //
 // Inside the kernel every term of every row lives in ONE shared-memory array of 32-byte slots:
 //     [0, window)                         the witness window (TMA)
-//     [window, window + max_far)          "far" witness elements: the distinct columns outside the window,
-//                                         gathered once per tile
+//     [window, window + 2 * max_far)      "far" witness elements: the distinct columns outside the window,
+//                                         gathered once per tile; two buffers, used by even / odd tiles
 //     [.., + max_gen)                     products coefficient * operand of the general-coefficient entries
 //     last slot                           zero (padding)
 // Blob = header | entry words in ELL (slot-major) order: for matrix A, then B, then C, for slot
@@ -99,8 +99,16 @@ constexpr uint32_t tile_terms_offset(const TileGeometry& g) {
 }
 // far gathers per thread (the far witness columns of a tile are gathered tid, tid + threads, ...)
 constexpr uint32_t kFarPerThread = 3;
+// the far slots are double-buffered by tile parity: tile i uses far buffer (i & 1), so the far witness
+// elements of tile i + 1 are gathered (cp.async) while tile i computes
 constexpr uint32_t tile_term_slots(const TileGeometry& g) {
-    return g.window + g.max_far + g.max_gen + 1u;
+    return g.window + 2u * g.max_far + g.max_gen + 1u;
+}
+constexpr uint32_t tile_far_slot0(const TileGeometry& g, uint32_t tile) {
+    return g.window + (tile & 1u) * g.max_far;
+}
+constexpr uint32_t tile_prod_slot0(const TileGeometry& g) {
+    return g.window + 2u * g.max_far;
 }
 
 struct alignas(32) TileMeta {
@@ -112,6 +120,17 @@ struct alignas(32) TileMeta {
     uint32_t n_far;
     uint32_t pad[2];
 };
+// resident CTAs of the tiled kernel per SM: bounded by shared memory (227 KB, 1 KB per CTA reserved), by the
+// register budget of 96 per thread and by the hardware limit of 32
+constexpr uint32_t tile_smem_bytes(const TileGeometry& g) {
+    return tile_terms_offset(g) + tile_term_slots(g) * 32u;
+}
+constexpr uint32_t tile_ctas_per_sm(const TileGeometry& g) {
+    const uint32_t by_smem = (227u * 1024u) / (tile_smem_bytes(g) + 1024u + 64u);
+    const uint32_t by_regs = 65536u / (g.threads * 96u);
+    const uint32_t m = by_smem < by_regs ? by_smem : by_regs;
+    return m > 32u ? 32u : m;
+}
 struct DevTileStream {
     const uint8_t* blobs;       // concatenated tile blobs
     const TileMeta* meta;       // n_tiles records

@@ -15,6 +15,7 @@
 #include "dev.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
 #include <vector>
 
 namespace acg {
@@ -44,6 +45,13 @@ struct NttPlan {
     fr_t* d_lo = nullptr;     // w_N^i, i < 2^lo_bits
     uint32_t lo_bits = 0;
     fr_t scale;               // 1/n (Montgomery) for inverse plans
+    // Four-step twiddle corrections of the column passes as full tables, indexed like the data (one factor per
+    // element): one product per element instead of two (table lookup product + application).  The kernel is
+    // bound by the 32x32->64 multiplier, not by HBM, so trading 32 B of extra read per
+    // element for a 256-bit product is a net win; the tables cost 32 * N bytes per column pass.
+    // Inverse plans fold 1/n into the table of the last column pass.
+    std::vector<fr_t*> d_corr;
+    bool scale_folded = false;
 };
 
 __device__ __forceinline__ uint32_t brev_bits(uint32_t x, uint32_t bits) {
@@ -84,10 +92,11 @@ struct SmemPlanes {
 
 template <class P>
 __global__ void __launch_bounds__(kNttThreads)
-    k_ntt_pass(fr_t* __restrict__ data, const fr_t* __restrict__ tw_small, uint32_t small_log, uint32_t k,
+    k_ntt_pass(const fr_t* src, fr_t* dst, uint32_t permute_log, const fr_t* __restrict__ tw_small,
+               uint32_t small_log, uint32_t k,
                uint32_t log_s, uint32_t log_c, uint32_t log_g, const fr_t* __restrict__ tw_hi,
                const fr_t* __restrict__ tw_lo, uint32_t lo_bits, uint32_t corr_shift, int apply_corr, fr_t scale,
-               int apply_scale) {
+               int apply_scale, const fr_t* __restrict__ corr, uint64_t corr_mask) {
     extern __shared__ __align__(16) uint8_t ntt_smem[];
     const uint32_t tile_log = k + log_c + log_g;
     const uint32_t tile_n = 1u << tile_log;
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(kNttThreads)
         const uint32_t j = (L >> log_c) & kmask;
         const uint32_t g = L >> (log_c + k);
         const uint64_t addr = ((((outer0 + g) << k) + j) << log_s) + ((uint64_t)cb << log_c) + c;
-        const fr_t v = data[addr];
+        const fr_t v = src[addr];
         sm.store(L, v);
     }
     __syncthreads();
@@ -146,7 +155,9 @@ __global__ void __launch_bounds__(kNttThreads)
         const uint32_t g = L >> (log_c + k);
         const uint64_t addr = ((((outer0 + g) << k) + j) << log_s) + ((uint64_t)cb << log_c) + c;
         fr_t v = sm.load(L);
-        if (apply_corr) {
+        if (corr) {
+            v = fr_mul<P>(v, corr[addr & corr_mask]);
+        } else if (apply_corr) {
             const uint64_t n2 = ((uint64_t)cb << log_c) + c;
             const uint64_t e = (n2 * (uint64_t)brev_bits(j, k)) << corr_shift;
             if (e != 0ull) {
@@ -156,7 +167,27 @@ __global__ void __launch_bounds__(kNttThreads)
             }
         }
         if (apply_scale) v = fr_mul<P>(v, scale);
-        data[addr] = v;
+        if (permute_log) {  // last pass of a natural-order transform: undo the bit reversal on the way out
+            const uint64_t m = (1ull << permute_log) - 1ull;
+            dst[(addr & ~m) | brev_bits((uint32_t)(addr & m), permute_log)] = v;
+        } else {
+            dst[addr] = v;
+        }
+    }
+}
+
+// corr[addr] = w_N^((n2 * bitrev_k(j)) << corr_shift) (* scale), addr = (((outer << k) + j) << log_s) + n2
+template <class P>
+__global__ void k_fill_corr(fr_t* __restrict__ corr, uint64_t n, uint32_t k, uint32_t log_s, uint32_t corr_shift,
+                            const fr_t* __restrict__ tw_hi, const fr_t* __restrict__ tw_lo, uint32_t lo_bits, fr_t scale,
+                            int use_scale) {
+    for (uint64_t a = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; a < n; a += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t n2 = a & ((1ull << log_s) - 1ull);
+        const uint32_t j = (uint32_t)(a >> log_s) & ((1u << k) - 1u);
+        const uint64_t e = (n2 * (uint64_t)brev_bits(j, k)) << corr_shift;
+        fr_t f = fr_mul<P>(tw_hi[e >> lo_bits], tw_lo[e & ((1ull << lo_bits) - 1ull)]);
+        if (use_scale) f = fr_mul<P>(f, scale);
+        corr[a] = f;
     }
 }
 
@@ -263,6 +294,24 @@ static cudaError_t plan_fill(NttPlan* p) {
     // 1/n
     fr_t n_m = fr_from_u64<P>(1ull << log_n);
     p->scale = fr_inv<P>(n_m);
+    // correction tables of the column passes (ACG_NTT_NO_CORR_TABLES=1 keeps the two-product on-the-fly form)
+    p->d_corr.assign(p->passes.size(), nullptr);
+    if (!getenv("ACG_NTT_NO_CORR_TABLES")) {
+        size_t last_col = p->passes.size();
+        for (size_t i = 0; i < p->passes.size(); ++i)
+            if (p->passes[i].correct) last_col = i;
+        for (size_t i = 0; i < p->passes.size(); ++i) {
+            const NttPass& ps = p->passes[i];
+            if (!ps.correct) continue;
+            const uint64_t n = 1ull << log_n;
+            if ((e = cudaMalloc(&p->d_corr[i], n * sizeof(fr_t))) != cudaSuccess) return e;
+            const bool fold = p->inverse && i == last_col;
+            k_fill_corr<P><<<grid_for(n, 256, 148 * 16), 256>>>(p->d_corr[i], n, ps.k, ps.log_s, log_n - ps.log_m, p->d_hi,
+                                                               p->d_lo, p->lo_bits, p->scale, fold ? 1 : 0);
+            if (fold) p->scale_folded = true;
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
     return cudaDeviceSynchronize();
 }
 
@@ -312,12 +361,17 @@ void ntt_plan_destroy(NttPlan* p) {
     cudaFree(p->d_small);
     cudaFree(p->d_hi);
     cudaFree(p->d_lo);
+    for (fr_t* c : p->d_corr) cudaFree(c);
     delete p;
 }
 
 template <class P>
-static cudaError_t run_dif(const NttPlan* p, fr_t* data, uint32_t batch, bool scale_last, cudaStream_t s,
-                           uint32_t* launches) {
+// permute: write natural order.  Passes work tile by tile (load a tile, transform it in shared memory, store it
+// to the same addresses), so any pass can also run out of place; with more than one pass the one before the last
+// stores to `scratch` and the last one reads it and scatters into `data`.  A single pass holds whole transforms in
+// its tile and permutes in place.
+static cudaError_t run_dif(const NttPlan* p, fr_t* data, fr_t* scratch, bool permute, uint32_t batch, bool scale_last,
+                           cudaStream_t s, uint32_t* launches) {
     {
         cudaError_t e = cudaFuncSetAttribute(k_ntt_pass<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(kNttTile * sizeof(fr_t)));
@@ -337,29 +391,27 @@ static cudaError_t run_dif(const NttPlan* p, fr_t* data, uint32_t batch, bool sc
         const uint32_t tile_log = ps.k + ps.log_c + ps.log_g;
         const uint64_t n_tiles = total >> tile_log;
         const size_t smem = (size_t)sizeof(fr_t) << tile_log;
+        const bool via_scratch = permute && p->passes.size() > 1;
+        const fr_t* src = (via_scratch && last) ? scratch : data;
+        fr_t* dst = (via_scratch && i + 2 == p->passes.size()) ? scratch : data;
         k_ntt_pass<P><<<(unsigned)n_tiles, kNttThreads, smem, s>>>(
-            data, p->d_small, p->small_log, ps.k, ps.log_s, ps.log_c, ps.log_g, p->d_hi, p->d_lo, p->lo_bits,
-            p->log_n - ps.log_m, ps.correct ? 1 : 0, p->scale, (last && scale_last) ? 1 : 0);
+            src, dst, (permute && last) ? p->log_n : 0u, p->d_small, p->small_log, ps.k, ps.log_s, ps.log_c, ps.log_g, p->d_hi, p->d_lo, p->lo_bits,
+            p->log_n - ps.log_m, ps.correct ? 1 : 0, p->scale, (last && scale_last && !p->scale_folded) ? 1 : 0,
+            p->d_corr.empty() ? nullptr : p->d_corr[i], (1ull << p->log_n) - 1ull);
         if (launches) ++*launches;
     }
     return cudaGetLastError();
 }
 
 cudaError_t ntt_run_dif(const NttPlan* p, fr_t* data, uint32_t batch, cudaStream_t s, uint32_t* launches) {
-    ACG_DISPATCH_FIELD(p->field, return (run_dif<P>(p, data, batch, false, s, launches)));
+    if (p->scale_folded) return cudaErrorInvalidValue;  // an inverse plan always scales: use ntt_run
+    ACG_DISPATCH_FIELD(p->field, return (run_dif<P>(p, data, nullptr, false, batch, false, s, launches)));
     return cudaErrorInvalidValue;
 }
 
 cudaError_t ntt_run(const NttPlan* p, fr_t* data, fr_t* scratch, uint32_t batch, cudaStream_t s, uint32_t* launches) {
-    cudaError_t e;
-    ACG_DISPATCH_FIELD(p->field, e = (run_dif<P>(p, data, batch, p->inverse, s, launches)));
-    if (e != cudaSuccess) return e;
-    const uint64_t total = (uint64_t)batch << p->log_n;
-    if (p->log_n == 0) return cudaSuccess;
-    k_bitrev_permute<<<grid_for(total, 256, 148 * 32), 256, 0, s>>>(data, scratch, p->log_n, total);
-    if (launches) ++*launches;
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    return cudaMemcpyAsync(data, scratch, total * sizeof(fr_t), cudaMemcpyDeviceToDevice, s);
+    ACG_DISPATCH_FIELD(p->field, return (run_dif<P>(p, data, scratch, p->log_n > 0, batch, p->inverse, s, launches)));
+    return cudaErrorInvalidValue;
 }
 
 const fr_t* ntt_plan_pow_hi(const NttPlan* p) { return p->d_hi; }

@@ -150,9 +150,6 @@ __global__ void k_validate_csr(const uint32_t* __restrict__ rowptr, const uint32
 #ifndef ACG_K2_ILP2
 #define ACG_K2_ILP2 0
 #endif
-#ifndef ACG_K2_REGS
-#define ACG_K2_REGS 96u
-#endif
 namespace tiled {
 constexpr uint32_t align_up(uint32_t x, uint32_t a) {
     return (x + a - 1) / a * a;
@@ -162,17 +159,13 @@ template <int V>
 struct Cfg {
     static constexpr uint32_t kThreads = kTileGeom[V].threads;
     static constexpr uint32_t kWin = kTileGeom[V].window;
-    static constexpr uint32_t kFar0 = kWin;                              // first far slot
-    static constexpr uint32_t kProd0 = kWin + kTileGeom[V].max_far;      // first product slot
+    static constexpr uint32_t kFar0 = kWin;                              // first far slot of even tiles
+    static constexpr uint32_t kFarN = kTileGeom[V].max_far;              // odd tiles: kFar0 + kFarN
+    static constexpr uint32_t kProd0 = tile_prod_slot0(kTileGeom[V]);    // first product slot
     static constexpr uint32_t kZero = tile_term_slots(kTileGeom[V]) - 1u;  // the zero slot
     static constexpr uint32_t kOffTerms = tile_terms_offset(kTileGeom[V]);
-    static constexpr uint32_t kBytes = kOffTerms + tile_term_slots(kTileGeom[V]) * 32;
-    // resident CTAs per SM: bounded by shared memory (227 KB, 1 KB per CTA reserved), by 96 registers per
-    // thread and by the hardware limit of 32
-    static constexpr uint32_t kCtasBySmem = (227u * 1024u) / (kBytes + 1024u + 64u);
-    static constexpr uint32_t kCtasByRegs = 65536u / (kThreads * ACG_K2_REGS);
-    static constexpr uint32_t kCtasMin = kCtasBySmem < kCtasByRegs ? kCtasBySmem : kCtasByRegs;
-    static constexpr uint32_t kCtasPerSm = kCtasMin > 32u ? 32u : kCtasMin;
+    static constexpr uint32_t kBytes = tile_smem_bytes(kTileGeom[V]);
+    static constexpr uint32_t kCtasPerSm = tile_ctas_per_sm(kTileGeom[V]);
 };
 
 __device__ __forceinline__ fr_t load_term(const uint4* terms, uint32_t slot) {
@@ -209,7 +202,7 @@ __device__ __forceinline__ void issue_tile_load(const DevTileStream& ts, const f
                                                 uint8_t* blob_dst, uint8_t* win_dst, uint64_t* bar) {
     mbar_arrive_expect_tx(bar, blob_bytes + win_n * 32u);
     tma_load_1d_stream(blob_dst, ts.blobs + (size_t)blob_off16 * 16u, blob_bytes, bar);
-    if (win_n) tma_load_1d(win_dst, w + win_lo, win_n * 32u, bar);
+    if (win_n) tma_load_1d_keep(win_dst, w + win_lo, win_n * 32u, bar);
 }
 // one thread: pull what most likely comes after the tile being loaded towards L2 -- the stream is linear per
 // CTA and windows of successive tiles are (for circuits built gate by gate) successive slices of w, so the
@@ -217,7 +210,7 @@ __device__ __forceinline__ void issue_tile_load(const DevTileStream& ts, const f
 __device__ __forceinline__ void prefetch_behind(const DevTileStream& ts, const fr_t* __restrict__ w, uint32_t blob_off16,
                                                 uint32_t blob_bytes, uint32_t win_lo, uint32_t win_n) {
     const uint32_t o = blob_off16 + blob_bytes / 16u;
-    if (o < ts.blobs_len16) prefetch_l2_bulk(ts.blobs + (size_t)o * 16u, min(blob_bytes, (ts.blobs_len16 - o) * 16u));
+    if (o < ts.blobs_len16) prefetch_l2_bulk_stream(ts.blobs + (size_t)o * 16u, min(blob_bytes, (ts.blobs_len16 - o) * 16u));
     const uint32_t c = win_lo + win_n;
     if (c < ts.n_cols) prefetch_l2_bulk(w + c, min(win_n, ts.n_cols - c) * 32u);
 }
@@ -265,7 +258,7 @@ __device__ __forceinline__ void row_sums_fixed(const uint4* terms, const uint32_
         fr_t ta, tb, tc;
         if (j < WA) ta = signed_term<P>(terms, pa[j * nrows]);
         if (j < WB) tb = signed_term<P>(terms, pb[j * nrows]);
-        if (j < WC) tc = signed_term<P>(terms, pc[j * nrows]);
+        if (j < WC) tc = load_term(terms, pc[j * nrows]);  // C entries carry no sign (upload tags -1 in C general)
         if (j == 0) {
             a = ta;
             b = tb;
@@ -274,10 +267,9 @@ __device__ __forceinline__ void row_sums_fixed(const uint4* terms, const uint32_
             // the last L-1 steps of a may skip the reduction: value <= p * (1 + remaining steps) <= L * p
             if (j < WA) a = (WA - j <= L - 1) ? acc_step<P, true>(a, ta) : acc_step<P, false>(a, ta);
             if (j < WB) b = acc_step<P, false>(b, tb);
-            if (j < WC) c = acc_step<P, false>(c, tc);
+            if (j < WC) c = fr_add<P>(c, tc);  // both < p: canonical
         }
     }
-    c = fr_add<P>(c, fr_zero<P>());  // p (a negated zero) -> 0: c is compared, not multiplied
 }
 // Run-time widths.  a, b, c in [0, p).
 template <class P>
@@ -294,7 +286,7 @@ __device__ __forceinline__ void row_sums_any(const uint4* terms, const uint32_t*
         fr_t ta, tb, tc;
         if (ua) ta = signed_term<P>(terms, pa[j * nrows]);
         if (ub) tb = signed_term<P>(terms, pb[j * nrows]);
-        if (uc) tc = signed_term<P>(terms, pc[j * nrows]);
+        if (uc) tc = load_term(terms, pc[j * nrows]);
         if (ua) a = fr_add<P>(a, ta);
         if (ub) b = fr_add<P>(b, tb);
         if (uc) c = fr_add<P>(c, tc);
@@ -312,11 +304,12 @@ __device__ __forceinline__ fr_t canonical(fr_t x) {
 // phase cycle counters of the TIMING instantiation (a measurement aid: ACG_TILED_TIMING=1)
 __device__ unsigned long long g_tiled_phase_cycles[2][8];
 
-// One CTA walks a contiguous run of tiles.  While tile i computes, the blob and window of tile i + 1 are already
-// in (or on their way to) L2 (cp.async.bulk.prefetch.L2 issued a tile earlier); the moment P3 of tile i is done
-// the CTA issues the bulk copies of tile i + 1 and -- with the far witness columns that blob i carried --
-// gathers its far witness elements, all loads of a thread in flight together and overlapping the bulk copies.
-// Memory latency per tile is one L2 round trip instead of a DRAM bulk copy followed by a dependent gather.
+// One CTA walks a contiguous run of tiles.  While tile i computes:
+//   * its far witness elements are already in the far buffer (i & 1): they were gathered with 16-byte cp.async
+//     copies issued during tile i - 1, from the far witness columns that blob i - 1 carried;
+//   * the gathers of tile i + 1 are in flight into the other far buffer;
+//   * the blob and window of tile i + 1 are in (or on their way to) L2 (cp.async.bulk.prefetch.L2 issued a tile
+//     earlier), so that the bulk copies issued the moment P3 of tile i is done complete after one L2 round trip.
 template <class P, bool EMIT, int V, bool TIMING = false>
 __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerSm)
     k_r1cs_tiled(DevTileStream ts, const fr_t* __restrict__ w, uint64_t row_base,
@@ -345,27 +338,32 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     uint8_t* blob = smem;
     uint4* terms = reinterpret_cast<uint4*>(smem + C::kOffTerms);
     const uint4* smem4 = reinterpret_cast<const uint4*>(smem);  // entry / operand words address 32-byte units from here
-    // column 0 is the constant wire: w[0] == 1 for every witness the reference builds, and then a general
-    // coefficient on column 0 is its own product (kernels.h); anything else takes the multiply-in-place path
-    const bool w0_is_one = fr_is_one<P>(ld_witness(w));
     // this CTA's run of tiles
     const uint32_t t_begin = (uint32_t)((uint64_t)blockIdx.x * ts.n_tiles / gridDim.x);
     const uint32_t t_end = (uint32_t)((uint64_t)(blockIdx.x + 1u) * ts.n_tiles / gridDim.x);
     if (t_begin >= t_end) return;
-    // gather this thread's far witness elements (far slot f = tid + k * threads) : all loads, then the stores
-    auto gather_far = [&](uint32_t n_far, const uint32_t (&idx)[kFarPerThread]) {
-        fr_t x[kFarPerThread];
+    const TileMeta tm = ts.meta[t_begin];  // the first tile of the run is described from outside
+    // column 0 is the constant wire: w[0] == 1 for every witness the reference builds, and then a general
+    // coefficient on column 0 is its own product (kernels.h); anything else takes the multiply-in-place path
+    // (loaded here, behind the tile record, and first looked at in P2: off the start-up critical path)
+    const fr_t w0_first = ld_witness(w);
+    // start the gather of this thread's far witness elements of tile `tile` (far slot f = tid + k * threads)
+    // from the column list `cols`
+    auto gather_far_async = [&](uint32_t tile, uint32_t n_far, const uint32_t* cols) {
+        uint4* dst = terms + 2u * (C::kFar0 + (tile & 1u) * C::kFarN);
 #pragma unroll
-        for (uint32_t k = 0; k < kFarPerThread; ++k)
-            if (tid + k * C::kThreads < n_far) x[k] = ld_witness(w + idx[k]);
-#pragma unroll
-        for (uint32_t k = 0; k < kFarPerThread; ++k)
-            if (tid + k * C::kThreads < n_far) store_term(terms, C::kFar0 + tid + k * C::kThreads, x[k]);
+        for (uint32_t k = 0; k < kFarPerThread; ++k) {
+            const uint32_t f = tid + k * C::kThreads;
+            if (f < n_far) {
+                const uint4* src = reinterpret_cast<const uint4*>(w + cols[f]);
+                cp_async16(dst + 2u * f, src);
+                cp_async16(dst + 2u * f + 1u, src + 1);
+            }
+        }
     };
 
     uint32_t next_off16;  // where the next blob starts (thread 0)
     {
-        const TileMeta tm = ts.meta[t_begin];  // the first tile of the run is described from outside
         if (tid == 0) {
             mbar_init(&full_bar, 1);
             mbar_fence_init();
@@ -375,27 +373,26 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
             prefetch_behind(ts, w, tm.blob_off16, tm.blob_bytes, tm.win_lo, tm.win_n);
         }
         next_off16 = tm.blob_off16 + tm.blob_bytes / 16u;
-        uint32_t idx[kFarPerThread];
-#pragma unroll
-        for (uint32_t k = 0; k < kFarPerThread; ++k) {
-            const uint32_t f = tid + k * C::kThreads;
-            idx[k] = f < tm.n_far ? ts.far_cols[tm.far_off + f] : 0u;
-        }
-        gather_far(tm.n_far, idx);
+        gather_far_async(t_begin, tm.n_far, ts.far_cols + tm.far_off);
     }
+    const bool w0_is_one = fr_is_one<P>(w0_first);
     __syncthreads();  // mbarrier initialised before anyone waits on it
 
     uint32_t it = 0;
     if (TIMING) t_last = clock64();
     for (uint32_t tile = t_begin; tile < t_end; ++tile, ++it) {
         mbar_wait(&full_bar, it & 1u);
+        cp_async_wait_all();  // this thread's far gathers of the tile
         mark(0);
-        __syncthreads();  // far slots written by every thread
+        __syncthreads();      // .. and everybody else's
         mark(1);
         const TileHeader h = *reinterpret_cast<const TileHeader*>(blob);
         const uint32_t* words = reinterpret_cast<const uint32_t*>(blob + h.off_words);
         const uint16_t* gop = reinterpret_cast<const uint16_t*>(blob + h.off_gop);
         uint8_t* gval = blob + h.off_gval;
+        // the far witness elements of the NEXT tile start their way into the other far buffer
+        if (tile + 1u < t_end)
+            gather_far_async(tile + 1u, h.next_n_far, reinterpret_cast<const uint32_t*>(blob + h.off_next_far));
 
         // ---- P2: dense 256-bit Montgomery products, one general entry per lane (no divergence between
         //          coefficient kinds): product slot <- coefficient * operand slot
@@ -453,29 +450,17 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         if (bal != 0u && lane == 0u) report_bad_rows(result, bal, row_base + h.row0 + (tid & ~31u));
         mark(4);
         if (tile + 1u == t_end) break;
-
-        // ---- refill: the far witness columns of the next tile leave the blob before it is overwritten
-        uint32_t idx[kFarPerThread];
-        {
-            const uint32_t* nfar = reinterpret_cast<const uint32_t*>(blob + h.off_next_far);
-#pragma unroll
-            for (uint32_t k = 0; k < kFarPerThread; ++k) {
-                const uint32_t f = tid + k * C::kThreads;
-                idx[k] = f < h.next_n_far ? nfar[f] : 0u;
-            }
-        }
         // blob and window were read (and the term array written) through the generic proxy; order that before
         // the TMA (async proxy) refill of the same bytes
         fence_proxy_async_smem();
         __syncthreads();
         mark(5);
-        if (tid == 0) {
+        if (tid == 0)
             issue_tile_load(ts, w, next_off16, h.next_bytes, h.next_win_lo, h.next_win_n, smem, smem + C::kOffTerms,
                             &full_bar);
+        else if (tid == C::kThreads - 1u)  // another warp: the prefetches do not delay the loads
             prefetch_behind(ts, w, next_off16, h.next_bytes, h.next_win_lo, h.next_win_n);
-        }
         next_off16 += h.next_bytes / 16u;
-        gather_far(h.next_n_far, idx);
         mark(6);
     }
     if (TIMING && rec) {

@@ -63,7 +63,7 @@ def main():
                           "ms_best": best, "ms_all": ms, "points_per_s": n / (best * 1e-3),
                           "modmul_per_s": butterflies / (best * 1e-3),
                           "hbm_floor_ms_one_pass": 64 * n / 6548.2e9 * 1e3,
-                          "note": "natural->natural: DIF passes + bit-reversal permutation + copy"}), flush=True)
+                          "note": "natural->natural: DIF passes, bit reversal fused into the last pass"}), flush=True)
 
     # QAP witness on the synthetic family
     g, w = acg.synth_r1cs(fid, n, 20260003)
