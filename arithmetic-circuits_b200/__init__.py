@@ -3,4 +3,4 @@
 The directory name follows the project name and is not a valid Python identifier; import it as
 `arithmetic_circuits_b200` (the alias package at the repository root extends its __path__ here)."""
 from .qap import *  # noqa: F401,F403
-from . import qap, _lib  # noqa: F401
+from . import qap, _lib, json_io  # noqa: F401
