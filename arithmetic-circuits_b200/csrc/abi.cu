@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/acg.h"
+#include "host/circuit.hpp"
 #include "kernels.h"
 
 using namespace acg;
@@ -871,6 +872,91 @@ int acg_witness_upload(acg_ctx* ctx, const uint64_t* w, uint32_t n_cols, acg_vec
         acg_vec_free(v);
         return rc;
     }
+    *out = v;
+    return ACG_OK;
+}
+
+int acg_vec_download(acg_ctx* ctx, const acg_vec* v, uint64_t* out, uint32_t n) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!v || !out || v->ctx != ctx || n != v->n) return fail(ctx, ACG_ERR_BAD_ARG, "acg_vec_download: bad argument");
+    DevBuf tmp;
+    CU(ctx, tmp.alloc((size_t)n * sizeof(fr_t)));
+    CU(ctx, cudaMemcpyAsync(tmp.p, v->d, (size_t)n * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(ctx, launch_from_mont(ctx->field, tmp.as<fr_t>(), n, ctx->stream));
+    ++ctx->launches;
+    CU(ctx, cudaMemcpyAsync(out, tmp.p, (size_t)n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ACG_OK;
+}
+
+int acg_generate_assignment_device(acg_ctx* ctx, const acg_circuit* c, const uint32_t* input_ix,
+                                   const uint64_t* input_vals, uint32_t n_inputs, uint32_t n_in, uint32_t n_mid,
+                                   uint32_t n_out, acg_vec** out, uint32_t* n_levels_out) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!c || !out || (n_inputs && (!input_ix || !input_vals)) || c->field != ctx->field)
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_generate_assignment_device: bad argument");
+    *out = nullptr;
+    for (uint32_t i = 0; i < n_inputs; ++i) {
+        if (input_ix[i] >= 0x7FFFFFFFu) return fail(ctx, ACG_ERR_BAD_ARG, "acg_generate_assignment_device: input index");
+        n_in = std::max(n_in, input_ix[i] + 1u);
+    }
+    host::GatePlan plan;
+    rc = host::build_gate_plan(c, n_in, n_mid, n_out, plan);
+    if (rc == ACG_ERR_UNSUPPORTED)
+        return fail(ctx, rc, "acg_generate_assignment_device: gate list is not in single-assignment, define-before-use "
+                             "form; use acg_generate_assignment (sequential fold)");
+    if (rc) return fail(ctx, rc, "acg_generate_assignment_device: cannot plan the circuit");
+    static_assert(sizeof(host::GateRec) == sizeof(WitnessGate), "gate record layouts differ");
+    const uint64_t n_cols64 = 1ull + plan.n_in + plan.n_mid + plan.n_out;
+    if (n_cols64 > kColMask) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_generate_assignment_device: too many wires");
+    const uint32_t n_cols = (uint32_t)n_cols64;
+    // initial witness: constant 1 (initialQapSet, src/QAP.hs:591-595), the inputs, zero elsewhere (missing = 0)
+    std::vector<uint64_t> init((size_t)4 * (1 + plan.n_in), 0);
+    init[0] = 1;
+    for (uint32_t i = 0; i < n_inputs; ++i) std::memcpy(&init[4 * (1 + (size_t)input_ix[i])], input_vals + 4ull * i, 32);
+    acg_vec* v = new (std::nothrow) acg_vec();
+    if (!v) return ACG_ERR_OOM;
+    v->ctx = ctx;
+    v->n = n_cols;
+    struct Guard {
+        acg_vec* p;
+        ~Guard() {
+            if (p) acg_vec_free(p);
+        }
+    } guard{v};
+    CU(ctx, cudaMalloc(&v->d, (size_t)n_cols * sizeof(fr_t)));
+    CU(ctx, cudaMemsetAsync(v->d, 0, (size_t)n_cols * sizeof(fr_t), ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = upload_canonical(ctx, v->d, init.data(), 1 + plan.n_in);  // rejects inputs >= r
+    if (rc) return rc;
+    DevBuf d_gates, d_lvl, d_tcol, d_tcoef, d_souts;
+    const size_t n_terms = plan.term_col.size();
+    CU(ctx, d_gates.alloc(plan.gates.size() * sizeof(WitnessGate)));
+    CU(ctx, d_lvl.alloc(plan.level_ptr.size() * sizeof(uint32_t)));
+    CU(ctx, d_tcol.alloc(n_terms * sizeof(uint32_t)));
+    CU(ctx, d_tcoef.alloc(n_terms * sizeof(fr_t)));
+    CU(ctx, d_souts.alloc(plan.split_outs.size() * sizeof(uint32_t)));
+    auto h2d = [&](DevBuf& d, const void* src, size_t bytes) {
+        return bytes ? cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+    };
+    CU(ctx, h2d(d_gates, plan.gates.data(), plan.gates.size() * sizeof(WitnessGate)));
+    CU(ctx, h2d(d_lvl, plan.level_ptr.data(), plan.level_ptr.size() * sizeof(uint32_t)));
+    CU(ctx, h2d(d_tcol, plan.term_col.data(), n_terms * sizeof(uint32_t)));
+    CU(ctx, h2d(d_tcoef, plan.term_coef.data(), n_terms * sizeof(fr_t)));  // already Montgomery (host mirror)
+    CU(ctx, h2d(d_souts, plan.split_outs.data(), plan.split_outs.size() * sizeof(uint32_t)));
+    CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    const uint32_t n_levels = plan.level_ptr.empty() ? 0u : (uint32_t)plan.level_ptr.size() - 1u;
+    CU(ctx, launch_witness_levels(ctx->field, d_gates.as<WitnessGate>(), d_lvl.as<uint32_t>(), n_levels, plan.max_width,
+                                  d_tcol.as<uint32_t>(), d_tcoef.as<fr_t>(), d_souts.as<uint32_t>(), v->d,
+                                  ctx->sm_count, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches += n_levels ? 2 : 1;
+    ctx->timing = acg_timing{elapsed(ctx->ev[0], ctx->ev[1]), elapsed(ctx->ev[1], ctx->ev[2]), 0.f, n_levels ? 2u : 1u, 0};
+    if (n_levels_out) *n_levels_out = n_levels;
+    guard.p = nullptr;
     *out = v;
     return ACG_OK;
 }

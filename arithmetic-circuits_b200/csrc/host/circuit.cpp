@@ -379,6 +379,93 @@ int dispatch(int field, F&& f) {
 
 }  // namespace
 
+namespace acg {
+namespace host {
+int build_gate_plan(const acg_circuit* c, uint32_t n_in, uint32_t n_mid, uint32_t n_out, GatePlan& out) {
+    if (!c) return ACG_ERR_BAD_ARG;
+    uint32_t dims[3];
+    circuit_dims(c, dims);
+    const Layout lay{std::max(n_in, dims[0]), std::max(n_mid, dims[1]), std::max(n_out, dims[2])};
+    out = GatePlan{};
+    out.n_in = lay.n_in;
+    out.n_mid = lay.n_mid;
+    out.n_out = lay.n_out;
+    const uint32_t n_cols = 1 + lay.n_in + lay.n_mid + lay.n_out;
+    const size_t n = c->gates.size();
+    std::vector<uint32_t> col_level(n_cols, 0), gate_level(n, 0);
+    std::vector<uint8_t> written(n_cols, 0), read(n_cols, 0);
+    std::vector<GateRec> recs(n);
+    uint32_t n_levels = 0;
+    int rc = dispatch(c->field, [&](auto p) {
+        using P = decltype(p);
+        Row row;
+        auto produce = [&](uint32_t col, uint32_t lvl) {
+            // a wire assigned twice, or read (as 0) before its gate: only the sequential fold is faithful
+            if (written[col] || read[col] || col <= lay.n_in) return false;
+            written[col] = 1;
+            col_level[col] = lvl;
+            return true;
+        };
+        for (size_t gi = 0; gi < n; ++gi) {
+            const GateH& g = c->gates[gi];
+            GateRec& r = recs[gi];
+            r = GateRec{};
+            r.kind = g.kind;
+            uint32_t lvl = 0;
+            if (g.kind == G_MUL) {
+                for (int side = 0; side < 2; ++side) {
+                    affine_to_row<P>(side ? g.r : g.l, lay, row);
+                    (side ? r.r0 : r.l0) = (uint32_t)out.term_col.size();
+                    for (auto& e : row) {
+                        if (e.first != 0 && !written[e.first] && e.first > lay.n_in) read[e.first] = 1;
+                        lvl = std::max(lvl, col_level[e.first]);
+                        out.term_col.push_back(e.first);
+                        out.term_coef.insert(out.term_coef.end(), e.second.v, e.second.v + 4);
+                    }
+                    (side ? r.r1 : r.l1) = (uint32_t)out.term_col.size();
+                }
+                r.out = lay.col(g.w2);
+                if (!produce(r.out, lvl + 1)) return (int)ACG_ERR_UNSUPPORTED;
+            } else if (g.kind == G_EQUAL) {
+                r.in = lay.col(g.w0);
+                r.magic = lay.col(g.w1);
+                r.out = lay.col(g.w2);
+                if (r.in > lay.n_in && !written[r.in]) return (int)ACG_ERR_BAD_ARG;  // lookup fails: reference panics
+                lvl = col_level[r.in];
+                if (!produce(r.magic, lvl + 1) || !produce(r.out, lvl + 1)) return (int)ACG_ERR_UNSUPPORTED;
+            } else {
+                r.in = lay.col(g.w0);
+                if (r.in > lay.n_in && !written[r.in]) return (int)ACG_ERR_BAD_ARG;
+                lvl = col_level[r.in];
+                r.l0 = (uint32_t)out.split_outs.size();
+                for (uint64_t o : g.outs) {
+                    const uint32_t oc = lay.col(o);
+                    if (!produce(oc, lvl + 1)) return (int)ACG_ERR_UNSUPPORTED;
+                    out.split_outs.push_back(oc);
+                }
+                r.l1 = (uint32_t)out.split_outs.size();
+            }
+            gate_level[gi] = lvl;  // 0-based level of the gate
+            n_levels = std::max(n_levels, lvl + 1);
+        }
+        return (int)ACG_OK;
+    });
+    if (rc != ACG_OK) return rc;
+    // counting sort by level (stable: circuit order inside a level)
+    out.level_ptr.assign((size_t)n_levels + 1, 0);
+    for (size_t gi = 0; gi < n; ++gi) ++out.level_ptr[gate_level[gi] + 1];
+    for (uint32_t l = 0; l < n_levels; ++l) {
+        out.max_width = std::max(out.max_width, out.level_ptr[l + 1]);
+        out.level_ptr[l + 1] += out.level_ptr[l];
+    }
+    out.gates.resize(n);
+    std::vector<uint32_t> cursor(out.level_ptr.begin(), out.level_ptr.end() - (n_levels ? 1 : 0));
+    for (size_t gi = 0; gi < n; ++gi) out.gates[cursor[gate_level[gi]]++] = recs[gi];
+    return ACG_OK;
+}
+}  // namespace host
+}  // namespace acg
+
 extern "C" {
 
 int acg_circuit_parse(int field_id, const uint64_t* words, uint64_t n_words, acg_circuit** out) {

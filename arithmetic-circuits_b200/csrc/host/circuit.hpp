@@ -5,6 +5,7 @@
 
 #include "fr_host.hpp"
 
+struct acg_circuit;
 namespace acg {
 namespace host {
 
@@ -27,6 +28,30 @@ struct WireMap {  // Map Int f with dense storage
     std::vector<El> val;  // Montgomery form
     std::vector<uint8_t> present;
 };
+
+// Device-ready, level-ordered description of a circuit for the witness-generation kernel (K6).
+// Level of a gate = 1 + the highest level among the gates that produce its input wires (inputs: level 0), so the
+// gates of one level only read wires of earlier levels and can be evaluated in parallel.
+struct GateRec {          // 32 bytes
+    uint32_t kind;        // 1 Mul, 2 Equal, 3 Split
+    uint32_t out;         // Mul / Equal: witness column of the output wire
+    uint32_t l0, l1;      // Mul: left terms [l0, l1);  Split: outputs [l0, l1) in split_outs
+    uint32_t r0, r1;      // Mul: right terms [r0, r1)
+    uint32_t in;          // Equal / Split: witness column of the input wire
+    uint32_t magic;       // Equal: witness column of the magic wire
+};
+struct GatePlan {
+    uint32_t n_in = 0, n_mid = 0, n_out = 0;
+    std::vector<uint32_t> level_ptr;    // gates of level l: [level_ptr[l], level_ptr[l + 1])
+    std::vector<GateRec> gates;         // level order
+    std::vector<uint32_t> term_col;     // affine-map terms (column 0 = the constant wire)
+    std::vector<uint64_t> term_coef;    // 4 limbs each, Montgomery form
+    std::vector<uint32_t> split_outs;   // witness columns of Split outputs
+    uint32_t max_width = 0;             // widest level
+};
+// affineCircuitToAffineMap per Mul side + levelisation.  0 / ACG_ERR_*; ACG_ERR_UNSUPPORTED when the gate list is
+// not in single-assignment, define-before-use form (then only the sequential host fold is faithful).
+int build_gate_plan(const struct ::acg_circuit* c, uint32_t n_in, uint32_t n_mid, uint32_t n_out, GatePlan& out);
 
 }  // namespace host
 }  // namespace acg

@@ -161,6 +161,20 @@ cudaError_t launch_to_mont_scattered(int field, uint8_t* blobs, const uint32_t* 
 cudaError_t launch_validate_csr(const uint32_t* rowptr, const uint32_t* col, uint32_t n_rows, uint64_t nnz,
                                 uint32_t n_cols, int* d_flag, cudaStream_t s);
 
+// Witness generation (K6): gates in dependency-level order (host/circuit.hpp GatePlan has the same record).
+struct WitnessGate {
+    uint32_t kind;        // 1 Mul, 2 Equal, 3 Split
+    uint32_t out;         // Mul / Equal: witness column of the output wire
+    uint32_t l0, l1;      // Mul: left terms [l0, l1);  Split: outputs [l0, l1) in split_outs
+    uint32_t r0, r1;      // Mul: right terms [r0, r1)
+    uint32_t in;          // Equal / Split: witness column of the input wire
+    uint32_t magic;       // Equal: witness column of the magic wire
+};
+// Evaluates the levels in order into w (Montgomery form, zero-initialised except constant and inputs).
+cudaError_t launch_witness_levels(int field, const WitnessGate* gates, const uint32_t* level_ptr, uint32_t n_levels,
+                                  uint32_t max_width, const uint32_t* term_col, const fr_t* term_coef,
+                                  const uint32_t* split_outs, fr_t* w, int sm_count, cudaStream_t s);
+
 // NTT (K3).  A plan owns the twiddle tables of one (field, log_n, direction).
 struct NttPlan;
 cudaError_t ntt_plan_create(int field, uint32_t log_n, bool inverse, NttPlan** out);

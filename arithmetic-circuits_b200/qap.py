@@ -433,6 +433,17 @@ class Context:
         return DeviceVec(self, h)
 
     # ---- R1CS check
+    def generate_assignment(self, circuit: ArithCircuit, inputs: Dict[int, int],
+                            layout: Tuple[int, int, int] = (0, 0, 0)) -> Tuple["DeviceVec", int]:
+        """generateAssignment (src/QAP.hs:597-603) on the device, level by level (K6).  Returns the device witness
+        (qapSetToMap order) and the number of dependency levels."""
+        ix = np.array(sorted(inputs), dtype=np.uint32)
+        vals = to_limbs([inputs[int(i)] for i in ix])
+        h, lv = C.c_void_p(), C.c_uint32()
+        _check(_lib.lib().acg_generate_assignment_device(self._h, circuit._h, _ptr(ix), _ptr(vals), len(ix), layout[0],
+                                                         layout[1], layout[2], C.byref(h), C.byref(lv)), self)
+        return DeviceVec(self, h), lv.value
+
     def r1cs_check(self, m: "DeviceR1cs", w: "DeviceVec") -> Tuple[int, int]:
         """(number of violated rows, first violated global row or -1)."""
         nv, fb = C.c_uint64(), C.c_uint64()
@@ -545,6 +556,12 @@ class DeviceVec:
     @property
     def device_ptr(self) -> int:
         return _lib.lib().acg_vec_device_ptr(self._h)
+
+    def download(self) -> np.ndarray:
+        """The vector as canonical limbs, shape (n, 4)."""
+        out = np.zeros((len(self), 4), np.uint64)
+        _check(_lib.lib().acg_vec_download(self.ctx._h, self._h, _ptr(out), len(self)), self.ctx)
+        return out
 
     def update(self, w: np.ndarray):
         w = np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4)

@@ -236,6 +236,20 @@ int acg_r1cs_host_csr(const acg_r1cs_host* m, int which, acg_csr* out);
 /* Sorted roots, one per row (4*n_rows limbs). */
 const uint64_t* acg_r1cs_host_roots(const acg_r1cs_host* m);
 
+/* ---- witness generation on the device (K6): generateAssignment (src/QAP.hs:597-603) = the evalGate fold of
+ * evalArithCircuit (src/Circuit/Arithmetic.hs:106-145, 221-235), evaluated by dependency level on the GPU.
+ * Needs a context (device); the result is a device-resident witness vector in qapSetToMap order
+ * (src/QAP.hs:605-620) with layout (max(n_in, circuit), max(n_mid, circuit), max(n_out, circuit)) -- pass zeros
+ * to take the circuit's own sizes -- ready for acg_r1cs_check / acg_qap_witness without a host round trip.
+ * The gate list must be in single-assignment, define-before-use form (what validArithCircuit accepts and every
+ * circuit of the reference's tests and examples is); otherwise ACG_ERR_UNSUPPORTED and the caller uses the
+ * sequential acg_generate_assignment.  *n_levels (optional) = number of dependency levels = barrier count. */
+int acg_generate_assignment_device(acg_ctx* ctx, const acg_circuit* c, const uint32_t* input_ix,
+                                   const uint64_t* input_vals, uint32_t n_inputs, uint32_t n_in, uint32_t n_mid,
+                                   uint32_t n_out, acg_vec** out, uint32_t* n_levels);
+/* Copy a device vector back as canonical limbs (n must equal acg_vec_len). */
+int acg_vec_download(acg_ctx* ctx, const acg_vec* v, uint64_t* out, uint32_t n);
+
 /* Synthetic family S(n, seed, field) of SURVEY.md 8(d) (bench / parity workloads): n Mul gates over
  * 1024 inputs, ~5.5 nnz per row.  Returns the lowered system and its honest witness directly
  * (same result as parse -> generate_assignment -> to_r1cs on the equivalent ArithCircuit, which

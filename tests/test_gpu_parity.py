@@ -144,6 +144,73 @@ def test_mixed_circuits_gpu(acg, ctxs, idx):
             assert acg.strip(acg.from_limbs(bufs[k])) == unhex(q[k]), k
 
 
+# ------------------------------------------------------------------------------------------------ K6
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_device_witness_generation_golden(acg, ctxs, idx):
+    """generateAssignment on the device (K6) == the golden witness of the Mul/Equal/Split circuits (which the big-int
+    oracle produced) == the sequential C++ fold; and the device witness passes the check without a host round trip."""
+    case = golden("mixed_circuits.json")[idx]
+    fid = case["field"]
+    ctx = ctxs[fid]
+    c = acg.ArithCircuit(fid, gates_acg(acg, gates_oracle(case["gates"])))
+    g = acg.arith_circuit_to_gen_qap(c, None, 1)
+    inputs = {int(k): int(v, 16) for k, v in case["inputs"].items()}
+    w_gold = acg.to_limbs(unhex(case["w"]))
+    dw, n_levels = ctx.generate_assignment(c, inputs, g.layout)
+    assert n_levels >= 1 and len(dw) == g.n_cols
+    assert (dw.download() == w_gold).all()
+    host = acg.generate_assignment(c, inputs).to_vector(g.layout)
+    assert (host == w_gold).all()
+    m = ctx.upload_r1cs(g)
+    assert _both_kernels(acg, ctx, lambda: ctx.r1cs_check(m, dw)) == (0, -1)
+
+
+@pytest.mark.parametrize("fid,n,seed,dense", [(0, 300, 11, False), (1, 2000, 12, False), (0, 1500, 13, True)])
+def test_device_witness_generation_synth(acg, ctxs, fid, n, seed, dense):
+    """S(n, seed) as an ArithCircuit: the levelised device evaluation reproduces the sequential witness exactly."""
+    ctx = ctxs[fid]
+    circuit, inputs = acg.synth_circuit(fid, n, seed, dense)
+    g, w = acg.synth_r1cs(fid, n, seed, dense)
+    dw, n_levels = ctx.generate_assignment(circuit, inputs, g.layout)
+    assert 1 <= n_levels <= n
+    assert (dw.download() == w).all()
+    m = ctx.upload_r1cs(g)
+    assert ctx.r1cs_check(m, dw) == (0, -1)
+
+
+def test_device_witness_generation_wide_and_special(acg, ctx_bn):
+    """A wide, shallow circuit (grid-barrier mode: one level of 5000 Mul gates, then Equal and Split levels), with
+    Equal on zero and non-zero inputs and a 254-bit Split; against the sequential host fold."""
+    r = O.BN254.r
+    rnd = random.Random(99)
+    n = 5000
+    gates = [acg.Mul(acg.Add(acg.ConstGate(rnd.randrange(r)), acg.Var(acg.InputWire(i % 7))),
+                     acg.ScalarMul(rnd.randrange(r), acg.Var(acg.InputWire((i * 3) % 7))), acg.IntermediateWire(i))
+             for i in range(n)]
+    # in_5 = 0 makes some products zero: Equal sees both cases
+    base = n
+    for i in range(64):
+        gates.append(acg.Equal(acg.IntermediateWire(i), acg.IntermediateWire(base + 2 * i), acg.IntermediateWire(base + 2 * i + 1)))
+    base2 = base + 128
+    gates.append(acg.Split(acg.IntermediateWire(3), [acg.IntermediateWire(base2 + i) for i in range(254)]))
+    gates.append(acg.Mul(acg.unsplit([acg.IntermediateWire(base2 + i) for i in range(254)]), acg.ConstGate(1), acg.OutputWire(0)))
+    c = acg.ArithCircuit(0, gates)
+    inputs = {i: rnd.randrange(r) for i in range(7)}
+    inputs[5] = 0
+    host = acg.generate_assignment(c, inputs)
+    dw, n_levels = ctx_bn.generate_assignment(c, inputs)
+    assert n_levels == 3
+    got = dw.download()
+    assert (got == host.to_vector()).all()
+    assert host.lookup(acg.OutputWire(0)) == host.lookup(acg.IntermediateWire(3))
+    # not single-assignment: refused loudly, the sequential fold stays the faithful path
+    bad = acg.ArithCircuit(0, [acg.Mul(acg.Var(acg.InputWire(0)), acg.Var(acg.InputWire(1)), acg.IntermediateWire(0)),
+                               acg.Mul(acg.Var(acg.InputWire(0)), acg.Var(acg.InputWire(0)), acg.IntermediateWire(0))])
+    with pytest.raises(acg.AcgError) as e:
+        ctx_bn.generate_assignment(bad, {0: 1, 1: 2})
+    assert e.value.code == -6
+
+
 @pytest.mark.parametrize("fid,n,seed,dense", [(0, 96, 20260002, False), (0, 64, 7, True), (1, 96, 20260005, False),
                                               (0, 1 << 12, 1, False), (0, 5000, 2, True), (1, (1 << 13) + 3, 3, False)])
 def test_synth_parity_small(acg, ctxs, fid, n, seed, dense):
