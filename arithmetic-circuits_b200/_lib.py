@@ -49,6 +49,7 @@ PROTOTYPES = {
     "acg_vec_free": (None, [vp]),
     "acg_vec_len": (C.c_uint32, [vp]),
     "acg_vec_device_ptr": (vp, [vp]),
+    "acg_poly_combine": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp]),
     "acg_vec_download": (C.c_int, [vp, vp, vp, C.c_uint32]),
     "acg_generate_assignment_device": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                                  C.POINTER(vp), u32p]),

@@ -1412,4 +1412,26 @@ int acg_fr_binop(acg_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uin
     return ACG_OK;
 }
 
+int acg_poly_combine(acg_ctx* ctx, const uint64_t* polys, const uint64_t* weights, uint32_t n_polys, uint32_t len,
+                     uint64_t* out) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!out || (n_polys && len && (!polys || !weights))) return fail(ctx, ACG_ERR_BAD_ARG, "acg_poly_combine: bad argument");
+    if (len == 0) return ACG_OK;
+    DevBuf dp, dw, dout;
+    CU(ctx, dp.alloc((size_t)n_polys * len * sizeof(fr_t)));
+    CU(ctx, dw.alloc((size_t)n_polys * sizeof(fr_t)));
+    CU(ctx, dout.alloc((size_t)len * sizeof(fr_t)));
+    if (n_polys) {
+        if ((rc = upload_canonical(ctx, dp.as<fr_t>(), polys, (uint64_t)n_polys * len))) return rc;
+        if ((rc = upload_canonical(ctx, dw.as<fr_t>(), weights, n_polys))) return rc;
+    }
+    CU(ctx, launch_poly_combine(ctx->field, dp.as<fr_t>(), dw.as<fr_t>(), n_polys, len, dout.as<fr_t>(), ctx->stream));
+    if ((rc = download_canonical(ctx, dout.as<fr_t>(), len, out))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 4;
+    ctx->timing = acg_timing{0.f, 0.f, 0.f, 4, 0};
+    return ACG_OK;
+}
+
 }  // extern "C"

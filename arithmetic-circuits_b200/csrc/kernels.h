@@ -202,6 +202,10 @@ cudaError_t launch_bitrev_permute(const fr_t* in, fr_t* out, uint32_t log_n, uin
 cudaError_t launch_axpy2(int field, fr_t* h, const fr_t* a, const fr_t* b, fr_t d2, fr_t d1, uint64_t n,
                          cudaStream_t s);
 
+// out[i] = sum_k weight[k] * polys[k * len + i]
+cudaError_t launch_poly_combine(int field, const fr_t* polys, const fr_t* weight, uint32_t n_polys, uint64_t len,
+                                fr_t* out, cudaStream_t s);
+
 // Lagrange (K5): n <= 4096 distinct xs (Montgomery), n_polys value vectors -> coefficient vectors;
 // target: n+1 coefficients of prod (X - x_i) (may be null).  d_status: set to 1 if two xs coincide.
 cudaError_t launch_lagrange(int field, const fr_t* xs, const fr_t* ys, uint32_t n, uint32_t n_polys, fr_t* coeffs,

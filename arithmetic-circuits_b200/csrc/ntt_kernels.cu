@@ -233,6 +233,18 @@ __global__ void k_axpy2(fr_t* __restrict__ h, const fr_t* __restrict__ a, const 
     }
 }
 
+// out[i] = sum_k weight[k] * polys[k * len + i]: the scale-and-sum of verificationWitnessZk over a per-wire QAP
+// (foldQapSet / combineWithDefaults, src/QAP.hs:163-181, 314-324).  Thread per coefficient, coalesced across i.
+template <class P>
+__global__ void k_poly_combine(const fr_t* __restrict__ polys, const fr_t* __restrict__ weight, uint32_t n_polys,
+                               uint64_t len, fr_t* __restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
+        fr_t acc = fr_zero<P>();
+        for (uint32_t k = 0; k < n_polys; ++k) acc = fr_add<P>(acc, fr_mul<P>(polys[(uint64_t)k * len + i], weight[k]));
+        out[i] = acc;
+    }
+}
+
 #define ACG_DISPATCH_FIELD(field, EXPR)   \
     do {                                  \
         if ((field) == 0) {               \
@@ -442,6 +454,14 @@ cudaError_t launch_quotient_pointwise(int field, const fr_t* a, const fr_t* b, c
                                       fr_t zinv, cudaStream_t s) {
     ACG_DISPATCH_FIELD(field,
                        (k_quotient_pointwise<P><<<grid_for(n, 256, 148 * 16), 256, 0, s>>>(a, b, c, h, n, zinv)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_poly_combine(int field, const fr_t* polys, const fr_t* weight, uint32_t n_polys, uint64_t len,
+                                fr_t* out, cudaStream_t s) {
+    if (len == 0) return cudaSuccess;
+    ACG_DISPATCH_FIELD(field,
+                       (k_poly_combine<P><<<grid_for(len, 128, 148 * 16), 128, 0, s>>>(polys, weight, n_polys, len, out)));
     return cudaGetLastError();
 }
 

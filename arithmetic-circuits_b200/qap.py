@@ -623,3 +623,170 @@ def create_polynomials(ctx: Context, xs: Sequence[int], ys: Sequence[Sequence[in
     """createPolynomials' Lagrange build (src/QAP.hs:486-508): (stripped interpolants, target)."""
     polys, target = ctx.lagrange(xs, ys, True)
     return [strip(p) for p in polys], strip(target)
+
+
+# ---------------------------------------------------------------------------------------------------
+# per-wire QAP value (SURVEY 8f N4): QAP f (src/QAP.hs:74-79) as createPolynomials[FFT] returns it
+# ---------------------------------------------------------------------------------------------------
+class QAP:
+    """QAP f: one polynomial per wire for the left / right / output sets plus the target.  Storage is dense:
+    `left`, `right`, `out` are (n_cols, N, 4) limb arrays in qapSetToMap wire order (index 0 = the constant), zero-padded
+    little-endian coefficients; `target` is a stripped integer coefficient list.  kind: "fft" (roots = powers of the
+    2^k-th root of unity, src/QAP.hs:512-525) or "lagrange" (arbitrary roots, :486-508)."""
+
+    def __init__(self, field: int, layout, n_rows: int, left, right, out, target: List[int], kind: str, roots=None):
+        self.field, self.layout, self.n_rows = field, tuple(layout), n_rows
+        self.left, self.right, self.out = left, right, out
+        self.target, self.kind, self.roots = target, kind, roots
+
+    @property
+    def n_cols(self) -> int:
+        return self.left.shape[0]
+
+    def wire_poly(self, which: str, col: int) -> List[int]:
+        """The VPoly of one wire (stripped), which in {"left", "right", "out"}; col in qapSetToMap order."""
+        return strip(from_limbs(getattr(self, which)[col]))
+
+    def sets(self):
+        """-> three (constant, {i: poly}, {i: poly}, {i: poly}) tuples in the reference's QapSet shape (all wires of
+        the layout present, as after addMissingZeroes, src/QAP.hs:566-576) -- what json_io.qap_to_json takes."""
+        n_in, n_mid, n_out = self.layout
+        res = []
+        for which in ("left", "right", "out"):
+            arr = getattr(self, which)
+            polys = [strip(from_limbs(arr[c])) for c in range(self.n_cols)]
+            res.append((polys[0], {i: polys[1 + i] for i in range(n_in)},
+                        {i: polys[1 + n_in + i] for i in range(n_mid)},
+                        {i: polys[1 + n_in + n_mid + i] for i in range(n_out)}))
+        return res
+
+
+def _dense_columns(g: GenQAP, N: int) -> List[np.ndarray]:
+    """The three GenQAP column sets as dense (n_cols, N, 4) arrays: entry [col, row] = coefficient (row = position of
+    the root in ascending order, `Map.elems`), zero where the wire does not occur (addMissingZeroes) and in the padding."""
+    res = []
+    for rowptr, col, val in g.mats:
+        arr = np.zeros((g.n_cols, N, 4), np.uint64)
+        rows = np.repeat(np.arange(g.n_rows, dtype=np.int64), np.diff(rowptr.astype(np.int64)))
+        arr[col.astype(np.int64), rows] = val
+        res.append(arr)
+    return res
+
+
+def create_polynomials_fft_qap(ctx: Context, g: GenQAP, target_full_domain: bool = False) -> QAP:
+    """createPolynomialsFFT (src/QAP.hs:512-525): every wire's column interpolated on the 2^k-th roots of unity by one
+    batched inverse NTT on the device (3 * n_cols transforms of size N).  Memory is 3 * n_cols * N * 32 bytes: this is
+    the API-completeness path for moderate n_cols * N; checks at scale use the GenQAP form (linearity collapse)."""
+    N = 1
+    while N < max(1, g.n_rows):
+        N <<= 1
+    cols = _dense_columns(g, N)
+    polys = [ctx.interpolate_columns(c) if N > 1 else c for c in cols]
+    r = field_constants(g.field)["modulus"]
+    if target_full_domain or g.n_rows == N:
+        target = strip([r - 1] + [0] * (N - 1) + [1])
+    else:  # prod_{i < n} (X - omega^i)  (the convention switch of DESIGN.md section 3)
+        k = N.bit_length() - 1
+        omega, x, target = get_root_of_unity(g.field, k), 1, [1]
+        for _ in range(g.n_rows):
+            nxt = [0] * (len(target) + 1)
+            for i, c in enumerate(target):
+                nxt[i] = (nxt[i] - x * c) % r
+                nxt[i + 1] = (nxt[i + 1] + c) % r
+            target, x = nxt, x * omega % r
+    return QAP(g.field, g.layout, g.n_rows, polys[0], polys[1], polys[2], target, "fft")
+
+
+def arith_circuit_to_qap_fft(ctx: Context, circuit: ArithCircuit, roots: Optional[Sequence[Sequence[int]]] = None,
+                             root_start: int = 1) -> QAP:
+    """arithCircuitToQAPFFT (src/QAP.hs:552-561); the primitive-root function is getRootOfUnity of the field."""
+    return create_polynomials_fft_qap(ctx, arith_circuit_to_gen_qap(circuit, roots, root_start))
+
+
+def create_polynomials_qap(ctx: Context, g: GenQAP) -> QAP:
+    """createPolynomials (src/QAP.hs:486-508): Lagrange interpolation through the GenQAP's own roots on the device (K5),
+    target = prod (X - root).  n_rows <= 4096."""
+    xs = from_limbs(g.roots)
+    n = g.n_rows
+    cols = _dense_columns(g, n)
+    outs, target = [], None
+    for c in cols:
+        ys = [from_limbs(c[k]) for k in range(g.n_cols)]
+        polys, target = ctx.lagrange(xs, ys, True)
+        arr = np.zeros((g.n_cols, n, 4), np.uint64)
+        for k, p in enumerate(polys):
+            arr[k, :len(p)] = to_limbs(p) if len(p) else np.zeros((0, 4), np.uint64)
+        outs.append(arr)
+    return QAP(g.field, g.layout, n, outs[0], outs[1], outs[2], strip(target), "lagrange", xs)
+
+
+def arith_circuit_to_qap(ctx: Context, circuit: ArithCircuit, roots: Optional[Sequence[Sequence[int]]] = None,
+                         root_start: int = 1) -> QAP:
+    """arithCircuitToQAP (src/QAP.hs:542-549)."""
+    return create_polynomials_qap(ctx, arith_circuit_to_gen_qap(circuit, roots, root_start))
+
+
+def _combine(ctx: Context, arr: np.ndarray, w: np.ndarray) -> np.ndarray:
+    out = np.zeros((arr.shape[1], 4), np.uint64)
+    _check(_lib.lib().acg_poly_combine(ctx._h, _ptr(np.ascontiguousarray(arr)), _ptr(np.ascontiguousarray(w)),
+                                       arr.shape[0], arr.shape[1], _ptr(out)), ctx)
+    return out
+
+
+def verification_witness_zk_qap(ctx: Context, d1: int, d2: int, d3: int, qap: QAP, assignment: QapSet):
+    """verificationWitnessZk (src/QAP.hs:300-327) on a per-wire QAP value: a = d1*T + sum_k w_k L_k (device scale-and-sum,
+    acg_poly_combine), likewise b, c; then p = a*b - c and the exact division by T.
+      * FFT-built QAP whose row count is a power of two (T = X^N - 1): evaluations by forward NTT, the product on a
+        2N-point domain, p = h*X^N - h  =>  h is the upper half; the delta terms enter as
+        h_zk = h + d2*a + d1*b + d1*d2*T - d3 (expand (a + d1 T)(b + d2 T) - (c + d3 T)).
+      * otherwise (Lagrange build, or a padded FFT build): validity by evaluating a, b, c at the target's roots on the
+        host (small systems only: n_rows <= 512); h is then not produced here -- use the GenQAP form.
+    Returns `h` (stripped coefficient list), or None when T does not divide p; for the second case True/None."""
+    r = field_constants(qap.field)["modulus"]
+    w = assignment.to_vector(qap.layout)
+    a, b, c = (_combine(ctx, arr, w) for arr in (qap.left, qap.right, qap.out))
+    N = a.shape[0]
+    if qap.kind == "fft" and qap.n_rows == N:
+        if N == 1:
+            av, bv, cv = from_limbs(a)[0], from_limbs(b)[0], from_limbs(c)[0]
+            if (av * bv - cv) % r:
+                return None
+            h = []
+        else:
+            ea, eb, ec = ctx.ntt(a, False), ctx.ntt(b, False), ctx.ntt(c, False)
+            resid = ctx.fr_binop(1, ctx.fr_binop(2, ea, eb), ec)
+            if resid.any():
+                return None
+            pad = lambda v: np.concatenate([v, np.zeros_like(v)])
+            e2 = [ctx.ntt(pad(v), False) for v in (a, b, c)]
+            p = ctx.ntt(ctx.fr_binop(1, ctx.fr_binop(2, e2[0], e2[1]), e2[2]), True)
+            h = from_limbs(p[N:])
+        ai, bi = from_limbs(a), from_limbs(b)
+        hz = [0] * (N + 1)
+        for i in range(N):
+            hz[i] = ((h[i] if i < len(h) else 0) + d2 * ai[i] + d1 * bi[i]) % r
+        hz[0] = (hz[0] - d3 - d1 * d2) % r      # d1*d2*T = d1*d2*(X^N - 1)
+        hz[N] = (hz[N] + d1 * d2) % r
+        return strip(hz)
+    if qap.n_rows > 512:
+        raise AcgError(-6, "verification on a per-wire QAP with arbitrary roots is limited to 512 rows; use the GenQAP form")
+    if qap.kind == "fft":
+        omega = get_root_of_unity(qap.field, N.bit_length() - 1)
+        roots = [pow(omega, i, r) for i in range(qap.n_rows)]
+    else:
+        roots = [x % r for x in qap.roots]
+    ai, bi, ci = from_limbs(a), from_limbs(b), from_limbs(c)
+
+    def horner(p, x):
+        acc = 0
+        for coef in reversed(p):
+            acc = (acc * x + coef) % r
+        return acc
+    # T vanishes on its roots, so the delta terms do not change the verdict
+    ok = all((horner(ai, x) * horner(bi, x) - horner(ci, x)) % r == 0 for x in roots)
+    return True if ok else None
+
+
+def verify_assignment_qap(ctx: Context, qap: QAP, assignment: QapSet) -> bool:
+    """verifyAssignment (src/QAP.hs:276-282) on a per-wire QAP value."""
+    return verification_witness_zk_qap(ctx, 0, 0, 0, qap, assignment) is not None

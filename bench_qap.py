@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--field", default="bn254", choices=["bn254", "bls12_381"])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--witness-log-n", type=int, default=16, help="gates of the witness-generation measurement")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -82,6 +83,56 @@ def main():
                       "constraints_per_s_kernels": n / (kbest * 1e-3),
                       "note": "R1CS eval + 3 iNTT + 3 coset NTT + quotient + iNTT; wall includes D2H of h (%.0f MB)" % (32 * (n + 1) / 1e6)}),
           flush=True)
+    # witness generation (K6) on the synthetic family as an ArithCircuit, and on a wide shallow circuit
+    wg_n = min(n, 1 << args.witness_log_n)
+    circuit, inputs = acg.synth_circuit(fid, wg_n, 20260003)
+    gw, ww = acg.synth_r1cs(fid, wg_n, 20260003)
+    t0 = time.perf_counter()
+    host = acg.generate_assignment(circuit, inputs)
+    t_host = time.perf_counter() - t0
+    ctx.generate_assignment(circuit, inputs, gw.layout)  # warm-up
+    t0 = time.perf_counter()
+    dwg, n_levels = ctx.generate_assignment(circuit, inputs, gw.layout)
+    t_dev_wall = time.perf_counter() - t0
+    tm = ctx.last_timing()
+    same_w = bool((dwg.download() == ww).all())
+    print(json.dumps({"what": "witness_generation", "field": args.field, "circuit": "S(2^%d) as ArithCircuit" % args.witness_log_n
+                      if wg_n == 1 << args.witness_log_n else "S(%d)" % wg_n, "gates": wg_n, "levels": n_levels,
+                      "device_kernel_ms": tm["kernel_ms"], "device_call_wall_ms": t_dev_wall * 1e3,
+                      "host_sequential_fold_ms": t_host * 1e3, "bit_exact_vs_sequential": same_w,
+                      "note": "the synthetic family is a long dependency chain (few gates per level): single-CTA level "
+                              "mode; the device call's wall time includes the host-side levelisation"}), flush=True)
+    assert same_w
+    # a wide, shallow circuit: 8 levels of 4096 Mul gates, each over two wires of the previous level
+    import random
+    rnd = random.Random(7)
+    r_mod = acg.field_constants(fid)["modulus"]
+    width, depth = 4096, 8
+    prev = [acg.InputWire(i) for i in range(64)]
+    gates, nxt_ix = [], 0
+    for _ in range(depth):
+        cur = []
+        for _ in range(width):
+            out = acg.IntermediateWire(nxt_ix)
+            nxt_ix += 1
+            gates.append(acg.Mul(acg.Add(acg.ConstGate(rnd.randrange(r_mod)), acg.Var(rnd.choice(prev))),
+                                 acg.ScalarMul(rnd.randrange(r_mod), acg.Var(rnd.choice(prev))), out))
+            cur.append(out)
+        prev = cur
+    wide = acg.ArithCircuit(fid, gates)
+    win = {i: rnd.randrange(r_mod) for i in range(64)}
+    t0 = time.perf_counter()
+    hw = acg.generate_assignment(wide, win)
+    t_host = time.perf_counter() - t0
+    ctx.generate_assignment(wide, win)
+    dww, lv = ctx.generate_assignment(wide, win)
+    tm = ctx.last_timing()
+    same_w = bool((dww.download() == hw.to_vector()).all())
+    print(json.dumps({"what": "witness_generation", "field": args.field, "circuit": "wide: %d levels x %d Mul gates" % (depth, width),
+                      "gates": len(gates), "levels": lv, "device_kernel_ms": tm["kernel_ms"],
+                      "host_sequential_fold_ms": t_host * 1e3, "bit_exact_vs_sequential": same_w,
+                      "note": "grid-barrier mode (cooperative launch)"}), flush=True)
+    assert same_w
     if not args.no_cpu:
         from oracle import c_oracle as CO
         CO.build()

@@ -170,6 +170,13 @@ int acg_qap_witness(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, const uin
 int acg_lagrange(acg_ctx* ctx, const uint64_t* xs, const uint64_t* ys, uint32_t n, uint32_t n_polys,
                  uint64_t* coeffs, uint64_t* target);
 
+/* ---- per-wire QAP: the scale-and-sum of verificationWitnessZk (src/QAP.hs:314-324; foldQapSet,
+ * combineWithDefaults :163-181) over polynomials held per wire, as createPolynomials[FFT] returns them:
+ * out[i] = sum_k weights[k] * polys[k*len + i].  polys: n_polys coefficient vectors of length len (zero-padded),
+ * weights: the witness value of each wire.  Canonical limbs in and out; blocking. */
+int acg_poly_combine(acg_ctx* ctx, const uint64_t* polys, const uint64_t* weights, uint32_t n_polys, uint32_t len,
+                     uint64_t* out);
+
 /* ---- field ops on the device (K1 self-test surface) ------------------------------------------------
  * op: 0 add, 1 sub, 2 mul, 3 inverse of a (inv 0 = 0, as evalGate treats it, Arithmetic.hs:130).
  * n canonical elements each; blocking. */

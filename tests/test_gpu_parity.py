@@ -144,6 +144,66 @@ def test_mixed_circuits_gpu(acg, ctxs, idx):
             assert acg.strip(acg.from_limbs(bufs[k])) == unhex(q[k]), k
 
 
+# ------------------------------------------------------------------------------------------------ per-wire QAP (N4)
+def _oracle_sets_as_columns(F, qap_sets, layout):
+    """oracle QapSet of polynomials -> list over qapSetToMap columns"""
+    n_in, n_mid, n_out = layout
+    cols = [qap_sets.constant]
+    cols += [qap_sets.inputs.get(i, []) for i in range(n_in)]
+    cols += [qap_sets.mids.get(i, []) for i in range(n_mid)]
+    cols += [qap_sets.outputs.get(i, []) for i in range(n_out)]
+    return [O.p_norm(F, c) for c in cols]
+
+
+def test_per_wire_qap_matches_oracle(acg, ctx_bn):
+    """arithCircuitToQAPFFT / arithCircuitToQAP as QAP values: every wire polynomial and the target equal the big-int
+    oracle's; verificationWitnessZk on the QAP value (device scale-and-sum + NTT product) equals the oracle's h for
+    deltas (3, 5, 7); a bad witness gives None.  KAT-1 circuit (test/Test/QAP.hs:48-62) extended to 4 gates so that the
+    FFT domain is exactly the row count, and the 3-gate original for the padded / Lagrange cases."""
+    F = O.BN254
+    og = [O.Mul(O.Var(O.inw(0)), O.Var(O.inw(1)), O.midw(0)), O.Mul(O.Var(O.inw(2)), O.Var(O.inw(3)), O.midw(1)),
+          O.Mul(O.Add(O.ConstGate(10), O.Var(O.midw(0))), O.Var(O.midw(1)), O.midw(2)),
+          O.Mul(O.ScalarMul(F.r - 3, O.Var(O.midw(2))), O.Add(O.Var(O.inw(0)), O.ConstGate(5)), O.outw(0))]
+    inputs = {0: 2, 1: 3, 2: 4, 3: 5}
+    for gates_o, lagrange_roots in ((og, None), (og[:3], [[7], [8], [9]])):
+        c = acg.ArithCircuit(0, gates_acg(acg, gates_o))
+        a = acg.generate_assignment(c, inputs)
+        oa = O.generate_assignment(F, gates_o, inputs)
+        # FFT build, roots 1.. (Example.hs:24)
+        roots = O.fresh_roots(gates_o, 1)
+        oq = O.arith_circuit_to_qap_fft(F, roots, gates_o)
+        q = acg.arith_circuit_to_qap_fft(ctx_bn, c, None, 1)
+        for which, osets in (("left", oq.left), ("right", oq.right), ("out", oq.out)):
+            want = _oracle_sets_as_columns(F, osets, q.layout)
+            assert [q.wire_poly(which, k) for k in range(q.n_cols)] == want, which
+        assert q.target == O.p_norm(F, oq.target)
+        oh = O.verification_witness_zk(F, 3, 5, 7, oq, oa)[0]
+        got = acg.verification_witness_zk_qap(ctx_bn, 3, 5, 7, q, a)
+        if len(gates_o) == 4:
+            assert oh is not None and got == O.p_norm(F, oh)
+            assert acg.verification_witness_zk_qap(ctx_bn, 0, 0, 0, q, a) == O.p_norm(F, O.verification_witness(F, oq, oa))
+        else:
+            assert oh is not None and got is True
+        assert acg.verify_assignment_qap(ctx_bn, q, a)
+        # JSON of the QAP value round-trips (N2)
+        from arithmetic_circuits_b200 import json_io as J
+        l2, r2, o2, t2 = J.qap_from_json(J.loads(J.dumps(J.qap_to_json(*q.sets(), q.target))))
+        assert t2 == q.target and l2[1][0] == q.wire_poly("left", 1)
+        if lagrange_roots is not None:
+            oql = O.arith_circuit_to_qap(F, lagrange_roots, gates_o)
+            ql = acg.arith_circuit_to_qap(ctx_bn, c, lagrange_roots)
+            for which, osets in (("left", oql.left), ("right", oql.right), ("out", oql.out)):
+                assert [ql.wire_poly(which, k) for k in range(ql.n_cols)] == _oracle_sets_as_columns(F, osets, ql.layout)
+            assert ql.target == O.p_norm(F, oql.target)        # KAT-1: X^3 - 24X^2 + 191X - 504
+            assert ql.target == [F.r - 504, 191, F.r - 24, 1]
+            assert acg.verify_assignment_qap(ctx_bn, ql, a)
+        # a bad witness
+        bad = acg.generate_assignment(c, inputs)
+        bad.update(acg.IntermediateWire(0), 7)
+        assert acg.verification_witness_zk_qap(ctx_bn, 3, 5, 7, q, bad) is None
+        assert not acg.verify_assignment_qap(ctx_bn, q, bad)
+
+
 # ------------------------------------------------------------------------------------------------ K6
 @pytest.mark.parametrize("idx", [0, 1, 2])
 def test_device_witness_generation_golden(acg, ctxs, idx):
