@@ -49,6 +49,10 @@ PROTOTYPES = {
     "acg_vec_free": (None, [vp]),
     "acg_vec_len": (C.c_uint32, [vp]),
     "acg_vec_device_ptr": (vp, [vp]),
+    "acg_peer_create": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.POINTER(vp), vp]),
+    "acg_peer_connect": (C.c_int, [vp, vp, vp]),
+    "acg_peer_free": (None, [vp]),
+    "acg_r1cs_check_async_allreduce": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "acg_poly_combine": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp]),
     "acg_vec_download": (C.c_int, [vp, vp, vp, C.c_uint32]),
     "acg_generate_assignment_device": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,

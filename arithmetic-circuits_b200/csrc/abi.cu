@@ -30,6 +30,8 @@ struct acg_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* d_result = nullptr;  // {n_violations, first_bad_row}
+    unsigned long long* d_accum = nullptr;   // scratch pair the check kernels accumulate into + CTA ticket (u32)
+    unsigned int* d_ticket = nullptr;        //   both reset by the finalising CTA of every check (CheckEpilogue)
     int* d_flag = nullptr;
     unsigned long long* h_result = nullptr;  // pinned
     int* h_flag = nullptr;                   // pinned
@@ -70,6 +72,16 @@ struct acg_vec {
     acg_ctx* ctx = nullptr;
     fr_t* d = nullptr;
     uint32_t n = 0;
+};
+
+struct acg_peer {  // exchange buffers of a group of row-shard ranks (one process per GPU, CUDA IPC)
+    acg_ctx* ctx = nullptr;
+    uint32_t world = 0, rank = 0;
+    unsigned long long* local = nullptr;  // this rank's buffer (cudaMalloc)
+    void* mapped[kMaxPeers] = {};         // peers' buffers as opened here (null for self / not connected)
+    PeerSlots slots{};
+    unsigned long long seq = 0;
+    bool connected = false;
 };
 
 namespace {
@@ -266,40 +278,63 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
     }
 }
 
+// Enqueues one check of the shard: the kernels accumulate into the context's scratch pair and the LAST launch
+// finalises into d_result (kernels.h CheckEpilogue) -- including, when `peer` is given, the all-reduce over peer
+// memory.  No initialisation launch; one kernel for a system without over-long rows.
 int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long long* d_result, fr_t* Aw, fr_t* Bw,
-                  fr_t* Cw, cudaStream_t s, uint32_t* launches) {
+                  fr_t* Cw, cudaStream_t s, uint32_t* launches, acg_peer* peer = nullptr) {
     const uint32_t n_local = m->row_end - m->row_begin;
-    CU(ctx, launch_init_result(d_result, s));
-    ++*launches;
-    int which = ctx->check_kernel == ACG_CHECK_AUTO ? ACG_CHECK_TILED : ctx->check_kernel;
+    CheckEpilogue acc{ctx->d_accum, ctx->d_ticket, nullptr, PeerSlots{}, 0ull};  // accumulate only
+    CheckEpilogue fin = acc;                                                     // .. and finalise
+    fin.out = d_result;
+    if (peer) {
+        fin.peers = peer->slots;
+        fin.seq = ++peer->seq;
+    }
+    const int which = ctx->check_kernel == ACG_CHECK_AUTO ? ACG_CHECK_TILED : ctx->check_kernel;
+    const bool prof = 2 * (ctx->prof_used + 1) <= ctx->prof_ev.size();
+    bool finalised = false;
     if (which == ACG_CHECK_ROWWISE) {
-        const bool prof_r = 2 * (ctx->prof_used + 1) <= ctx->prof_ev.size();
-        if (prof_r) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
+        if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
         if (n_local) {
-            CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, 0, n_local, m->row_begin, d_result, Aw, Bw, Cw, s));
+            CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, 0, n_local, m->row_begin, fin, Aw, Bw, Cw, s));
             ++*launches;
+            finalised = true;
         }
-        if (prof_r) {
+        if (prof) {
             CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], s));
             ++ctx->prof_used;
         }
-        return ACG_OK;
+    } else {
+        if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
+        if (m->n_tiles) {
+            DevTileStream ts{m->d_stream, m->d_meta, m->d_far_cols, m->n_tiles, (uint32_t)m->variant,
+                             (uint32_t)(m->blob_bytes / 16), m->n_cols};
+            const bool last = m->long_ranges.empty();
+            CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin, last ? fin : acc, Aw, Bw, Cw, ctx->sm_count, s));
+            ++*launches;
+            finalised = last;
+        }
+        if (prof) {
+            CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], s));
+            ++ctx->prof_used;
+        }
+        for (size_t i = 0; i < m->long_ranges.size(); ++i) {
+            const auto& lr = m->long_ranges[i];
+            const bool last = i + 1 == m->long_ranges.size();
+            CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, lr.first, lr.second, m->row_begin, last ? fin : acc, Aw,
+                                        Bw, Cw, s));
+            ++*launches;
+            finalised = finalised || last;
+        }
     }
-    const bool prof = 2 * (ctx->prof_used + 1) <= ctx->prof_ev.size();
-    if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
-    if (m->n_tiles) {
-        DevTileStream ts{m->d_stream, m->d_meta, m->d_far_cols, m->n_tiles, (uint32_t)m->variant,
-                         (uint32_t)(m->blob_bytes / 16), m->n_cols};
-        CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin, d_result, Aw, Bw, Cw, ctx->sm_count, s));
+    if (!finalised) {  // an empty shard: nothing ran, the result is {0, none} (and the peers still expect this rank)
+        CU(ctx, launch_init_result(d_result, s));
         ++*launches;
-    }
-    if (prof) {
-        CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], s));
-        ++ctx->prof_used;
-    }
-    for (const auto& lr : m->long_ranges) {
-        CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, lr.first, lr.second, m->row_begin, d_result, Aw, Bw, Cw, s));
-        ++*launches;
+        if (peer) {
+            CU(ctx, launch_peer_allreduce(fin.peers, fin.seq, d_result, s));
+            ++*launches;
+        }
     }
     return ACG_OK;
 }
@@ -371,6 +406,13 @@ int acg_ctx_create(int field_id, int device, acg_ctx** out) {
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc(&ctx->d_result, 2 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->d_accum, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    ctx->d_ticket = reinterpret_cast<unsigned int*>(ctx->d_accum + 2);
+    {
+        const unsigned long long init[4] = {0ull, ~0ull, 0ull, 0ull};
+        if ((e = cudaMemcpy(ctx->d_accum, init, sizeof init, cudaMemcpyHostToDevice)) != cudaSuccess)
+            return bail(e, "cudaMemcpy");
+    }
     if ((e = cudaMalloc(&ctx->d_flag, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMallocHost(&ctx->h_result, 2 * sizeof(unsigned long long))) != cudaSuccess)
         return bail(e, "cudaMallocHost");
@@ -390,6 +432,7 @@ void acg_ctx_destroy(acg_ctx* ctx) {
         cudaFree(kv.second.ilo);
     }
     if (ctx->d_result) cudaFree(ctx->d_result);
+    if (ctx->d_accum) cudaFree(ctx->d_accum);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
@@ -1058,10 +1101,13 @@ int acg_r1cs_check_host(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const ac
     if (*ctx->h_flag & 2) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_check_host: malformed CSR (rowptr / column index)");
     if (*ctx->h_flag & 1) return fail(ctx, ACG_ERR_NON_CANONICAL, "acg_r1cs_check_host: field element >= modulus");
     dev.tagged = 0;
-    CU(ctx, launch_init_result(ctx->d_result, s));
-    ++launches;
+    const CheckEpilogue fin{ctx->d_accum, ctx->d_ticket, ctx->d_result, PeerSlots{}, 0ull};
+    if (n_rows == 0) {
+        CU(ctx, launch_init_result(ctx->d_result, s));
+        ++launches;
+    }
     if (n_rows) {
-        CU(ctx, launch_r1cs_rowwise(ctx->field, dev, d_w, 0, n_rows, 0, ctx->d_result, nullptr, nullptr, nullptr, s));
+        CU(ctx, launch_r1cs_rowwise(ctx->field, dev, d_w, 0, n_rows, 0, fin, nullptr, nullptr, nullptr, s));
         ++launches;
     }
     CU(ctx, cudaEventRecord(ctx->ev[2], s));
@@ -1431,6 +1477,81 @@ int acg_poly_combine(acg_ctx* ctx, const uint64_t* polys, const uint64_t* weight
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->launches += 4;
     ctx->timing = acg_timing{0.f, 0.f, 0.f, 4, 0};
+    return ACG_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// multi-GPU: result all-reduce over peer memory
+// --------------------------------------------------------------------------------------------------
+int acg_peer_create(acg_ctx* ctx, uint32_t world, uint32_t rank, acg_peer** out, uint8_t* handle_out) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!out || !handle_out || world == 0 || world > kMaxPeers || rank >= world)
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_peer_create: bad argument (1 <= world <= 8)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == ACG_PEER_HANDLE_BYTES, "IPC handle size");
+    *out = nullptr;
+    acg_peer* p = new (std::nothrow) acg_peer();
+    if (!p) return ACG_ERR_OOM;
+    p->ctx = ctx;
+    p->world = world;
+    p->rank = rank;
+    cudaError_t e = cudaMalloc(&p->local, kPeerBufferBytes);
+    if (e == cudaSuccess) e = cudaMemset(p->local, 0, kPeerBufferBytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p->local);
+    if (e != cudaSuccess) {
+        cudaFree(p->local);
+        delete p;
+        return fail_cuda(ctx, e, "acg_peer_create");
+    }
+    std::memcpy(handle_out, &h, sizeof h);
+    *out = p;
+    return ACG_OK;
+}
+
+int acg_peer_connect(acg_ctx* ctx, acg_peer* p, const uint8_t* handles) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!p || p->ctx != ctx || !handles || p->connected) return fail(ctx, ACG_ERR_BAD_ARG, "acg_peer_connect: bad argument");
+    for (uint32_t r = 0; r < p->world; ++r) {
+        if (r == p->rank) {
+            p->slots.base[r] = p->local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)r * sizeof h, sizeof h);
+        CU(ctx, cudaIpcOpenMemHandle(&p->mapped[r], h, cudaIpcMemLazyEnablePeerAccess));
+        p->slots.base[r] = static_cast<unsigned long long*>(p->mapped[r]);
+    }
+    p->slots.world = p->world;
+    p->slots.rank = p->rank;
+    p->connected = true;
+    return ACG_OK;
+}
+
+void acg_peer_free(acg_peer* p) {
+    if (!p) return;
+    if (p->ctx) cudaSetDevice(p->ctx->device);
+    for (uint32_t r = 0; r < kMaxPeers; ++r)
+        if (p->mapped[r]) cudaIpcCloseMemHandle(p->mapped[r]);
+    cudaFree(p->local);
+    delete p;
+}
+
+int acg_r1cs_check_async_allreduce(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, acg_peer* peer,
+                                   uint64_t* d_result, void* stream) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!m || !w || !d_result || !peer || m->ctx != ctx || w->ctx != ctx || peer->ctx != ctx || w->n != m->n_cols ||
+        !peer->connected)
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_check_async_allreduce: bad argument");
+    uint32_t launches = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rc = enqueue_check(ctx, m, w->d, reinterpret_cast<unsigned long long*>(d_result), nullptr, nullptr, nullptr, s,
+                       &launches, peer);
+    if (rc) return rc;
+    ctx->launches += launches;
+    ctx->timing.kernel_launches = launches;
     return ACG_OK;
 }
 

@@ -141,6 +141,31 @@ struct DevTileStream {
     uint32_t n_cols;            // witness length
 };
 
+// All-reduce of the check result over peer memory (multi-GPU row shards): base[r] = rank r's exchange buffer as
+// mapped into this process, 2 (sequence parity) x kMaxPeers slots of 4 x u64 {count, first bad row, sequence, pad}.
+constexpr uint32_t kMaxPeers = 8;
+constexpr size_t kPeerBufferBytes = 2 * kMaxPeers * 4 * sizeof(unsigned long long);
+struct PeerSlots {
+    unsigned long long* base[kMaxPeers];
+    uint32_t world, rank;
+};
+// How a check kernel hands over its result.  The kernels accumulate {violation count, first bad row} into the
+// context's scratch pair `accum`; the launch that carries `out != nullptr` (the last one of a check) finalises: its
+// last CTA to finish (ticket counter) reads the pair, resets scratch and ticket for the next check, all-reduces the
+// pair over peer memory when peers.world > 1 (see PeerSlots), and writes the final pair to `out`.  No separate
+// initialisation or reduction launch, no collective library call.
+struct CheckEpilogue {
+    unsigned long long* accum;
+    unsigned int* ticket;
+    unsigned long long* out;
+    PeerSlots peers;
+    unsigned long long seq;
+};
+// Publishes d_result[0..1] to every peer, waits for every peer's pair of step `seq`, leaves {sum of the counts,
+// min of the first bad rows} in d_result (count = ~0 if a peer did not arrive within ~4 s).
+cudaError_t launch_peer_allreduce(const PeerSlots& ps, unsigned long long seq, unsigned long long* d_result,
+                                  cudaStream_t s);
+
 cudaError_t launch_to_mont(int field, fr_t* v, uint64_t n, int* d_bad_flag, cudaStream_t s);
 cudaError_t launch_from_mont(int field, fr_t* v, uint64_t n, cudaStream_t s);
 cudaError_t launch_fr_binop(int field, int op, const fr_t* a, const fr_t* b, fr_t* o, uint64_t n, cudaStream_t s);
@@ -148,12 +173,11 @@ cudaError_t launch_init_result(unsigned long long* d_result, cudaStream_t s);
 
 // thread-per-row check over local rows [row_lo, row_hi); Aw/Bw/Cw may be null
 cudaError_t launch_r1cs_rowwise(int field, const DevR1cs& m, const fr_t* w, uint32_t row_lo, uint32_t row_hi,
-                                uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
+                                uint64_t row_base, const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw,
                                 cudaStream_t s);
 // TMA-staged tile kernel over the tile stream.
 cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w, uint64_t row_base,
-                              unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count,
-                              cudaStream_t s);
+                              const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count, cudaStream_t s);
 // general values inside the blobs: canonical -> Montgomery in place; offs[i] = byte offset / 16 of value i
 cudaError_t launch_to_mont_scattered(int field, uint8_t* blobs, const uint32_t* offs, uint64_t n, int* d_bad_flag,
                                      cudaStream_t s);

@@ -78,6 +78,101 @@ __global__ void k_init_result(unsigned long long* r) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// all-reduce of the {violation count, first bad row} pair over peer memory (NVLink / NVSwitch P2P)
+// ------------------------------------------------------------------------------------------------
+// The only exchange of the row-sharded check is 16 bytes per rank per check.  Instead of a NCCL collective (a
+// separate launch with ~15 us of latency next to a ~65 us kernel) every rank STORES its pair straight into every
+// peer's exchange buffer -- plain system-scope stores through the NVLink peer mapping (CUDA IPC), data first, then a
+// release store of the step's sequence number -- and then reads the world's pairs from its OWN buffer, spinning on
+// the sequence numbers with acquire loads.  One warp, one lane per rank.  Buffers are double-buffered by sequence
+// parity: a rank can publish step s + 1 while a slower peer still reads step s, and it cannot get two steps ahead
+// because finishing s + 1 needs that peer's s + 1 publication, which follows its step-s read in stream order.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// one warp: (cnt, first) of this rank in, the world's {sum, min} out (valid on every lane); cnt = ~0 on a timeout
+__device__ __forceinline__ void peer_allreduce_warp(const PeerSlots& ps, unsigned long long seq, unsigned long long& cnt,
+                                                    unsigned long long& first) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t par = (uint32_t)(seq & 1ull);
+    if (lane < ps.world) {
+        unsigned long long* dst = ps.base[lane] + (size_t)(par * kMaxPeers + ps.rank) * 4u;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(cnt) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(first) : "memory");
+        st_release_sys(dst + 2, seq);
+    }
+    unsigned long long c = 0ull, f = ~0ull;
+    bool timed_out = false;
+    if (lane < ps.world) {
+        const unsigned long long* src = ps.base[ps.rank] + (size_t)(par * kMaxPeers + lane) * 4u;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(src + 2) != seq) {
+            if (clock64() - t0 > 8000000000ll) {  // ~4 s: a peer never arrived; report instead of hanging the GPU
+                timed_out = true;
+                break;
+            }
+            __nanosleep(100);
+        }
+        c = src[0];
+        f = src[1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        const unsigned long long g = __shfl_xor_sync(0xffffffffu, f, o);
+        f = g < f ? g : f;
+    }
+    const bool any_timeout = __any_sync(0xffffffffu, timed_out);
+    cnt = any_timeout ? ~0ull : c;
+    first = f;
+}
+// stand-alone form (a check that launched no kernel on this rank still has to take part)
+__global__ void k_peer_allreduce(PeerSlots ps, unsigned long long seq, unsigned long long* __restrict__ result) {
+    unsigned long long cnt = result[0], first = result[1];
+    peer_allreduce_warp(ps, seq, cnt, first);
+    if (threadIdx.x == 0) {
+        result[0] = cnt;
+        result[1] = first;
+    }
+}
+
+// End of a check kernel (every thread of every CTA calls it): see CheckEpilogue in kernels.h.
+__device__ __forceinline__ void finish_check(const CheckEpilogue& ep) {
+    if (ep.out == nullptr) return;  // an earlier launch of the same check: it only accumulates
+    __shared__ uint32_t s_last;
+    __syncthreads();  // every warp of this CTA has reported
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(ep.ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last == 0u || threadIdx.x >= 32u) return;
+    __threadfence();
+    unsigned long long cnt = __ldcg(ep.accum), first = __ldcg(ep.accum + 1);
+    if (threadIdx.x == 0) {  // scratch and ticket ready for the next check
+        ep.accum[0] = 0ull;
+        ep.accum[1] = ~0ull;
+        *ep.ticket = 0u;
+    }
+    if (ep.peers.world > 1u) peer_allreduce_warp(ep.peers, ep.seq, cnt, first);
+    if (threadIdx.x == 0) {
+        ep.out[0] = cnt;
+        ep.out[1] = first;
+    }
+}
+
+cudaError_t launch_peer_allreduce(const PeerSlots& ps, unsigned long long seq, unsigned long long* d_result,
+                                  cudaStream_t s) {
+    k_peer_allreduce<<<1, 32, 0, s>>>(ps, seq, d_result);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // row-wise kernel
 // ------------------------------------------------------------------------------------------------
 template <class P>
@@ -104,9 +199,9 @@ __device__ __forceinline__ fr_t row_dot(const DevCsr& M, uint32_t row, const fr_
 
 template <class P, bool EMIT>
 __global__ void __launch_bounds__(256) k_r1cs_rowwise(DevR1cs m, const fr_t* __restrict__ w, uint32_t row_lo,
-                                                      uint32_t row_hi, uint64_t row_base,
-                                                      unsigned long long* __restrict__ result, fr_t* __restrict__ Aw,
-                                                      fr_t* __restrict__ Bw, fr_t* __restrict__ Cw) {
+                                                      uint32_t row_hi, uint64_t row_base, CheckEpilogue ep,
+                                                      fr_t* __restrict__ Aw, fr_t* __restrict__ Bw,
+                                                      fr_t* __restrict__ Cw) {
     // rows are handed out in warp-sized groups so the ballot below is warp-uniform
     const uint32_t n = row_hi - row_lo;
     const uint32_t n_groups = (n + 31u) / 32u;
@@ -126,8 +221,9 @@ __global__ void __launch_bounds__(256) k_r1cs_rowwise(DevR1cs m, const fr_t* __r
             bad = !fr_eq(fr_mul<P>(a, b), c);
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, bad);
-        if (bal != 0u && lane_id() == 0u) report_bad_rows(result, bal, row_base + row_lo + (uint64_t)g * 32u);
+        if (bal != 0u && lane_id() == 0u) report_bad_rows(ep.accum, bal, row_base + row_lo + (uint64_t)g * 32u);
     }
+    finish_check(ep);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -312,9 +408,8 @@ __device__ unsigned long long g_tiled_phase_cycles[2][8];
 //     earlier), so that the bulk copies issued the moment P3 of tile i is done complete after one L2 round trip.
 template <class P, bool EMIT, int V, bool TIMING = false>
 __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerSm)
-    k_r1cs_tiled(DevTileStream ts, const fr_t* __restrict__ w, uint64_t row_base,
-                 unsigned long long* __restrict__ result, fr_t* __restrict__ Aw, fr_t* __restrict__ Bw,
-                 fr_t* __restrict__ Cw) {
+    k_r1cs_tiled(DevTileStream ts, const fr_t* __restrict__ w, uint64_t row_base, CheckEpilogue ep,
+                 fr_t* __restrict__ Aw, fr_t* __restrict__ Bw, fr_t* __restrict__ Cw) {
     using namespace tiled;
     using C = Cfg<V>;
     static_assert(kTileGeom[V].max_far <= kFarPerThread * C::kThreads, "far slots exceed the per-thread gathers");
@@ -341,7 +436,10 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     // this CTA's run of tiles
     const uint32_t t_begin = (uint32_t)((uint64_t)blockIdx.x * ts.n_tiles / gridDim.x);
     const uint32_t t_end = (uint32_t)((uint64_t)(blockIdx.x + 1u) * ts.n_tiles / gridDim.x);
-    if (t_begin >= t_end) return;
+    if (t_begin >= t_end) {  // (the launcher never makes the grid larger than the tile count)
+        finish_check(ep);
+        return;
+    }
     const TileMeta tm = ts.meta[t_begin];  // the first tile of the run is described from outside
     // column 0 is the constant wire: w[0] == 1 for every witness the reference builds, and then a general
     // coefficient on column 0 is its own product (kernels.h); anything else takes the multiply-in-place path
@@ -447,7 +545,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
             bad = !fr_eq(fr_mul<P>(b, a), c);  // b (<= p) is the vector operand, a the limb-wise scalar
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, bad);
-        if (bal != 0u && lane == 0u) report_bad_rows(result, bal, row_base + h.row0 + (tid & ~31u));
+        if (bal != 0u && lane == 0u) report_bad_rows(ep.accum, bal, row_base + h.row0 + (tid & ~31u));
         mark(4);
         if (tile + 1u == t_end) break;
         // blob and window were read (and the term array written) through the generic proxy; order that before
@@ -467,6 +565,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         for (int k = 0; k < 7; ++k) atomicAdd(&g_tiled_phase_cycles[rw][k], ph[rw][k]);
         atomicAdd(&g_tiled_phase_cycles[rw][7], (unsigned long long)it);
     }
+    finish_check(ep);
 }
 
 template <class P>
@@ -532,24 +631,24 @@ cudaError_t launch_init_result(unsigned long long* d_result, cudaStream_t s) {
 }
 
 cudaError_t launch_r1cs_rowwise(int field, const DevR1cs& m, const fr_t* w, uint32_t row_lo, uint32_t row_hi,
-                                uint64_t row_base, unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw,
+                                uint64_t row_base, const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw,
                                 cudaStream_t s) {
     if (row_hi <= row_lo) return cudaSuccess;
     const bool emit = Aw || Bw || Cw;
     const unsigned grid = grid_for(row_hi - row_lo, 256, 148 * 64);
     if (emit) {
-        ACG_DISPATCH_FIELD(field, (k_r1cs_rowwise<P, true><<<grid, 256, 0, s>>>(m, w, row_lo, row_hi, row_base,
-                                                                                 d_result, Aw, Bw, Cw)));
+        ACG_DISPATCH_FIELD(field, (k_r1cs_rowwise<P, true><<<grid, 256, 0, s>>>(m, w, row_lo, row_hi, row_base, ep,
+                                                                                 Aw, Bw, Cw)));
     } else {
-        ACG_DISPATCH_FIELD(field, (k_r1cs_rowwise<P, false><<<grid, 256, 0, s>>>(m, w, row_lo, row_hi, row_base,
-                                                                                  d_result, Aw, Bw, Cw)));
+        ACG_DISPATCH_FIELD(field, (k_r1cs_rowwise<P, false><<<grid, 256, 0, s>>>(m, w, row_lo, row_hi, row_base, ep,
+                                                                                  Aw, Bw, Cw)));
     }
     return cudaGetLastError();
 }
 
 template <class P, bool EMIT, int V>
 static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uint64_t row_base,
-                                     unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count,
+                                     const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count,
                                      cudaStream_t s) {
     using C = tiled::Cfg<V>;
     // ACG_K2_CTAS_PER_SM=k (a measurement aid): pad the dynamic shared memory so that only k CTAs fit on an SM
@@ -573,8 +672,8 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
                                  (int)C::kBytes);
             unsigned long long z[2][8] = {};
             cudaMemcpyToSymbolAsync(g_tiled_phase_cycles, z, sizeof z, 0, cudaMemcpyHostToDevice, s);
-            k_r1cs_tiled<P, false, 0, true><<<grid, kTileGeom[0].threads, C::kBytes, s>>>(ts, w, row_base, d_result,
-                                                                                          Aw, Bw, Cw);
+            k_r1cs_tiled<P, false, 0, true><<<grid, kTileGeom[0].threads, C::kBytes, s>>>(ts, w, row_base, ep, Aw, Bw,
+                                                                                          Cw);
             cudaMemcpyFromSymbolAsync(z, g_tiled_phase_cycles, sizeof z, 0, cudaMemcpyDeviceToHost, s);
             cudaStreamSynchronize(s);
             static int printed = 0;
@@ -593,18 +692,16 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
             return cudaGetLastError();
         }
     }
-    k_r1cs_tiled<P, EMIT, V><<<grid, kTileGeom[V].threads, smem_bytes, s>>>(ts, w, row_base, d_result, Aw, Bw, Cw);
+    k_r1cs_tiled<P, EMIT, V><<<grid, kTileGeom[V].threads, smem_bytes, s>>>(ts, w, row_base, ep, Aw, Bw, Cw);
     return cudaGetLastError();
 }
 
 cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w, uint64_t row_base,
-                              unsigned long long* d_result, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count,
-                              cudaStream_t s) {
+                              const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count, cudaStream_t s) {
     if (ts.n_tiles == 0) return cudaSuccess;
     const bool emit = Aw || Bw || Cw;
 #define ACG_TILED(EMITV, VAR)                                                                                     \
-    ACG_DISPATCH_FIELD(field, return (launch_tiled_impl<P, EMITV, VAR>(ts, w, row_base, d_result, Aw, Bw, Cw, \
-                                                                       sm_count, s)))
+    ACG_DISPATCH_FIELD(field, return (launch_tiled_impl<P, EMITV, VAR>(ts, w, row_base, ep, Aw, Bw, Cw, sm_count, s)))
 #define ACG_TILED_V(VAR)                \
     do {                                \
         if (emit) ACG_TILED(true, VAR); \

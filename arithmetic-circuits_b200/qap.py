@@ -453,6 +453,12 @@ class Context:
     def r1cs_check_async(self, m: "DeviceR1cs", w: "DeviceVec", d_result_ptr: int, stream: int):
         _check(_lib.lib().acg_r1cs_check_async(self._h, m._h, w._h, C.c_void_p(d_result_ptr), C.c_void_p(stream)), self)
 
+    def r1cs_check_async_allreduce(self, m: "DeviceR1cs", w: "DeviceVec", peer: "PeerExchange", d_result_ptr: int,
+                                   stream: int):
+        """Shard check + all-reduce of the result pair over peer memory (acg_r1cs_check_async_allreduce)."""
+        _check(_lib.lib().acg_r1cs_check_async_allreduce(self._h, m._h, w._h, peer._h, C.c_void_p(d_result_ptr),
+                                                         C.c_void_p(stream)), self)
+
     def r1cs_check_host(self, g: GenQAP, w: np.ndarray) -> Tuple[int, int]:
         w = np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4)
         a, b, c = g.csr_structs()
@@ -514,6 +520,32 @@ class Context:
         o = np.empty_like(a)
         _check(_lib.lib().acg_fr_binop(self._h, op, _ptr(a), _ptr(b), _ptr(o), a.shape[0]), self)
         return o
+
+
+class PeerExchange:
+    """Exchange buffers of a group of row-shard ranks (include/acg.h "multi-GPU row shards").  `all_gather_bytes` is a
+    callable taking this rank's 64-byte handle (bytes) and returning the list of all ranks' handles in rank order --
+    sharding.connect_peers() supplies one over torch.distributed."""
+
+    def __init__(self, ctx: Context, world: int, rank: int, all_gather_bytes):
+        self.ctx = ctx
+        h = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        _check(_lib.lib().acg_peer_create(ctx._h, world, rank, C.byref(h), handle), ctx)
+        self._h = h
+        handles = all_gather_bytes(bytes(handle))
+        if len(handles) != world or any(len(x) != 64 for x in handles):
+            raise AcgError(-1, "PeerExchange: need one 64-byte handle per rank")
+        blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+        _check(_lib.lib().acg_peer_connect(ctx._h, self._h, blob), ctx)
+
+    def free(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            _lib.lib().acg_peer_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        self.free()
 
 
 class DeviceR1cs:

@@ -36,6 +36,25 @@ def row_shard_balanced(rowptrs: Sequence[np.ndarray], world_size: int, rank: int
     return cuts[rank], cuts[rank + 1]
 
 
+def connect_peers(ctx, group=None):
+    """PeerExchange for the ranks of a torch.distributed group (one process per GPU on one NVSwitch node): the 64-byte
+    CUDA IPC handles are all-gathered through the group, then every rank maps its peers' exchange buffers."""
+    import torch
+    import torch.distributed as dist
+    from .qap import PeerExchange
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def all_gather_bytes(mine: bytes):
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t, group=group)
+        return [bytes(x.cpu().tolist()) for x in out]
+
+    return PeerExchange(ctx, world, rank, all_gather_bytes)
+
+
 def reduce_check_result(result, group=None):
     """result: int64 tensor [n_violations, first_bad_row] (first_bad_row = -1, i.e. UINT64_MAX, when the
     shard is clean), on the device of the process group's backend.  Returns (total violations, first bad

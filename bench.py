@@ -8,14 +8,16 @@ circuits S(n, seed, field) of SURVEY.md 8(d).  Metric: R1CS constraints / second
 
 One "step" = one check of every constraint of the (sharded) system.  Weak scaling: each rank owns
 2^log_rows consecutive rows of a global system of N * 2^log_rows rows (witness replicated), checks
-them with the tiled CUDA kernel and joins ONE NCCL all-reduce of the violated-row count.
+them with the tiled CUDA kernel -- ONE kernel launch per step: the kernel's last CTA finalises the result pair
+and, for N > 1, all-reduces it over peer memory (NVLink P2P stores; `--collective nccl` uses one NCCL all-reduce).
 
   value     device-resident throughput: K steps timed with CUDA events on the launching stream, barrier +
             synchronize on both sides, max over ranks.
   e2e       same metric through the host-buffer C-ABI call acg_r1cs_check_host (pinned host CSR + witness
             -> H2D -> kernels -> D2H of the result), every step.
-  roofline  tiled check kernel: SURVEY 8(d) algorithmic bytes of the shard / average per-launch duration
-            (CUDA event pairs recorded around each launch inside the timed region) vs MEASURED_PEAKS.json.
+  roofline  tiled check kernel: SURVEY 8(d) algorithmic bytes of the shard / average per-launch duration (CUDA
+            event pairs around every 8th launch inside the timed region; bounded by the step time, a step being
+            exactly one launch) vs MEASURED_PEAKS.json.
   cpu_baseline / --impl reference
             the oracle's C restatement of the reference algorithm (oracle/r1cs_oracle.c, "port": the Haskell
             reference cannot be built in this image) on the host cores.
@@ -48,6 +50,8 @@ def parse_args():
     ap.add_argument("--field", default="bn254", choices=list(FIELD_IDS))
     ap.add_argument("--dense", action="store_true", help="all coefficients uniform (stress variant)")
     ap.add_argument("--kernel", default="tiled", choices=["tiled", "rowwise"])
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: all-reduce of the result pair over peer memory (default) or by NCCL")
     ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2, 3], help="tiled kernel geometry: rows per tile 128/256/64/32")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -222,7 +226,27 @@ def run_ours(args, rank, world, local_rank):
     result = torch.zeros(2, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream()
 
+    # the one exchange of the sharded check: the result pair, all-reduced over peer memory by the last CTA of the
+    # check kernel itself (NVLink P2P stores, include/acg.h) -- or, with --collective nccl, by one NCCL all-reduce
+    peer = None
+    collective = "none"
+    if world > 1:
+        collective = args.collective
+        if collective == "p2p":
+            try:
+                peer = sharding.connect_peers(ctx)
+            except Exception as e:  # no peer access between these GPUs: say so and use NCCL
+                sys.stderr.write("bench.py: peer exchange unavailable (%s); using NCCL\n" % (e,))
+                collective = "nccl"
+            ok = torch.tensor([1 if peer is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                peer, collective = None, "nccl"
+
     def step():
+        if peer is not None:
+            ctx.r1cs_check_async_allreduce(m, dw, peer, result.data_ptr(), stream.cuda_stream)
+            return
         ctx.r1cs_check_async(m, dw, result.data_ptr(), stream.cuda_stream)
         if world > 1:
             dist.all_reduce(result[0:1], op=dist.ReduceOp.SUM)
@@ -233,23 +257,35 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     assert int(result[0].item()) == 0, "honest witness must verify"
 
-    # ---- device-resident timed region
+    # ---- device-resident timed region.  One step is ONE kernel launch (the check kernel finalises its own result
+    # and, for N > 1, all-reduces it over peer memory in its last CTA), so consecutive steps run back to back.
+    # Per-launch durations are sampled with CUDA event pairs on the launching stream around every 8th step: an
+    # event pair around EVERY launch costs ~6 us of front-end time per step (measured), i.e. it would perturb the
+    # very number it measures.
     launches0 = ctx.kernel_launch_count()
-    ctx.profile_begin(args.steps)
+    sample_every = 8
+    pairs = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
     e0.record(stream)
-    for _ in range(args.steps):
-        step()
+    for i in range(args.steps):
+        if i % sample_every == sample_every // 2:
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(stream)
+            step()
+            eb.record(stream)
+            pairs.append((ea, eb))
+        else:
+            step()
     e1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     total_ms = e0.elapsed_time(e1)
-    kernel_ms = ctx.profile_end(args.steps)
+    kernel_ms = [a.elapsed_time(b) for a, b in pairs]
     launches = ctx.kernel_launch_count() - launches0
     assert int(result[0].item()) == 0
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -313,8 +349,13 @@ def run_ours(args, rank, world, local_rank):
                 traffic = (float(k2["dram__bytes_read.sum"]) + float(k2["dram__bytes_write.sum"])) * 1e6
             except Exception:
                 traffic = None
+        # average launch duration of the dominant kernel: the sampled event pairs (each pair adds ~3 us of event
+        # latency to what it brackets), bounded by the step time when a step is exactly one launch of that kernel
         k_ms = statistics.mean(kernel_ms) if kernel_ms else float("nan")
-        achieved = algo_bytes / (k_ms * 1e-3) / 1e9 if kernel_ms else None
+        one_launch_per_step = launches == args.steps
+        if one_launch_per_step and (not kernel_ms or total_ms / args.steps < k_ms):
+            k_ms = total_ms / args.steps
+        achieved = algo_bytes / (k_ms * 1e-3) / 1e9
         line = {
             "metric": "R1CS constraints/sec (BN254 Fr)" if field_id == 0 else "R1CS constraints/sec (BLS12-381 Fr)",
             "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -323,14 +364,20 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": workload_name(args, world), "kernel": args.kernel, "tiled_variant": args.variant,
                        "l2": "inputs streamed per step (%.0f MB CSR + %.0f MB witness per GPU) exceed the 126 MB L2; no explicit flush"
                              % ((algo_bytes - 32 * g.n_cols) / 1e6, 32 * g.n_cols / 1e6),
-                       "parallelism": "rows sharded over %d rank(s), 1 all-reduce(sum) of the violation count per step" % world,
+                       "parallelism": "rows sharded over %d rank(s), 1 all-reduce of the result pair per step (%s)" % (
+                           world, {"p2p": "fused: the check kernel's last CTA stores the pair into every peer's memory over NVLink (CUDA IPC) and reduces", "nccl": "NCCL",
+                                   "none": "single GPU: none"}[collective]),
                        "setup_s": {"generate": round(t_gen, 2)}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "k_r1cs_tiled" if args.kernel == "tiled" else "k_r1cs_rowwise",
                          "algorithmic_bytes_per_launch": algo_bytes, "device_stream_bytes_per_launch": m.stream_bytes + 32 * g.n_cols,
                          "kernel_ms_mean": k_ms,
-                         "kernel_ms_min": min(kernel_ms) if kernel_ms else None},
+                         "kernel_ms_sampled_mean": statistics.mean(kernel_ms) if kernel_ms else None,
+                         "kernel_ms_min": min(kernel_ms) if kernel_ms else None,
+                         "timing": "event pairs around every 8th launch (%d samples); kernel_ms_mean = min(sampled mean, "
+                                   "step time) because a step is exactly one launch of this kernel" % len(kernel_ms)
+                                   if one_launch_per_step else "event pairs around every 8th step (%d samples)" % len(kernel_ms)},
             "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "call": "acg_r1cs_check_host",
                     "witness_only_ms_per_step": 1e3 * e2e_w_s / e2e_steps},

@@ -141,6 +141,27 @@ int acg_r1cs_check_host(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const ac
 int acg_r1cs_eval(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* Aw, uint64_t* Bw,
                   uint64_t* Cw);
 
+/* ---- multi-GPU row shards: one process per GPU, each holding rows [row_begin, row_end) and the whole
+ * witness.  The only exchange is the {violation count, first bad row} pair; it travels over peer memory
+ * (NVLink / NVSwitch, CUDA IPC) instead of a collective library call:
+ *   1. every rank: acg_peer_create -> a 64-byte handle of its exchange buffer;
+ *   2. the caller all-gathers the handles (any transport; the Python binding uses torch.distributed);
+ *   3. every rank: acg_peer_connect with all `world` handles (rank order);
+ *   4. acg_r1cs_check_async_allreduce enqueues the shard's check; the last CTA of the check kernel to finish stores
+ *      this rank's pair into every peer's buffer (system-scope stores, release-ordered sequence number) and sums /
+ *      mins the world's pairs from its own buffer: d_result (device, 2 x uint64) then holds the GLOBAL count and
+ *      first bad row on every rank -- one kernel launch per check, no collective call.  All ranks must make the
+ *      call (like a collective).
+ *      A peer that does not arrive within ~4 s yields count = UINT64_MAX instead of a hang.
+ * world <= 8 (one NVSwitch node). */
+#define ACG_PEER_HANDLE_BYTES 64
+typedef struct acg_peer acg_peer;
+int acg_peer_create(acg_ctx* ctx, uint32_t world, uint32_t rank, acg_peer** out, uint8_t* handle_out);
+int acg_peer_connect(acg_ctx* ctx, acg_peer* p, const uint8_t* handles /* world * ACG_PEER_HANDLE_BYTES */);
+void acg_peer_free(acg_peer* p);
+int acg_r1cs_check_async_allreduce(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, acg_peer* peer,
+                                   uint64_t* d_result, void* stream);
+
 /* ---- NTT: replaces FFT.interpolate / the DFT of galois-fft (src/QAP.hs:521-523) -------------------
  * In place on 2^log_n canonical elements, natural order in and out.  inverse=0: out[i] = sum_j
  * in[j] w^(ij); inverse=1: the inverse (scaled by 1/n), w = getRootOfUnity log_n. */
