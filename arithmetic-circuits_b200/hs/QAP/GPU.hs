@@ -66,6 +66,19 @@ foreign import ccall safe "acg_qap_witness"     c_qap_witness
   :: Ptr AcgCtx -> Ptr AcgR1cs -> Ptr AcgVec -> Ptr Word64 -> Ptr Word64 -> Ptr Word64 -> Ptr Word64 -> Ptr Word64 -> Ptr CInt -> IO CInt
 foreign import ccall safe "acg_interpolate_columns" c_interpolate_columns
   :: Ptr AcgCtx -> Ptr Word64 -> CUInt -> CUInt -> IO CInt
+-- scale-and-sum over a per-wire QAP (foldQapSet / combineWithDefaults, src/QAP.hs:163-181, 314-324):
+-- polys (n_polys * len * 4 limbs), weights (n_polys * 4 limbs) -> out (len * 4 limbs)
+foreign import ccall safe "acg_poly_combine"    c_poly_combine
+  :: Ptr AcgCtx -> Ptr Word64 -> Ptr Word64 -> CUInt -> CUInt -> Ptr Word64 -> IO CInt
+-- witness generation on the device (K6): circuit handle from acg_circuit_parse (the word stream a
+-- `ArithCircuit Fr -> [Word64]` marshaller emits, include/acg.h), inputs as (index, limbs) pairs
+data AcgCircuit
+foreign import ccall safe "acg_circuit_parse"   c_circuit_parse   :: CInt -> Ptr Word64 -> Word64 -> Ptr (Ptr AcgCircuit) -> IO CInt
+foreign import ccall safe "acg_circuit_free"    c_circuit_free    :: Ptr AcgCircuit -> IO ()
+foreign import ccall safe "acg_generate_assignment_device" c_generate_assignment_device
+  :: Ptr AcgCtx -> Ptr AcgCircuit -> Ptr Word32 -> Ptr Word64 -> CUInt -> CUInt -> CUInt -> CUInt
+  -> Ptr (Ptr AcgVec) -> Ptr CUInt -> IO CInt
+foreign import ccall safe "acg_vec_download"    c_vec_download    :: Ptr AcgCtx -> Ptr AcgVec -> Ptr Word64 -> CUInt -> IO CInt
 
 -- | One context per device; the reference is single-threaded, so a process-wide context is enough.
 withAcg :: Int -> (Ptr AcgCtx -> IO a) -> IO a

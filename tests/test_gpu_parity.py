@@ -1,6 +1,7 @@
 """GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI (libacg.so);
 expected values come from the oracle (Python big-int / C), the committed golden vectors, or -- at
 BASELINE sizes -- size-independent properties.  Integer work: the bar is bit-exact."""
+import os
 import random
 
 import numpy as np
@@ -564,3 +565,19 @@ def test_lagrange_matches_reference_qap_build(acg, ctx_bn):
     polys, _ = ctx_bn.lagrange(xs, [ys], False)
     for i in (0, 1, 500, big_n - 1):
         assert O.p_eval(F, polys[0], xs[i]) == ys[i]
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU
+def test_peer_exchange_two_ranks():
+    """Row shards on two GPUs, result pair all-reduced over peer memory by the check kernel's last CTA: every rank
+    sees the oracle's global count / first bad row (tools/test_peer_exchange.py under torchrun).  Needs >= 2 GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29537",
+                        os.path.join(root, "tools", "test_peer_exchange.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "peer exchange ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
