@@ -32,6 +32,7 @@ PROTOTYPES = {
     "acg_ctx_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
     "acg_ctx_destroy": (None, [vp]),
     "acg_ctx_set_check_kernel": (C.c_int, [vp, C.c_int]),
+    "acg_ctx_set_overlap_checks": (C.c_int, [vp, C.c_int]),
     "acg_ctx_set_tiled_variant": (C.c_int, [vp, C.c_int]),
     "acg_r1cs_stream_bytes": (C.c_uint64, [vp]),
     "acg_last_timing": (C.c_int, [vp, C.POINTER(AcgTiming)]),

@@ -47,6 +47,14 @@ struct acg_ctx {
     // optional per-launch device timing of the main check kernel (acg_profile_*)
     std::vector<cudaEvent_t> prof_ev;  // pairs
     uint32_t prof_used = 0;
+    // overlap of consecutive checks (CheckEpilogue::overlap): allowed when the previous operation of this context
+    // was a single-launch tiled check of the same system and witness on the same stream
+    int overlap_checks = 1;
+    const void* last_m = nullptr;
+    const void* last_w = nullptr;
+    cudaStream_t last_stream = nullptr;
+    uint64_t last_check_op = 0;  // value of `ops` right after that check
+    uint64_t ops = 0;            // bumped by every entry point that enqueues device work
 };
 
 struct acg_r1cs {
@@ -162,6 +170,7 @@ int two_adicity(int field) { return field == 0 ? Bn254Fr::TWO_ADICITY : Bls12381
 int activate(acg_ctx* ctx) {
     if (!ctx) return ACG_ERR_BAD_ARG;
     ctx->err.clear();
+    ++ctx->ops;
     CU(ctx, cudaSetDevice(ctx->device));
     return ACG_OK;
 }
@@ -284,7 +293,7 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
 int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long long* d_result, fr_t* Aw, fr_t* Bw,
                   fr_t* Cw, cudaStream_t s, uint32_t* launches, acg_peer* peer = nullptr) {
     const uint32_t n_local = m->row_end - m->row_begin;
-    CheckEpilogue acc{ctx->d_accum, ctx->d_ticket, nullptr, PeerSlots{}, 0ull};  // accumulate only
+    CheckEpilogue acc{ctx->d_accum, ctx->d_ticket, nullptr, PeerSlots{}, 0ull, 0u};  // accumulate only
     CheckEpilogue fin = acc;                                                     // .. and finalise
     fin.out = d_result;
     if (peer) {
@@ -311,9 +320,21 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long 
             DevTileStream ts{m->d_stream, m->d_meta, m->d_far_cols, m->n_tiles, (uint32_t)m->variant,
                              (uint32_t)(m->blob_bytes / 16), m->n_cols};
             const bool last = m->long_ranges.empty();
+            // back-to-back checks of the same system and witness may overlap (see CheckEpilogue): every entry point
+            // bumps ctx->ops, so "the previous operation was that check" is ops == last_check_op + 1
+            const bool emit = Aw || Bw || Cw;
+            const bool chain = last && !emit && !prof && ctx->overlap_checks && ctx->last_m == m && ctx->last_w == w &&
+                               ctx->last_stream == s && ctx->ops == ctx->last_check_op + 1;
+            if (chain) fin.overlap = 1u;
             CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin, last ? fin : acc, Aw, Bw, Cw, ctx->sm_count, s));
             ++*launches;
             finalised = last;
+            if (last && !emit && !prof) {
+                ctx->last_m = m;
+                ctx->last_w = w;
+                ctx->last_stream = s;
+                ctx->last_check_op = ctx->ops;
+            }
         }
         if (prof) {
             CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], s));
@@ -449,6 +470,11 @@ int acg_ctx_set_check_kernel(acg_ctx* ctx, int which) {
     return ACG_OK;
 }
 
+int acg_ctx_set_overlap_checks(acg_ctx* ctx, int on) {
+    if (!ctx) return ACG_ERR_BAD_ARG;
+    ctx->overlap_checks = on ? 1 : 0;
+    return ACG_OK;
+}
 int acg_ctx_set_tiled_variant(acg_ctx* ctx, int variant) {
     if (!ctx || variant < 0 || variant >= kNumTileVariants) return ACG_ERR_BAD_ARG;
     ctx->tiled_variant = variant;
@@ -1101,7 +1127,7 @@ int acg_r1cs_check_host(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const ac
     if (*ctx->h_flag & 2) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_check_host: malformed CSR (rowptr / column index)");
     if (*ctx->h_flag & 1) return fail(ctx, ACG_ERR_NON_CANONICAL, "acg_r1cs_check_host: field element >= modulus");
     dev.tagged = 0;
-    const CheckEpilogue fin{ctx->d_accum, ctx->d_ticket, ctx->d_result, PeerSlots{}, 0ull};
+    const CheckEpilogue fin{ctx->d_accum, ctx->d_ticket, ctx->d_result, PeerSlots{}, 0ull, 0u};
     if (n_rows == 0) {
         CU(ctx, launch_init_result(ctx->d_result, s));
         ++launches;

@@ -124,6 +124,15 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) 
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
+// programmatic dependent launch (sm_90+): let the next kernel of the stream start launching / wait for the previous
+// kernel of the stream to have completed and flushed (both are no-ops for an ordinary launch)
+__device__ __forceinline__ void griddep_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t lane_id() {
     return threadIdx.x & 31u;
 }

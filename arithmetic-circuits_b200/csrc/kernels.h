@@ -154,12 +154,17 @@ struct PeerSlots {
 // last CTA to finish (ticket counter) reads the pair, resets scratch and ticket for the next check, all-reduces the
 // pair over peer memory when peers.world > 1 (see PeerSlots), and writes the final pair to `out`.  No separate
 // initialisation or reduction launch, no collective library call.
+// overlap != 0: the launch is a programmatic dependent of the previous check of the SAME system and witness on the
+// same stream (cudaLaunchAttributeProgrammaticStreamSerialization): its CTAs take the place of the previous check's
+// CTAs as those run out of tiles, and it waits for that check to complete (griddepcontrol.wait) only before it
+// touches the shared scratch pair -- consecutive checks overlap their tails, launch latency and cold starts.
 struct CheckEpilogue {
     unsigned long long* accum;
     unsigned int* ticket;
     unsigned long long* out;
     PeerSlots peers;
     unsigned long long seq;
+    uint32_t overlap;
 };
 // Publishes d_result[0..1] to every peer, waits for every peer's pair of step `seq`, leaves {sum of the counts,
 // min of the first bad rows} in d_result (count = ~0 if a peer did not arrive within ~4 s).

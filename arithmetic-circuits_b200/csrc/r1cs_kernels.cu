@@ -144,6 +144,7 @@ __global__ void k_peer_allreduce(PeerSlots ps, unsigned long long seq, unsigned 
 // End of a check kernel (every thread of every CTA calls it): see CheckEpilogue in kernels.h.
 __device__ __forceinline__ void finish_check(const CheckEpilogue& ep) {
     if (ep.out == nullptr) return;  // an earlier launch of the same check: it only accumulates
+    if (ep.overlap) griddep_wait();  // the previous check has finalised (and reset) the scratch pair
     __shared__ uint32_t s_last;
     __syncthreads();  // every warp of this CTA has reported
     if (threadIdx.x == 0) {
@@ -417,6 +418,8 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     __shared__ __align__(8) uint64_t full_bar;
     __shared__ unsigned long long ph[2][8];  // TIMING only: per-phase cycles seen by warp 0 and by the last warp
 
+    if (!ep.overlap) griddep_wait();   // (an overlapped launch reads only what the previous check also only read)
+    griddep_launch_dependents();       // the next check may move in as CTAs of this one exit
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const bool rec = TIMING && (tid == 0u || tid == C::kThreads - 32u);
@@ -545,7 +548,10 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
             bad = !fr_eq(fr_mul<P>(b, a), c);  // b (<= p) is the vector operand, a the limb-wise scalar
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, bad);
-        if (bal != 0u && lane == 0u) report_bad_rows(ep.accum, bal, row_base + h.row0 + (tid & ~31u));
+        if (bal != 0u && lane == 0u) {
+            if (ep.overlap) griddep_wait();  // the scratch pair belongs to the previous check until it completes
+            report_bad_rows(ep.accum, bal, row_base + h.row0 + (tid & ~31u));
+        }
         mark(4);
         if (tile + 1u == t_end) break;
         // blob and window were read (and the term array written) through the generic proxy; order that before
@@ -692,8 +698,17 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
             return cudaGetLastError();
         }
     }
-    k_r1cs_tiled<P, EMIT, V><<<grid, kTileGeom[V].threads, smem_bytes, s>>>(ts, w, row_base, ep, Aw, Bw, Cw);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTileGeom[V].threads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ep.overlap ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, k_r1cs_tiled<P, EMIT, V>, ts, w, row_base, ep, Aw, Bw, Cw);
 }
 
 cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w, uint64_t row_base,

@@ -395,6 +395,10 @@ class Context:
     def set_check_kernel(self, which: int):
         _check(_lib.lib().acg_ctx_set_check_kernel(self._h, which), self)
 
+    def set_overlap_checks(self, on: bool):
+        """Overlap of back-to-back checks of the same system and witness (include/acg.h); on by default."""
+        _check(_lib.lib().acg_ctx_set_overlap_checks(self._h, int(on)), self)
+
     def set_tiled_variant(self, variant: int):
         """Tile geometry for systems uploaded AFTER this call (0: 128-row tiles, 1: 256-row tiles)."""
         _check(_lib.lib().acg_ctx_set_tiled_variant(self._h, variant), self)

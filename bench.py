@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--field", default="bn254", choices=list(FIELD_IDS))
     ap.add_argument("--dense", action="store_true", help="all coefficients uniform (stress variant)")
     ap.add_argument("--kernel", default="tiled", choices=["tiled", "rowwise"])
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="do not overlap consecutive checks (programmatic dependent launch of the next check kernel)")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: all-reduce of the result pair over peer memory (default) or by NCCL")
     ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2, 3], help="tiled kernel geometry: rows per tile 128/256/64/32")
@@ -220,6 +222,7 @@ def run_ours(args, rank, world, local_rank):
     ctx = acg.Context(field_id, local_rank)
     ctx.set_check_kernel(acg.CHECK_TILED if args.kernel == "tiled" else acg.CHECK_ROWWISE)
     ctx.set_tiled_variant(args.variant)
+    ctx.set_overlap_checks(not args.no_overlap)
     m = ctx.upload_r1cs(g)
     dw = ctx.upload_witness(w)
     algo_bytes = m.algorithmic_bytes
@@ -362,6 +365,8 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u256 (8x32-bit-limb Montgomery Fr, integer)", "data": "synthetic",
             "config": {"workload": workload_name(args, world), "kernel": args.kernel, "tiled_variant": args.variant,
+                       "overlap": "consecutive checks overlap (next check kernel launched as a programmatic dependent)"
+                                  if not args.no_overlap else "off",
                        "l2": "inputs streamed per step (%.0f MB CSR + %.0f MB witness per GPU) exceed the 126 MB L2; no explicit flush"
                              % ((algo_bytes - 32 * g.n_cols) / 1e6, 32 * g.n_cols / 1e6),
                        "parallelism": "rows sharded over %d rank(s), 1 all-reduce of the result pair per step (%s)" % (

@@ -84,6 +84,13 @@ int acg_ctx_set_check_kernel(acg_ctx* ctx, int which);
 /* Tiled kernel tuning: tile geometry, bound to a system when it is uploaded.  0 = 128-row tiles (default),
  * 1 = 256, 2 = 64, 3 = 32 rows per tile. */
 int acg_ctx_set_tiled_variant(acg_ctx* ctx, int variant);
+/* Back-to-back checks (acg_r1cs_check*, tiled kernel) of the SAME system and witness on the same stream overlap by
+ * default: the later check is launched as a programmatic dependent of the earlier one, moves onto the SMs as the
+ * earlier one's CTAs run out of tiles, and waits for it only before it touches the shared result scratch.  The library
+ * tracks its own operations (any other call on the context between two checks disables the overlap for that pair).
+ * A caller that rewrites the witness through acg_vec_device_ptr with its own kernels between two checks must switch
+ * this off (on = 0). */
+int acg_ctx_set_overlap_checks(acg_ctx* ctx, int on);
 int acg_last_timing(const acg_ctx* ctx, acg_timing* out);
 /* Total launches of this library's kernels on this context since creation. */
 uint64_t acg_kernel_launch_count(const acg_ctx* ctx);
