@@ -2,7 +2,7 @@
 """Multi-GPU parity check of the peer-memory all-reduce (run under torchrun, one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \\
-        tools/test_peer_exchange.py
+        tests/peer_exchange_ranks.py
 
 Every rank checks its row shard of S(n) with acg_r1cs_check_async_allreduce and must see the GLOBAL violation count and
 first bad row that the C oracle computes for the whole system -- for the honest witness and for tampered ones whose
@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repository root (this file lives in tests/)
 sys.path.insert(0, ROOT)
 import arithmetic_circuits_b200 as acg  # noqa: E402
 from arithmetic_circuits_b200 import sharding  # noqa: E402

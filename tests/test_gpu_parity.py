@@ -570,7 +570,7 @@ def test_lagrange_matches_reference_qap_build(acg, ctx_bn):
 # ------------------------------------------------------------------------------------------------ multi-GPU
 def test_peer_exchange_two_ranks():
     """Row shards on two GPUs, result pair all-reduced over peer memory by the check kernel's last CTA: every rank
-    sees the oracle's global count / first bad row (tools/test_peer_exchange.py under torchrun).  Needs >= 2 GPUs."""
+    sees the oracle's global count / first bad row (tests/peer_exchange_ranks.py under torchrun).  Needs >= 2 GPUs."""
     import subprocess
     import sys
     import torch
@@ -579,5 +579,36 @@ def test_peer_exchange_two_ranks():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29537",
-                        os.path.join(root, "tools", "test_peer_exchange.py")], capture_output=True, text=True, timeout=600)
+                        os.path.join(root, "tests", "peer_exchange_ranks.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "peer exchange ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_overlapping_consecutive_checks(acg, ctx_bn):
+    """Back-to-back async checks of the same system and witness are launched as programmatic dependents of each other
+    (they overlap on the GPU and share one scratch result pair): every one of them must still deliver the oracle's
+    count and first bad row -- for a clean witness, for a tampered one (violation reports from overlapping launches),
+    after the witness changes in between (chain broken), and with the overlap switched off."""
+    import torch
+    n = 1 << 16
+    g, w = acg.synth_r1cs(0, n, 31337)
+    m, dw = ctx_bn.upload_r1cs(g), ctx_bn.upload_witness(w)
+    stream = torch.cuda.current_stream()
+    wb = w.copy()
+    for t in (1025 + 5, 1025 + n // 2, 1025 + n - 3):
+        wb[t, 1] ^= np.uint64(1 << 33)
+    ref = oracle_check(0, g, wb)
+    want_bad = (ref["n_violations"], ref["first_bad_row"])
+    assert want_bad[0] > 0
+    _select(acg, ctx_bn, "tiled", 0)
+    for overlap in (True, False):
+        ctx_bn.set_overlap_checks(overlap)
+        for witness, want in ((w, (0, -1)), (wb, want_bad), (w, (0, -1))):
+            dw.update(witness)
+            results = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(12)]
+            for r in results:   # no host synchronisation in between: launches 2..12 chain onto their predecessor
+                ctx_bn.r1cs_check_async(m, dw, r.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            got = {(int(r[0].item()), int(r[1].item())) for r in results}
+            assert got == {want}, (overlap, got, want)
+    ctx_bn.set_overlap_checks(True)
+    _reset(acg, ctx_bn)

@@ -6,6 +6,7 @@ G=gpurun_out; P=profiles
 cp $G/bench_ours.json $P/${R}_bench_ours.json
 cp $G/bench_reference.json $P/${R}_bench_reference.json
 cp $G/bench_ours_bls.json $P/${R}_bench_ours_bls12_381.json
+cp $G/bench_ours_no_overlap.json $P/${R}_bench_ours_no_overlap.json
 cp $G/bench_ours_21.json $P/${R}_bench_ours_2p21.json
 cp $G/bench_ours_22.json $P/${R}_bench_ours_2p22.json
 cp $G/bench_ours_dense.json $P/${R}_bench_ours_dense.json
