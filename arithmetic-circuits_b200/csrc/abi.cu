@@ -61,6 +61,7 @@ struct acg_r1cs {
     acg_ctx* ctx = nullptr;
     uint32_t n_rows_total = 0, n_cols = 0, row_begin = 0, row_end = 0;
     uint64_t nnz[3] = {0, 0, 0};
+    uint64_t distinct_cols = 0;  // witness columns referenced by the rows of this shard
     uint32_t* d_rowptr[3] = {nullptr, nullptr, nullptr};
     uint32_t* d_col[3] = {nullptr, nullptr, nullptr};
     fr_t* d_val[3] = {nullptr, nullptr, nullptr};
@@ -620,6 +621,19 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     acg_r1cs* m = new (std::nothrow) acg_r1cs();
     if (!m) return ACG_ERR_OOM;
     m->ctx = ctx;
+    {
+        std::vector<bool> seen(n_cols, false);
+        uint64_t distinct = 0;
+        for (int k = 0; k < 3; ++k)
+            for (uint32_t c : tagged_col[k]) {
+                const uint32_t col = c & kColMask;
+                if (!seen[col]) {
+                    seen[col] = true;
+                    ++distinct;
+                }
+            }
+        m->distinct_cols = distinct;
+    }
     m->n_rows_total = n_rows;
     m->n_cols = n_cols;
     m->row_begin = row_begin;
@@ -893,7 +907,7 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
 uint64_t acg_r1cs_algorithmic_bytes(const acg_r1cs* m) {
     if (!m) return 0;
     const uint64_t rows = m->row_end - m->row_begin;
-    uint64_t b = 32ull * m->n_cols + 8ull;
+    uint64_t b = 32ull * m->distinct_cols + 8ull;
     for (int k = 0; k < 3; ++k) b += m->nnz[k] * 36ull + 4ull * (rows + 1);
     return b;
 }

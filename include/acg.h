@@ -116,7 +116,9 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
                     const acg_csr* C, uint32_t row_begin, uint32_t row_end, acg_r1cs** out);
 void acg_r1cs_free(acg_r1cs* m);
 /* Algorithmic bytes one check of this (shard of the) system reads: SURVEY.md 8(d) formula
- * sum_M [nnz_M*(32+4) + 4*(rows+1)] + 32*n_cols + 8. */
+ * sum_M [nnz_M*(32+4) + 4*(rows+1)] + 32*(witness columns the rows reference) + 8.  For a whole system that is
+ * 32*n_cols (every wire occurs in some row); a row shard of a larger system is charged only the witness elements its
+ * own rows touch, not the whole replicated vector. */
 uint64_t acg_r1cs_algorithmic_bytes(const acg_r1cs* m);
 /* Bytes of the device-side tile stream the tiled kernel actually reads per check (columns as tagged words,
  * 16-bit row pointers, values of general coefficients only; +-1 coefficients are tags). */
