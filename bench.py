@@ -372,7 +372,7 @@ def run_ours(args, rank, world, local_rank):
                        "overlap": "consecutive checks overlap (next check kernel launched as a programmatic dependent)"
                                   if not args.no_overlap else "off",
                        "l2": "inputs streamed per step (%.0f MB CSR + %.0f MB witness per GPU) exceed the 126 MB L2; no explicit flush"
-                             % ((algo_bytes - 32 * g.n_cols) / 1e6, 32 * g.n_cols / 1e6),
+                             % ((sum(36 * k for k in g.nnz) + 12 * (g.n_rows + 1)) / 1e6, 32 * g.n_cols / 1e6),
                        "parallelism": "rows sharded over %d rank(s), 1 all-reduce of the result pair per step (%s)" % (
                            world, {"p2p": "fused: the check kernel's last CTA stores the pair into every peer's memory over NVLink (CUDA IPC) and reduces", "nccl": "NCCL",
                                    "none": "single GPU: none"}[collective]),
