@@ -8,26 +8,26 @@
 // Two kernels compute the same thing:
 //   k_r1cs_rowwise : thread per row, direct global loads.  Used for one-shot checks (no preprocessing)
 //                    and for rows too long to stage in shared memory.
-//   k_r1cs_tiled   : persistent CTAs over tiles of <= 128 (or 256) rows built at upload time.  Per tile:
-//                    (load) one thread issues TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) of
-//                           the tile's slices -- tagged columns and row pointers of A, B, C, the values
-//                           of the general-coefficient entries and their static index list -- into
-//                           shared memory; several CTAs per SM hide each other's load latency;
-//                           plus a second bulk copy of the tile's WITNESS WINDOW, the contiguous slice of
-//                           w most references of the tile fall into;
-//                           every term then lives in one shared-memory array of 32-byte slots
-//                           (window | far elements | products | zero);
-//                    (P1)   the tile's distinct references outside the window ("far") are gathered once,
-//                           one 256-bit load each, into the far slots;
-//                    (P2)   one lane per general entry: the 256-bit Montgomery product -- dense, no
-//                           divergence between coefficient kinds;
+//   k_r1cs_tiled   : persistent CTAs, each walking a contiguous run of the tiles (<= 128 / 256 / 64 / 32 rows) that
+//                    upload laid out as a stream of execution-ready blobs (kernels.h).  Per tile:
+//                    (load) two TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP): the blob and the tile's
+//                           WITNESS WINDOW, the contiguous slice of w most of its references fall into -- issued
+//                           the moment the previous tile is done, from L2 (prefetched a tile earlier); every term
+//                           then lives in one shared-memory array of 32-byte slots
+//                           (window | far buffer 0 | far buffer 1 | products | zero);
+//                    (far)  the distinct references outside the window were gathered during the previous tile
+//                           (16-byte cp.async copies into the far buffer of this tile's parity, from the column
+//                           list the previous blob carried); the gathers of the next tile start now;
+//                    (P2)   one lane per general entry off the constant wire: the 256-bit Montgomery product --
+//                           dense, no divergence between coefficient kinds;
 //                    (P3)   thread per row over the tile's ELL (slot-major, padded) entry words: the three
 //                           sums A.w, B.w, C.w advance together with warp-uniform control flow and touch
-//                           shared memory only (word = sign | term slot); then a*b == c.
-//                    The coefficient classification (+1 / -1 / general) lives in two tag bits of the
-//                    column word and is computed once at upload: the sparsity pattern is static, and the
-//                    32-byte encodings of +-1 never need to be re-read.  HBM traffic per check is one
-//                    pass over columns, row pointers and general values; the witness is gathered via L2.
+//                           shared memory only (word = sign | term address); then a*b == c.
+//                    The coefficient classification (+1 / -1 / general / general on the constant wire) is computed
+//                    once at upload: the sparsity pattern is static, and the 32-byte encodings of +-1 never need to
+//                    be re-read.  HBM traffic per check is one pass over the blobs; the witness is read via L2.
+// Both end with finish_check(): the last CTA of the last launch of a check finalises the result pair and, for row
+// shards on several GPUs, all-reduces it over peer memory (CheckEpilogue / PeerSlots in kernels.h).
 #include <cstdio>
 #include <cstdlib>
 
@@ -244,9 +244,6 @@ __global__ void k_validate_csr(const uint32_t* __restrict__ rowptr, const uint32
 // ------------------------------------------------------------------------------------------------
 // tiled kernel
 // ------------------------------------------------------------------------------------------------
-#ifndef ACG_K2_ILP2
-#define ACG_K2_ILP2 0
-#endif
 namespace tiled {
 constexpr uint32_t align_up(uint32_t x, uint32_t a) {
     return (x + a - 1) / a * a;
@@ -497,24 +494,8 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
 
         // ---- P2: dense 256-bit Montgomery products, one general entry per lane (no divergence between
         //          coefficient kinds): product slot <- coefficient * operand slot
-#if ACG_K2_ILP2
-        //          a lane that has two entries interleaves the two products (fr_mul2)
-        for (uint32_t j = tid; j < h.n_general; j += 2u * C::kThreads) {
-            const uint32_t j1 = j + C::kThreads;
-            if (j1 < h.n_general) {
-                fr_t r0, r1;
-                fr_mul2<P>(r0, r1, load_fr16(gval + (size_t)j * 32u), load_term(smem4, gop[j]),
-                           load_fr16(gval + (size_t)j1 * 32u), load_term(smem4, gop[j1]));
-                store_term(terms, C::kProd0 + j, r0);
-                store_term(terms, C::kProd0 + j1, r1);
-            } else {
-                store_term(terms, C::kProd0 + j, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), load_term(smem4, gop[j])));
-            }
-        }
-#else
         for (uint32_t j = tid; j < h.n_general; j += C::kThreads)
             store_term(terms, C::kProd0 + j, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), load_term(smem4, gop[j])));
-#endif
         if (!w0_is_one) {  // not a witness of the reference: coefficient * w[0] in place, inside the blob
             const fr_t w0 = ld_witness(w);
             for (uint32_t j = h.n_general + tid; j < h.n_general + h.n_const; j += C::kThreads)
