@@ -10,6 +10,7 @@ echo "=== bench reference arm"; timeout 900 python bench.py --impl reference --s
 echo "=== bench ours"; timeout 900 python bench.py 2>&1 | tail -1 | tee gpurun_out/bench_ours.json | cut -c1-1800
 echo "=== bench ours bls"; timeout 900 python bench.py --field bls12_381 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_ours_bls.json | cut -c1-300
 echo "=== bench ours (no overlap)"; timeout 900 python bench.py --no-overlap --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_ours_no_overlap.json | cut -c1-300
+for v in 1 2 3; do echo "=== bench ours variant $v"; timeout 600 python bench.py --variant $v --no-cpu-baseline --e2e-steps 1 2>&1 | tail -1 | tee gpurun_out/bench_ours_variant$v.json | cut -c1-120; done
 echo "=== bench ours 2^21"; timeout 900 python bench.py --log-rows 21 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_ours_21.json | cut -c1-300
 echo "=== bench ours 2^22"; timeout 900 python bench.py --log-rows 22 --steps 50 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_ours_22.json | cut -c1-300
 echo "=== bench ours dense"; timeout 900 python bench.py --dense --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_ours_dense.json | cut -c1-300
