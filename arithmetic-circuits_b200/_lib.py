@@ -55,6 +55,7 @@ PROTOTYPES = {
     "acg_peer_free": (None, [vp]),
     "acg_r1cs_check_async_allreduce": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "acg_poly_combine": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp]),
+    "acg_circuit_plan_stats": (C.c_int, [vp, u32p, u32p]),
     "acg_vec_download": (C.c_int, [vp, vp, vp, C.c_uint32]),
     "acg_generate_assignment_device": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                                  C.POINTER(vp), u32p]),

@@ -548,6 +548,16 @@ int acg_generate_assignment(const acg_circuit* c, const uint32_t* input_ix, cons
 }
 void acg_assignment_free(acg_assignment* a) { delete a; }
 
+int acg_circuit_plan_stats(const acg_circuit* c, uint32_t* n_levels, uint32_t* max_width) {
+    if (!c) return ACG_ERR_BAD_ARG;
+    acg::host::GatePlan plan;
+    const int rc = acg::host::build_gate_plan(c, 0, 0, 0, plan);
+    if (rc != ACG_OK) return rc;
+    if (n_levels) *n_levels = plan.level_ptr.empty() ? 0u : (uint32_t)plan.level_ptr.size() - 1u;
+    if (max_width) *max_width = plan.max_width;
+    return ACG_OK;
+}
+
 int acg_assignment_dims(const acg_assignment* a, uint32_t* n_in, uint32_t* n_mid, uint32_t* n_out) {
     if (!a) return ACG_ERR_BAD_ARG;
     uint32_t* outs[3] = {n_in, n_mid, n_out};

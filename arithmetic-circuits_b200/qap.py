@@ -205,6 +205,13 @@ class ArithCircuit:
     def num_roots(self) -> int:
         return _lib.lib().acg_circuit_num_roots(self._h)
 
+    def plan_stats(self) -> Tuple[int, int]:
+        """(dependency levels, widest level) of the device witness generation; raises AcgError(-6) for a gate list that
+        is not in single-assignment, define-before-use form."""
+        a, b = C.c_uint32(), C.c_uint32()
+        _check(_lib.lib().acg_circuit_plan_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def valid(self) -> bool:
         """validArithCircuit (src/Circuit/Arithmetic.hs:158-185)."""
         return bool(_lib.lib().acg_circuit_valid(self._h))

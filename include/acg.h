@@ -284,6 +284,9 @@ const uint64_t* acg_r1cs_host_roots(const acg_r1cs_host* m);
 int acg_generate_assignment_device(acg_ctx* ctx, const acg_circuit* c, const uint32_t* input_ix,
                                    const uint64_t* input_vals, uint32_t n_inputs, uint32_t n_in, uint32_t n_mid,
                                    uint32_t n_out, acg_vec** out, uint32_t* n_levels);
+/* Host-only: the dependency levels acg_generate_assignment_device would use (number of levels = barriers, widest
+ * level).  ACG_ERR_UNSUPPORTED / ACG_ERR_BAD_ARG exactly when the device entry point would refuse the circuit. */
+int acg_circuit_plan_stats(const acg_circuit* c, uint32_t* n_levels, uint32_t* max_width);
 /* Copy a device vector back as canonical limbs (n must equal acg_vec_len). */
 int acg_vec_download(acg_ctx* ctx, const acg_vec* v, uint64_t* out, uint32_t n);
 

@@ -60,6 +60,20 @@ def main():
         ctx.r1cs_check_async_allreduce(m, dw, peer, result.data_ptr(), stream.cuda_stream)
     torch.cuda.synchronize()
     assert (int(result[0].item()), int(result[1].item())) == (0, -1)
+    # a system with fewer rows than ranks: the ranks with an empty shard launch no check kernel but still take part
+    n_tiny = max(1, world - 1)
+    g_t, w_t = acg.synth_r1cs(0, n_tiny, 99)
+    rb, re = sharding.row_shard(n_tiny, world, rank)
+    m_t, dw_t = ctx.upload_r1cs(g_t, rb, re), ctx.upload_witness(w_t)
+    mats_t = [(x[0], x[1], x[2]) for x in g_t.mats]
+    wt_bad = w_t.copy()
+    wt_bad[1025, 0] ^= np.uint64(2)   # the first gate's output
+    for wc in (w_t, wt_bad, w_t):
+        ref = CO.r1cs_eval_check(0, n_tiny, g_t.n_cols, *mats_t, wc, False, 1)
+        dw_t.update(wc)
+        ctx.r1cs_check_async_allreduce(m_t, dw_t, peer, result.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        assert (int(result[0].item()), int(result[1].item())) == (ref["n_violations"], ref["first_bad_row"]), rank
     dist.barrier()
     if rank == 0:
         print("peer exchange ok: world=%d, %d cases, global count / first bad row == oracle == NCCL path" % (world, 3 * len(cases)))

@@ -172,3 +172,29 @@ def test_synth_statistics(acg):
     wire = cols != 0
     assert 0.45 < is_one[wire].mean() < 0.55 and 0.2 < is_m1[wire].mean() < 0.3
     assert g.mats[2][1].tolist() == list(range(1025, 1025 + n))
+
+
+def test_gate_plan_levels(acg):
+    """Levelisation behind the device witness generation (host side of K6): the KAT-1 circuit has two levels (two
+    independent products, then the gate that reads both), an unsplit chain adds one level per stage, and gate lists
+    that are not single-assignment / define-before-use are refused."""
+    c = _kat(acg)
+    assert c.plan_stats() == (2, 2)
+    mids = [acg.IntermediateWire(i) for i in range(8)]
+    sp = acg.ArithCircuit(0, [acg.Split(acg.InputWire(0), mids),
+                              acg.Mul(acg.ConstGate(1), acg.unsplit(mids), acg.OutputWire(0)),
+                              acg.Equal(acg.OutputWire(0), acg.IntermediateWire(8), acg.OutputWire(1))])
+    assert sp.plan_stats() == (3, 1)
+    twice = acg.ArithCircuit(0, [acg.Mul(acg.Var(acg.InputWire(0)), acg.Var(acg.InputWire(1)), acg.IntermediateWire(0)),
+                                 acg.Mul(acg.Var(acg.InputWire(0)), acg.Var(acg.InputWire(0)), acg.IntermediateWire(0))])
+    with pytest.raises(acg.AcgError) as e:
+        twice.plan_stats()
+    assert e.value.code == -6
+    early = acg.ArithCircuit(0, [acg.Mul(acg.Var(acg.IntermediateWire(1)), acg.Var(acg.InputWire(1)), acg.IntermediateWire(0)),
+                                 acg.Mul(acg.Var(acg.InputWire(0)), acg.Var(acg.InputWire(0)), acg.IntermediateWire(1))])
+    with pytest.raises(acg.AcgError) as e:
+        early.plan_stats()
+    assert e.value.code == -6
+    circuit, _inputs = acg.synth_circuit(0, 2000, 5)
+    levels, width = circuit.plan_stats()
+    assert 1 <= levels <= 2000 and width >= 1
