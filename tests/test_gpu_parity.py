@@ -281,7 +281,7 @@ def test_synth_parity_small(acg, ctxs, fid, n, seed, dense):
     assert ref["n_violations"] == 0
     m, dw = ctx.upload_r1cs(g), ctx.upload_witness(w)
     distinct = len(np.unique(np.concatenate([x[1] for x in g.mats])))
-    assert distinct <= g.n_cols and (n < 4096 or distinct == g.n_cols)
+    assert distinct <= g.n_cols
     assert m.algorithmic_bytes == sum(36 * k for k in g.nnz) + 3 * 4 * (n + 1) + 32 * distinct + 8
     for kernel, stages in KERNELS:
         _select(acg, ctx, kernel, stages)
