@@ -1,7 +1,10 @@
 """Multi-GPU row sharding of the R1CS check: one process per GPU (torch.distributed),
-rows split in contiguous blocks, witness replicated, and ONE all-reduce (sum) of the per-shard
-violated-row count.  The first violated row index needs a second (min) reduction, issued only when the
-count is non-zero.  No other data-path collective exists: the NTT / QAP build stays single-GPU."""
+rows split in contiguous blocks, witness replicated, and ONE all-reduce of the per-shard result pair
+{violated-row count, first violated row}.  connect_peers() sets up the exchange over peer memory that the
+check kernel performs itself (include/acg.h "multi-GPU row shards"); reduce_check_result() is the plain
+collective form of the same reduction (sum, then min only when the count is non-zero) for backends without
+peer access -- it is also what the CPU tests run over gloo.  No other data-path collective exists: the NTT /
+QAP build stays single-GPU."""
 from __future__ import annotations
 
 from typing import Optional, Sequence, Tuple

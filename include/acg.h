@@ -120,8 +120,9 @@ void acg_r1cs_free(acg_r1cs* m);
  * 32*n_cols (every wire occurs in some row); a row shard of a larger system is charged only the witness elements its
  * own rows touch, not the whole replicated vector. */
 uint64_t acg_r1cs_algorithmic_bytes(const acg_r1cs* m);
-/* Bytes of the device-side tile stream the tiled kernel actually reads per check (columns as tagged words,
- * 16-bit row pointers, values of general coefficients only; +-1 coefficients are tags). */
+/* Bytes of the device-side tile stream the tiled kernel actually reads per check besides the witness (per tile: a
+ * header, one 32-bit word per ELL slot, the far witness columns, and the values of the general coefficients only;
+ * +-1 coefficients are sign bits of the words). */
 uint64_t acg_r1cs_stream_bytes(const acg_r1cs* m);
 
 /* w: n_cols canonical elements in qapSetToMap order (src/QAP.hs:605-620). */
@@ -137,9 +138,10 @@ void* acg_vec_device_ptr(acg_vec* v);
  * GLOBAL row index, or UINT64_MAX when valid.  valid <=> *n_violations == 0  (verifyAssignment). */
 int acg_r1cs_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* n_violations,
                    uint64_t* first_bad_row);
-/* Enqueue only: d_result points to 2 device uint64 {n_violations, first_bad_row}; the kernel sequence
- * zero-initialises them itself.  Used to all-reduce the residual count across row shards (NCCL) and
- * to time the kernels with CUDA events on `stream`. */
+/* Enqueue only: d_result points to 2 device uint64 {n_violations, first_bad_row}, written by the last CTA of the
+ * check (no initialisation needed).  For timing the kernels with CUDA events on `stream`, for back-to-back checks
+ * (see acg_ctx_set_overlap_checks) and for callers that reduce the pair across row shards themselves
+ * (acg_r1cs_check_async_allreduce does it inside the kernel). */
 int acg_r1cs_check_async(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* d_result,
                          void* stream);
 /* One-shot from host buffers (upload + check + read-back): the end-to-end call a Haskell wrapper of
