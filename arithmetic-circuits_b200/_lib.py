@@ -47,6 +47,7 @@ PROTOTYPES = {
     "acg_r1cs_algorithmic_bytes": (C.c_uint64, [vp]),
     "acg_witness_upload": (C.c_int, [vp, vp, C.c_uint32, C.POINTER(vp)]),
     "acg_witness_update": (C.c_int, [vp, vp, vp, C.c_uint32]),
+    "acg_witness_update_range": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32]),
     "acg_vec_free": (None, [vp]),
     "acg_vec_len": (C.c_uint32, [vp]),
     "acg_vec_device_ptr": (vp, [vp]),

@@ -936,6 +936,21 @@ int acg_witness_update(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t n_c
     return ACG_OK;
 }
 
+int acg_witness_update_range(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t first, uint32_t count) {
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!v || v->ctx != ctx || (count && !w) || first > v->n || count > v->n - first)
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_witness_update_range: bad argument");
+    if (count == 0) return ACG_OK;
+    CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = upload_canonical(ctx, v->d + first, w, count);
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(ctx, cudaEventSynchronize(ctx->ev[1]));
+    ctx->timing = acg_timing{elapsed(ctx->ev[0], ctx->ev[1]), 0.f, 0.f, 1, 0};
+    return ACG_OK;
+}
+
 int acg_witness_upload(acg_ctx* ctx, const uint64_t* w, uint32_t n_cols, acg_vec** out) {
     int rc = activate(ctx);
     if (rc) return rc;

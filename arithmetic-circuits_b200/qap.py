@@ -600,6 +600,23 @@ class DeviceVec:
     def device_ptr(self) -> int:
         return _lib.lib().acg_vec_device_ptr(self._h)
 
+    def update_range(self, w_slice: np.ndarray, first: int):
+        """Overwrite elements [first, first + len(w_slice)) from host memory (canonical limbs)."""
+        w_slice = np.ascontiguousarray(w_slice, np.uint64).reshape(-1, 4)
+        _check(_lib.lib().acg_witness_update_range(self.ctx._h, self._h, _ptr(w_slice), first, len(w_slice)), self.ctx)
+
+    def as_torch_bytes(self):
+        """A torch uint8 tensor aliasing the device storage (Montgomery form, 32 bytes per element) -- for
+        device-to-device exchange with torch.distributed.  The DeviceVec must outlive the tensor."""
+        import torch
+
+        class _Alias:
+            pass
+        a = _Alias()
+        a.__cuda_array_interface__ = {"shape": (len(self) * 32,), "typestr": "|u1", "data": (int(self.device_ptr), False),
+                                      "version": 2}
+        return torch.as_tensor(a, device="cuda")
+
     def download(self) -> np.ndarray:
         """The vector as canonical limbs, shape (n, 4)."""
         out = np.zeros((len(self), 4), np.uint64)

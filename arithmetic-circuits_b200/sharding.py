@@ -58,6 +58,24 @@ def connect_peers(ctx, group=None):
     return PeerExchange(ctx, world, rank, all_gather_bytes)
 
 
+def upload_witness_sliced(dw, w_host: np.ndarray, group=None, dw_bytes=None):
+    """New witness for every rank of a row-sharded check, without every rank pulling the whole vector over PCIe:
+    rank r uploads the r-th contiguous slice of `w_host` (canonical limbs, the same array on every rank) into its own
+    device vector over its own PCIe link (range check + Montgomery conversion on the device), then the slices travel
+    device to device -- one broadcast per rank over NVLink (NCCL).  dw_bytes: cached dw.as_torch_bytes()."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = len(dw)
+    t = dw_bytes if dw_bytes is not None else dw.as_torch_bytes()
+    lo, hi = row_shard(n, world, rank)
+    dw.update_range(w_host[lo:hi], lo)
+    for r in range(world):
+        a, b = row_shard(n, world, r)
+        if b > a:
+            dist.broadcast(t[a * 32:b * 32], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+
+
 def reduce_check_result(result, group=None):
     """result: int64 tensor [n_violations, first_bad_row] (first_bad_row = -1, i.e. UINT64_MAX, when the
     shard is clean), on the device of the process group's backend.  Returns (total violations, first bad

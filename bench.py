@@ -341,8 +341,27 @@ def run_ours(args, rank, world, local_rank):
     # the end-to-end step of a prover: the circuit (the R1CS) is resident on the device -- as the reference keeps its QAP
     # value in memory between calls of verifyAssignment -- and every step brings a new witness from pinned host memory
     # (H2D + canonical-range check + Montgomery conversion), checks it and reads the result pair back (D2H).
+    # N > 1: every rank uploads only its slice of the new witness over its own PCIe link and the slices are exchanged
+    # over NVLink (sharding.upload_witness_sliced); falls back to a full upload per rank if that is unavailable
+    sliced = world > 1
+    dw_bytes = None
+    if sliced:
+        try:
+            dw_bytes = dw.as_torch_bytes()
+            sharding.upload_witness_sliced(dw, wp.reshape(-1, 4), None, dw_bytes)
+            torch.cuda.synchronize()
+        except Exception as e:
+            sys.stderr.write("bench.py: sliced witness upload unavailable (%s); every rank uploads the whole witness\n" % (e,))
+            sliced = False
+        ok = torch.tensor([1 if sliced else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        sliced = bool(int(ok.item()))
+
     def e2e_witness_step():
-        dw.update(wp)
+        if sliced:
+            sharding.upload_witness_sliced(dw, wp.reshape(-1, 4), None, dw_bytes)
+        else:
+            dw.update(wp)
         if peer is not None:
             ctx.r1cs_check_async_allreduce(m, dw, peer, result.data_ptr(), stream.cuda_stream)
             return int(result[0].item())
@@ -417,7 +436,10 @@ def run_ours(args, rank, world, local_rank):
                                    "kernel_ms_sampled_mean / frac_isolated_launch = event pairs around every 8th launch "
                                    "(%d samples), which serialise that launch and add ~3 us of event latency" % len(kernel_ms)
                                    if one_launch_per_step else "event pairs around every 8th step (%d samples)" % len(kernel_ms)},
-            "e2e": {"value": e2e_w_value, "unit": "constraints/s", "h2d_bytes_per_step": int(wp.nbytes), "d2h_bytes_per_step": 16,
+            "e2e": {"value": e2e_w_value, "unit": "constraints/s",
+                    "h2d_bytes_per_step": int(wp.nbytes) // world if sliced else int(wp.nbytes), "d2h_bytes_per_step": 16,
+                    "witness_upload": ("each rank uploads 1/%d of the witness over its own PCIe link, slices exchanged over "
+                                       "NVLink (one NCCL broadcast per rank)" % world) if sliced else "whole witness per rank",
                     "steps": e2e_w_steps, "ms_per_step": 1e3 * e2e_w_s / e2e_w_steps,
                     "call": "acg_witness_update (new witness from pinned host memory) + acg_r1cs_check against the system "
                             "resident on the device -- the reference, too, keeps its QAP value in memory between calls",

@@ -129,6 +129,10 @@ uint64_t acg_r1cs_stream_bytes(const acg_r1cs* m);
 int acg_witness_upload(acg_ctx* ctx, const uint64_t* w, uint32_t n_cols, acg_vec** out);
 /* Overwrite an existing device witness from host memory (same length). */
 int acg_witness_update(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t n_cols);
+/* Overwrite elements [first, first + count) only.  With row shards on several GPUs every rank uploads its own slice
+ * of a new witness over its own PCIe link and the slices are then exchanged device to device over NVLink
+ * (sharding.upload_witness_sliced), instead of every rank pulling the whole vector from the host. */
+int acg_witness_update_range(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t first, uint32_t count);
 void acg_vec_free(acg_vec* v);
 uint32_t acg_vec_len(const acg_vec* v);
 /* Raw device pointer of the vector's storage (Montgomery form), for zero-copy interop. */

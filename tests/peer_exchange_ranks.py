@@ -60,6 +60,15 @@ def main():
         ctx.r1cs_check_async_allreduce(m, dw, peer, result.data_ptr(), stream.cuda_stream)
     torch.cuda.synchronize()
     assert (int(result[0].item()), int(result[1].item())) == (0, -1)
+    # sliced witness upload: every rank uploads 1/world of the witness, the slices travel device to device
+    dw_bytes = dw.as_torch_bytes()
+    for wc in (cases[1], w, cases[3]):
+        ref = CO.r1cs_eval_check(0, n, g_all.n_cols, *mats, wc, False, 4)
+        sharding.upload_witness_sliced(dw, wc, None, dw_bytes)
+        ctx.r1cs_check_async_allreduce(m, dw, peer, result.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        assert (int(result[0].item()), int(result[1].item())) == (ref["n_violations"], ref["first_bad_row"]), rank
+        assert (dw.download() == wc).all()
     # a system with fewer rows than ranks: the ranks with an empty shard launch no check kernel but still take part
     n_tiny = max(1, world - 1)
     g_t, w_t = acg.synth_r1cs(0, n_tiny, 99)
