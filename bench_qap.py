@@ -148,6 +148,27 @@ def main():
         print(json.dumps({"what": "cpu_oracle", "field": args.field, "log_n": args.log_n, "threads": th,
                           "intt_ms": t_ntt * 1e3, "qap_witness_ms": t_qap * 1e3, "h_bit_exact_vs_gpu": same}), flush=True)
         assert same and okc
+        # the reference-SHAPED divisibility check (schoolbook product of a and b, long division by the
+        # target, as poly/semirings do it for verificationWitnessZk, src/QAP.hs:325-327) on small systems: the O(n^2)
+        # wall next to the NTT path's h of the same system on the GPU.  Single thread, like the reference.
+        for small_log in (8, 10, 12):
+            ns = 1 << small_log
+            gs, ws = acg.synth_r1cs(fid, ns, 20260003)
+            ms_, dws = ctx.upload_r1cs(gs), ctx.upload_witness(ws)
+            t0 = time.perf_counter()
+            bufs_s, ok_s = ctx.qap_witness(ms_, dws, want=("a", "b", "c", "h"))
+            t_gpu = time.perf_counter() - t0
+            a_, b_, c_ = (acg.strip(acg.from_limbs(bufs_s[k])) for k in ("a", "b", "c"))
+            r_mod = acg.field_constants(fid)["modulus"]
+            target = [r_mod - 1] + [0] * (ns - 1) + [1]
+            t0 = time.perf_counter()
+            q_, rem_, zero_ = CO.poly_mul_divmod_check(fid, a_, b_, c_, target)
+            t_ref = time.perf_counter() - t0
+            same_s = zero_ and ok_s and acg.strip(q_) == acg.strip(acg.from_limbs(bufs_s["h"]))
+            print(json.dumps({"what": "reference_shaped_divisibility_check", "field": args.field, "n": ns,
+                              "cpu_schoolbook_product_and_long_division_ms": t_ref * 1e3, "threads": 1,
+                              "gpu_qap_witness_call_wall_ms": t_gpu * 1e3, "h_equal": bool(same_s)}), flush=True)
+            assert same_s
 
 
 if __name__ == "__main__":
