@@ -20,6 +20,14 @@
 #define ACG_HD inline
 #endif
 
+// BN254 Fr's p0 = 2^32 - 2^28 + 1 lets m * p0 be built from shifts (see mont_round).  Measured on B200 (round 1, twice):
+// one IMAD.WIDE less per round, but SLOWER everywhere -- K1 ceiling 65.2 vs 66.9 Gproducts/s, tiled check 61.1 vs
+// 59.6 us, 2^22-point NTT 1.03 vs 0.96 ms: the six dependent ALU operations sit on the cross-round critical path.
+// Kept behind this switch (off) so the measurement can be repeated.
+#ifndef ACG_BN254_P0_SHIFTS
+#define ACG_BN254_P0_SHIFTS 0
+#endif
+
 namespace acg {
 
 #include "fr_constants.inc"
@@ -271,8 +279,8 @@ ACG_HD void mont_round(uint32_t nev[9], uint32_t nod[8], const uint32_t ev[9], c
 
     // m = -T * p^-1 mod 2^32.  BLS12-381 Fr has p0 = 1, p1 = 2^32 - 1 and -p^-1 = -1 (mod 2^32): m and the
     // products m*p0, m*p1 then come from adds on the ALU pipe instead of the quarter-rate 32x32->64 multiplier
-    // (measured +4% on the tiled check).  The analogous rewrite for BN254 Fr (p0 = 2^32 - 2^28 + 1) was
-    // measured 5% SLOWER: four dependent ALU operations replace one multiply on the cross-round critical path.
+    // (measured +4% on the tiled check).  The analogous rewrite for BN254 Fr (p0 = 2^32 - 2^28 + 1) is slower:
+    // see ACG_BN254_P0_SHIFTS at the top of this file.
     uint32_t m;
     if constexpr (P::NINV32 == 0xffffffffu)
         m = 0u - nev[0];
@@ -298,6 +306,17 @@ ACG_HD void mont_round(uint32_t nev[9], uint32_t nod[8], const uint32_t ev[9], c
     if constexpr (P::p(0) == 1u) {  // m * 1: the low word cancels nev[0] (carry iff nev[0] != 0)
         nev[0] = ptx::add_cc(nev[0], m);
         nev[1] = ptx::addc_cc(nev[1], 0u);
+#if ACG_BN254_P0_SHIFTS
+    } else if constexpr (P::p(0) == 0xf0000001u) {
+        // BN254 Fr: p0 = 2^32 - 2^28 + 1, so m * p0 = (m << 32) - (m << 28) + m needs no multiplier:
+        //   low word  = m - (m << 28)            (mod 2^32, borrow b)
+        //   high word = m - (m >> 4) - b
+        // One quarter-rate IMAD.WIDE less per round (8 of 136 per product) for six ALU operations.
+        const uint32_t lo = ptx::sub_cc(m, m << 28);
+        const uint32_t hi = ptx::subc(m, m >> 4);
+        nev[0] = ptx::add_cc(nev[0], lo);   // == 0
+        nev[1] = ptx::addc_cc(nev[1], hi);
+#endif
     } else {
         nev[0] = ptx::mad_lo_cc(P::p(0), m, nev[0]);   // == 0
         nev[1] = ptx::madc_hi_cc(P::p(0), m, nev[1]);
