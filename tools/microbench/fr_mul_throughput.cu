@@ -8,7 +8,7 @@
 #include "fr.cuh"
 using namespace acg;
 
-template <class P, int CHAINS>
+template <class P, int CHAINS, bool KARA = false>
 __global__ void k_chain(fr_t* out, int iters, unsigned long long* cycles) {
     fr_t x[CHAINS], y;
     for (int i = 0; i < 8; ++i) y.l[i] = 0x1234567u * (threadIdx.x + 3) + i;
@@ -23,7 +23,7 @@ __global__ void k_chain(fr_t* out, int iters, unsigned long long* cycles) {
             fr_mul2<P>(x[0], x[1], x[0], y, x[1], y);
         } else {
 #pragma unroll
-            for (int c = 0; c < CHAINS; ++c) x[c] = fr_mul<P>(x[c], y);
+            for (int c = 0; c < CHAINS; ++c) x[c] = KARA ? fr_mul_karatsuba<P>(x[c], y) : fr_mul<P>(x[c], y);
         }
     }
     const long long t1 = clock64();
@@ -33,7 +33,7 @@ __global__ void k_chain(fr_t* out, int iters, unsigned long long* cycles) {
     if (threadIdx.x == 0) atomicMax(cycles, (unsigned long long)(t1 - t0));
 }
 
-template <int CHAINS>
+template <int CHAINS, bool KARA = false>
 void run(int warps_per_sm, int sms) {
     const int iters = 2000;
     const int threads = 32 * warps_per_sm;
@@ -45,10 +45,10 @@ void run(int warps_per_sm, int sms) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    k_chain<Bn254Fr, CHAINS><<<sms, threads>>>(out, 10, cyc);
+    k_chain<Bn254Fr, CHAINS, KARA><<<sms, threads>>>(out, 10, cyc);
     cudaMemset(cyc, 0, 8);
     cudaEventRecord(e0);
-    k_chain<Bn254Fr, CHAINS><<<sms, threads>>>(out, iters, cyc);
+    k_chain<Bn254Fr, CHAINS, KARA><<<sms, threads>>>(out, iters, cyc);
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms;
@@ -57,9 +57,9 @@ void run(int warps_per_sm, int sms) {
     cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
     const double prods_per_sm = (double)iters * CHAINS * threads;
     const double ppc = prods_per_sm / (double)c;
-    printf("chains=%d warps/SM=%2d: %.1f cycles per product per warp, %.3f products/cycle/SM, %.2f Gprod/s (chip), "
+    printf("%schains=%d warps/SM=%2d: %.1f cycles per product per warp, %.3f products/cycle/SM, %.2f Gprod/s (chip), "
            "floor for 2.5*2^20 products: %.1f us  [%s]\n",
-           CHAINS, warps_per_sm, (double)c / (iters * CHAINS), ppc, prods_per_sm * sms / (ms * 1e6),
+           KARA ? "karatsuba " : "", CHAINS, warps_per_sm, (double)c / (iters * CHAINS), ppc, prods_per_sm * sms / (ms * 1e6),
            2.5 * 1048576.0 / (prods_per_sm * sms / (ms * 1e-3)) * 1e6, cudaGetErrorString(cudaGetLastError()));
     cudaFree(out);
     cudaFree(cyc);
@@ -72,5 +72,6 @@ int main() {
     for (int w : {1, 2, 4, 8, 12, 16, 20, 24, 32}) run<1>(w, p.multiProcessorCount);
     for (int w : {4, 8, 12, 16, 20}) run<2>(w, p.multiProcessorCount);
     for (int w : {4, 8, 16}) run<4>(w, p.multiProcessorCount);
+    for (int w : {1, 4, 8, 12, 16, 20, 32}) run<1, true>(w, p.multiProcessorCount);
     return 0;
 }
