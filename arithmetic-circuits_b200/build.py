@@ -22,7 +22,7 @@ CPP_SOURCES = ["host/circuit.cpp", "host/synth.cpp"]
 HEADERS = ["fr.cuh", "fr_constants.inc", "dev.cuh", "kernels.h", "host/fr_host.hpp", "host/circuit.hpp",
            "../../include/acg.h"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"] + os.environ.get("ACG_NVCC_EXTRA", "").split()
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"] + os.environ.get("ACG_NVCC_EXTRA", "").split()
 
 
 def _newer(target: str, deps) -> bool:
@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("libacg build failed")
     if force or procs or _newer(OUT, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-cudart", "static"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-cudart", "static", "-lpthread"]
         subprocess.check_call(cmd)
     return OUT
 

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "../../../include/acg.h"
@@ -308,11 +309,12 @@ struct RowSink {
     }
 };
 
-// gateToGenQAP, src/QAP.hs:366-474, emitted row by row
+// gateToGenQAP, src/QAP.hs:366-474, emitted row by row for the gates [g0, g1)
 template <class P>
-int lower_impl(const acg_circuit* c, const Layout& lay, RowSink& sink) {
+int lower_range(const acg_circuit* c, const Layout& lay, size_t g0, size_t g1, RowSink& sink) {
     const El one = Fr<P>::one(), m1 = Fr<P>::minus_one(), zero = Fr<P>::zero();
-    for (const GateH& g : c->gates) {
+    for (size_t gi = g0; gi < g1; ++gi) {
+        const GateH& g = c->gates[gi];
         if (g.kind == G_MUL) {  // :371-395
             Row A, B, C;
             affine_to_row<P>(g.l, lay, A);
@@ -357,6 +359,55 @@ int lower_impl(const acg_circuit* c, const Layout& lay, RowSink& sink) {
                 row_set(C2, 0, zero); row_set(C2, oc, zero);
                 sink.push<P>(0, A2); sink.push<P>(1, B2); sink.push<P>(2, C2);
             }
+        }
+    }
+    return ACG_OK;
+}
+
+// Worker threads of the host-side lowering: ACG_HOST_THREADS, else the hardware concurrency (at most 64).
+unsigned host_threads() {
+    if (const char* e = std::getenv("ACG_HOST_THREADS")) {
+        const long v = std::strtol(e, nullptr, 10);
+        if (v >= 1) return (unsigned)std::min<long>(v, 256);
+    }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(hc ? hc : 1u, 64u));
+}
+
+// The gates lower independently (a gate's rows depend on the gate and the layout only), so contiguous chunks of the
+// gate list are lowered by worker threads into private sinks and concatenated in order: the result is identical to
+// the sequential pass (at 2^24 gates the lowering, not the check, is what a caller waits for).
+template <class P>
+int lower_impl(const acg_circuit* c, const Layout& lay, RowSink& sink) {
+    const size_t n = c->gates.size();
+    const size_t T = std::min<size_t>(host_threads(), n / 2048 + 1);
+    if (T <= 1) return lower_range<P>(c, lay, 0, n, sink);
+    std::vector<RowSink> parts(T);
+    std::vector<int> rcs(T, ACG_OK);
+    std::vector<std::thread> workers;
+    workers.reserve(T);
+    for (size_t t = 0; t < T; ++t)
+        workers.emplace_back([&, t]() { rcs[t] = lower_range<P>(c, lay, n * t / T, n * (t + 1) / T, parts[t]); });
+    for (auto& w : workers) w.join();
+    for (int rc : rcs)
+        if (rc != ACG_OK) return rc;
+    for (int k = 0; k < 3; ++k) {
+        size_t rows = 0, nnz = 0;
+        for (const RowSink& p : parts) {
+            rows += p.rowptr[k].size() - 1;
+            nnz += p.col[k].size();
+        }
+        if (nnz > 0xFFFFFFF0ull) return ACG_ERR_UNSUPPORTED;
+        sink.rowptr[k].reserve(rows + 1);
+        sink.col[k].reserve(nnz);
+        sink.val[k].reserve(4 * nnz);
+        for (RowSink& p : parts) {
+            const uint32_t base = (uint32_t)sink.col[k].size();
+            for (size_t r = 1; r < p.rowptr[k].size(); ++r) sink.rowptr[k].push_back(base + p.rowptr[k][r]);
+            sink.col[k].insert(sink.col[k].end(), p.col[k].begin(), p.col[k].end());
+            sink.val[k].insert(sink.val[k].end(), p.val[k].begin(), p.val[k].end());
+            std::vector<uint32_t>().swap(p.col[k]);
+            std::vector<uint64_t>().swap(p.val[k]);
         }
     }
     return ACG_OK;

@@ -198,3 +198,36 @@ def test_gate_plan_levels(acg):
     circuit, _inputs = acg.synth_circuit(0, 2000, 5)
     levels, width = circuit.plan_stats()
     assert 1 <= levels <= 2000 and width >= 1
+
+
+def test_parallel_lowering_is_deterministic(acg, monkeypatch):
+    """arithCircuitToGenQAP in C++ lowers chunks of the gate list on worker threads (ACG_HOST_THREADS); the CSR is
+    identical for every thread count, including gates that emit several rows (Equal, Split) at chunk borders."""
+    rnd = random.Random(3)
+    gates = []
+    mid = 0
+    for i in range(9000):
+        k = rnd.random()
+        if k < 0.8 or mid < 3:
+            gates.append(acg.Mul(acg.Add(acg.ConstGate(rnd.randrange(1 << 200)), acg.Var(acg.InputWire(i % 5))),
+                                 acg.ScalarMul(rnd.randrange(1 << 100), acg.Var(acg.InputWire((i * 7) % 5))),
+                                 acg.IntermediateWire(mid)))
+            mid += 1
+        elif k < 0.9:
+            gates.append(acg.Equal(acg.IntermediateWire(mid - 1), acg.IntermediateWire(mid), acg.IntermediateWire(mid + 1)))
+            mid += 2
+        else:
+            outs = [acg.IntermediateWire(mid + j) for j in range(6)]
+            gates.append(acg.Split(acg.IntermediateWire(mid - 2), outs))
+            mid += 6
+    c = acg.ArithCircuit(0, gates)
+    ref = None
+    for th in ("1", "2", "3", "7", "32"):
+        monkeypatch.setenv("ACG_HOST_THREADS", th)
+        g = acg.arith_circuit_to_gen_qap(c, None, 1)
+        assert g.n_rows == c.num_roots
+        snap = [tuple(np.array(a, copy=True) for a in m) for m in g.mats]
+        if ref is None:
+            ref = snap
+        else:
+            assert all((a == b).all() for ma, mb in zip(ref, snap) for a, b in zip(ma, mb)), th
