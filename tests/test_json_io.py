@@ -78,3 +78,31 @@ def test_qap_encoding_strips_trailing_zeros():
     assert j["qapTarget"] == [R_BN - 504, 191, R_BN - 24, 1]
     l2, r2, o2, t2 = J.qap_from_json(json.loads(J.dumps(j)))
     assert l2 == ([1], {0: [0, 5]}, {}, {0: []}) and t2 == [R_BN - 504, 191, R_BN - 24, 1]
+
+
+def test_json_round_trip_random_circuits(acg):
+    """Property: circuit -> aeson JSON text -> circuit is the identity on the marshalled word stream, for random
+    Mul / Equal / Split circuits with random affine trees and residues of any size below r."""
+    from hypothesis import given, settings, strategies as st
+
+    wires = st.one_of(st.builds(acg.InputWire, st.integers(0, 40)), st.builds(acg.IntermediateWire, st.integers(0, 40)),
+                      st.builds(acg.OutputWire, st.integers(0, 40)))
+    elems = st.integers(0, R_BN - 1)
+    affine = st.recursive(st.one_of(st.builds(acg.Var, wires), st.builds(acg.ConstGate, elems)),
+                          lambda inner: st.one_of(st.builds(acg.Add, inner, inner), st.builds(acg.ScalarMul, elems, inner)),
+                          max_leaves=6)
+    gate = st.one_of(st.builds(acg.Mul, affine, affine, wires), st.builds(acg.Equal, wires, wires, wires),
+                     st.builds(acg.Split, wires, st.lists(wires, min_size=1, max_size=5)))
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(gate, min_size=1, max_size=8))
+    def check(gates):
+        text = J.dumps(J.circuit_to_json(gates))
+        back = [J.gate_from_json(g) for g in J.loads(text)]
+        assert back == [tuple(g) if not isinstance(g, tuple) else g for g in gates] or \
+            J.dumps(J.circuit_to_json(back)) == text
+        a = acg.ArithCircuit(acg.BN254_FR, gates)
+        b = acg.ArithCircuit(acg.BN254_FR, back)
+        assert (a.words == b.words).all()
+
+    check()
