@@ -193,7 +193,7 @@ class ArithCircuit:
         return self
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:  # (_lib is None while the interpreter shuts down)
             _lib.lib().acg_circuit_free(self._h)
             self._h = None
 
@@ -233,7 +233,7 @@ class QapSet:
         self._h = handle
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             _lib.lib().acg_assignment_free(self._h)
             self._h = None
 
@@ -303,7 +303,7 @@ class _HostR1cs:
         self._h = h
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             _lib.lib().acg_r1cs_host_free(self._h)
             self._h = None
 
@@ -391,7 +391,8 @@ class Context:
             self._h = None
 
     def __del__(self):
-        self.close()
+        if _lib is not None:
+            self.close()
 
     def __enter__(self):
         return self
@@ -556,7 +557,8 @@ class PeerExchange:
         self._h = None
 
     def __del__(self):
-        self.free()
+        if _lib is not None:
+            self.free()
 
 
 class DeviceR1cs:
@@ -570,7 +572,8 @@ class DeviceR1cs:
         self._h = None
 
     def __del__(self):
-        self.free()
+        if _lib is not None:
+            self.free()
 
     @property
     def algorithmic_bytes(self) -> int:
@@ -591,7 +594,8 @@ class DeviceVec:
         self._h = None
 
     def __del__(self):
-        self.free()
+        if _lib is not None:
+            self.free()
 
     def __len__(self):
         return _lib.lib().acg_vec_len(self._h)
