@@ -770,9 +770,21 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
         const uint32_t win_lo = ft.win_lo, win_n = ft.win_n;
         const uint32_t* far_b = far_all.data() + ft.far_off;
         const uint32_t* far_e = far_b + ft.n_far;
-        auto slot_of = [&](uint32_t c) -> uint32_t {  // witness column -> term slot
-            if (c >= win_lo && c - win_lo < win_n) return c - win_lo;
-            return tile_far_slot0(geom, (uint32_t)ti) + (uint32_t)(std::lower_bound(far_b, far_e, c) - far_b);
+        // chunk (16-byte unit from the start of shared memory) of the low half of a term slot / of the 32-byte value
+        // j of a blob section; the window is written by a linear bulk copy and stays in natural order (kernels.h)
+        const uint32_t term_base16 = tile_terms_offset(geom) / 16u;
+        auto term_chunk = [&](uint32_t slot, bool in_window) -> uint32_t {
+            const uint32_t c = term_base16 + 2u * slot;
+            return (geom.swizzle && !in_window) ? swz16(c) : c;
+        };
+        auto blob_chunk = [&](uint32_t off, uint32_t j) -> uint32_t {
+            const uint32_t c = off / 16u + 2u * j;
+            return geom.swizzle ? swz16(c) : c;
+        };
+        auto chunk_of = [&](uint32_t c) -> uint32_t {  // witness column -> chunk of its term
+            if (c >= win_lo && c - win_lo < win_n) return term_chunk(c - win_lo, true);
+            return term_chunk(tile_far_slot0(geom, (uint32_t)ti) + (uint32_t)(std::lower_bound(far_b, far_e, c) - far_b),
+                              false);
         };
         align16();
         const size_t base = stream.size();
@@ -814,24 +826,24 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
         h.off_next_far = up(h.off_words + (t.width[0] + t.width[1] + t.width[2]) * t.nrows * 4u, 16);
         h.off_gop = up(h.off_next_far + h.next_n_far * 4u, 16);
         h.off_gval = up(h.off_gop + n_prod * 2u, 32);
-        const uint32_t term_base = tile_terms_offset(geom) / 32u;  // 32-byte units from the start of shared memory
         // entry words, slot-major
         for (int k = 0; k < 3; ++k)
             for (uint32_t j = 0; j < t.width[k]; ++j)
                 for (uint32_t r = 0; r < t.nrows; ++r) {
                     const uint32_t s0 = local_rp[k][t.row0 + r], s1 = local_rp[k][t.row0 + r + 1];
                     if (s0 + j >= s1) {
-                        put32(term_base + kZero);
+                        put32(term_chunk(kZero, false));
                         continue;
                     }
                     const uint32_t word = tagged_col[k][s0 + j];
                     const uint32_t tag = word >> 30;
                     if (tag == kTagGeneral) {
                         const int32_t g = gid[k][s0 + j - t.e0[k]];
-                        put32(g >= 0 ? term_base + kProd0 + (uint32_t)g
-                                     : h.off_gval / 32u + n_prod + (uint32_t)(~g));
+                        put32(g >= 0 ? (geom.prod_in_place ? blob_chunk(h.off_gval, (uint32_t)g)
+                                                           : term_chunk(kProd0 + (uint32_t)g, false))
+                                     : blob_chunk(h.off_gval, n_prod + (uint32_t)(~g)));
                     } else {
-                        put32((tag == kTagMinusOne ? kTermSign : 0u) | (term_base + slot_of(word & kColMask)));
+                        put32((tag == kTagMinusOne ? kTermSign : 0u) | chunk_of(word & kColMask));
                     }
                 }
         stream.resize(base + h.off_next_far, 0);
@@ -840,8 +852,7 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
         for (int k = 0; k < 3; ++k)
             for (uint32_t e = 0; e < t.ne[k]; ++e) {
                 const uint32_t word = tagged_col[k][t.e0[k] + e];
-                if ((word >> 30) == kTagGeneral && gid[k][e] >= 0)
-                    put16((uint16_t)(term_base + slot_of(word & kColMask)));
+                if ((word >> 30) == kTagGeneral && gid[k][e] >= 0) put16((uint16_t)chunk_of(word & kColMask));
             }
         stream.resize(base + h.off_gval + (size_t)(n_prod + n_const) * 32u, 0);
         for (int k = 0; k < 3; ++k) {
@@ -850,9 +861,12 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
             for (uint32_t e = 0; e < t.ne[k]; ++e)
                 if ((tagged_col[k][t.e0[k] + e] >> 30) == kTagGeneral) {
                     const int32_t g = gid[k][e];
-                    const size_t at = base + h.off_gval + (size_t)(g >= 0 ? (uint32_t)g : n_prod + (uint32_t)(~g)) * 32u;
-                    gval_offs.push_back((uint32_t)(at / 16));
-                    std::memcpy(stream.data() + at, M->val + 4ull * (g0 + t.e0[k] + e), 32);
+                    const uint32_t lo = blob_chunk(h.off_gval, g >= 0 ? (uint32_t)g : n_prod + (uint32_t)(~g));
+                    const uint64_t* v = M->val + 4ull * (g0 + t.e0[k] + e);
+                    std::memcpy(stream.data() + base + (size_t)lo * 16u, v, 16);
+                    std::memcpy(stream.data() + base + (size_t)(lo ^ 1u) * 16u, v + 2, 16);
+                    // (the conversion kernel finds the high half before / after the low one: bit 31)
+                    gval_offs.push_back((uint32_t)(base / 16 + lo) | ((lo & 1u) ? 0x80000000u : 0u));
                 }
         }
         align16();
@@ -868,7 +882,7 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     const uint32_t n_tiles_out = (uint32_t)metas.size();
     std::sort(m->long_ranges.begin(), m->long_ranges.end());
     align16();
-    if (stream.size() / 16 > 0xFFFFFFF0ull) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_r1cs_upload: tile stream too large");
+    if (stream.size() / 16 > 0x7FFFFFF0ull) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_r1cs_upload: tile stream too large");
     m->n_tiles = n_tiles_out;
     // what one check streams from HBM besides the witness: blobs, tile records, far column lists
     m->blob_bytes = stream.size();

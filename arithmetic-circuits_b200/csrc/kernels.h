@@ -40,9 +40,10 @@ struct DevR1cs {
 //     [.., + max_gen)                     products coefficient * operand of the general-coefficient entries
 //     last slot                           zero (padding)
 // Blob = header | entry words in ELL (slot-major) order: for matrix A, then B, then C, for slot
-// j < width[k], for row r < nrows: one 32-bit word = sign<<31 | term address in 32-byte units from the start
-// of shared memory (coefficient -1 sets the sign; general entries point at their product slot, padding at the
-// zero slot) | u32 far witness columns of the next tile | u16 operand addresses of the general entries | their
+// j < width[k], for row r < nrows: one 32-bit word = sign<<31 | chunk (16-byte unit from the start of shared
+// memory) of the term's low half, see swz16 below (coefficient -1 sets the sign; general entries point at their
+// product slot, padding at the zero slot) | u32 far witness columns of the next tile | u16 operand chunks of the
+// general entries | their
 // coefficient values (Montgomery; 32-byte aligned in shared memory), followed by the coefficient values of
 // the general entries ON COLUMN 0.  Column 0 is the constant wire of the reference (w[0] = 1 by construction:
 // initialQapSet, src/QAP.hs:591-595; qapSetToMap puts it at index 0, :605-620), so coefficient * w[0] is the
@@ -83,17 +84,36 @@ struct TileGeometry {
     uint32_t window;     // witness elements staged per tile
     uint32_t max_far;    // distinct witness columns outside the window per tile
     uint32_t max_const;  // general-coefficient entries per tile on column 0 (the constant wire)
+    uint32_t swizzle;    // 1: 16-byte halves of every term outside the witness window are XOR-swizzled (swz16)
+    uint32_t far_bufs;   // 2: far slots double-buffered by tile parity (gathers of tile i + 1 run under tile i);
+                         // 1: one far buffer, gathered between two tiles (smaller footprint, one more resident CTA)
+    uint32_t prod_in_place;  // 1: a product overwrites its coefficient inside the blob (no separate product slots)
+    uint32_t reg_budget; // registers per thread the kernel is compiled for (bounds the resident CTAs per SM)
 };
 constexpr uint32_t kMaxEllWidth = 8;
-constexpr int kNumTileVariants = 4;
+constexpr int kNumTileVariants = 8;
 constexpr TileGeometry kTileGeom[kNumTileVariants] = {
-    {128, 10, 160, 192, 288, 96}, {256, 10, 320, 320, 576, 192}, {64, 10, 96, 128, 160, 64}, {32, 10, 64, 96, 96, 32}};
+    {128, 10, 160, 192, 288, 96, 1, 2, 0, 96}, {256, 10, 320, 320, 576, 192, 1, 2, 0, 96},
+    {64, 10, 96, 128, 160, 64, 1, 2, 0, 96},   {32, 10, 64, 96, 96, 32, 1, 2, 0, 96},
+    {128, 10, 160, 192, 288, 96, 0, 2, 0, 96}, {64, 10, 96, 128, 160, 64, 0, 2, 0, 96},
+    {128, 10, 160, 192, 288, 96, 1, 2, 1, 96}, {128, 10, 160, 192, 288, 96, 1, 1, 1, 85}};
+// Shared memory is addressed in 16-byte CHUNKS from the start of the CTA's dynamic shared memory.  A term (32 bytes)
+// occupies the two chunks of one 32-byte unit; an entry word names the chunk that holds its LOW half and the high
+// half is the other chunk of the unit (word ^ 1).  Eight lanes of a 128-bit shared-memory access are served per
+// wavefront from 8 bank groups of 16 bytes; with the low half always in the even chunk, the low-half loads of a warp
+// can only ever use 4 of them (two-way conflicts even for consecutive terms).  swz16 swaps the halves in every other
+// 128-byte row, which spreads both loads over all 8 groups.  The witness window is written by a linear TMA bulk copy
+// and stays in natural order; everything the kernel or the upload writes (far terms, products, coefficient values)
+// is swizzled.
+ACG_HD constexpr uint32_t swz16(uint32_t chunk) {
+    return chunk ^ ((chunk >> 3) & 1u);
+}
 constexpr uint32_t tile_blob_capacity(const TileGeometry& g) {
     return 64u + g.threads * g.max_slots * 4u + g.max_far * 4u + ((g.max_gen * 2u + 15u) / 16u) * 16u + 16u +
            (g.max_gen + g.max_const) * 32u;
 }
 // shared-memory offset of the term array (the blob sits at offset 0); entry words and operand words address
-// 32-byte units from the start of shared memory, so that a word can also point INTO the blob (see below)
+// 16-byte chunks from the start of shared memory, so that a word can also point INTO the blob (see below)
 constexpr uint32_t tile_terms_offset(const TileGeometry& g) {
     return (tile_blob_capacity(g) + 127u) / 128u * 128u;
 }
@@ -102,13 +122,13 @@ constexpr uint32_t kFarPerThread = 3;
 // the far slots are double-buffered by tile parity: tile i uses far buffer (i & 1), so the far witness
 // elements of tile i + 1 are gathered (cp.async) while tile i computes
 constexpr uint32_t tile_term_slots(const TileGeometry& g) {
-    return g.window + 2u * g.max_far + g.max_gen + 1u;
+    return g.window + g.far_bufs * g.max_far + (g.prod_in_place ? 0u : g.max_gen) + 1u;
 }
 constexpr uint32_t tile_far_slot0(const TileGeometry& g, uint32_t tile) {
-    return g.window + (tile & 1u) * g.max_far;
+    return g.window + (g.far_bufs == 2u ? (tile & 1u) * g.max_far : 0u);
 }
 constexpr uint32_t tile_prod_slot0(const TileGeometry& g) {
-    return g.window + 2u * g.max_far;
+    return g.window + g.far_bufs * g.max_far;
 }
 
 struct alignas(32) TileMeta {
@@ -121,13 +141,13 @@ struct alignas(32) TileMeta {
     uint32_t pad[2];
 };
 // resident CTAs of the tiled kernel per SM: bounded by shared memory (227 KB, 1 KB per CTA reserved), by the
-// register budget of 96 per thread and by the hardware limit of 32
+// register budget per thread (TileGeometry::reg_budget) and by the hardware limit of 32
 constexpr uint32_t tile_smem_bytes(const TileGeometry& g) {
     return tile_terms_offset(g) + tile_term_slots(g) * 32u;
 }
 constexpr uint32_t tile_ctas_per_sm(const TileGeometry& g) {
     const uint32_t by_smem = (227u * 1024u) / (tile_smem_bytes(g) + 1024u + 64u);
-    const uint32_t by_regs = 65536u / (g.threads * 96u);
+    const uint32_t by_regs = 65536u / (g.threads * g.reg_budget);
     const uint32_t m = by_smem < by_regs ? by_smem : by_regs;
     return m > 32u ? 32u : m;
 }
@@ -234,6 +254,14 @@ cudaError_t launch_axpy2(int field, fr_t* h, const fr_t* a, const fr_t* b, fr_t 
 // out[i] = sum_k weight[k] * polys[k * len + i]
 cudaError_t launch_poly_combine(int field, const fr_t* polys, const fr_t* weight, uint32_t n_polys, uint64_t len,
                                 fr_t* out, cudaStream_t s);
+
+// K7 (poly_kernels.cu): v[i] += s * t[i];  *d_flag |= 1 if any v[i] != 0;  exact division by the target:
+// p (len_p coefficients, destroyed: p[0..n) ends as the remainder) by T (n + 1 coefficients, T[n] != 0,
+// lc_inv = 1 / T[n], monic: T[n] == 1) -> h (len_p - n quotient coefficients).  Requires len_p > n.
+cudaError_t launch_axpy1(int field, fr_t* v, const fr_t* t, fr_t s, uint64_t n, cudaStream_t st);
+cudaError_t launch_any_nonzero(const fr_t* v, uint64_t n, int* d_flag, cudaStream_t s);
+cudaError_t launch_poly_divmod(int field, fr_t* p, uint32_t len_p, const fr_t* T, uint32_t n, fr_t lc_inv, bool monic,
+                               fr_t* h, cudaStream_t s, uint32_t* launches);
 
 // Lagrange (K5): n <= 4096 distinct xs (Montgomery), n_polys value vectors -> coefficient vectors;
 // target: n+1 coefficients of prod (X - x_i) (may be null).  d_status: set to 1 if two xs coincide.

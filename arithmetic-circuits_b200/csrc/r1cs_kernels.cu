@@ -28,8 +28,10 @@
 //                    be re-read.  HBM traffic per check is one pass over the blobs; the witness is read via L2.
 // Both end with finish_check(): the last CTA of the last launch of a check finalises the result pair and, for row
 // shards on several GPUs, all-reduces it over peer memory (CheckEpilogue / PeerSlots in kernels.h).
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "dev.cuh"
 #include "kernels.h"
@@ -260,25 +262,32 @@ struct Cfg {
     static constexpr uint32_t kOffTerms = tile_terms_offset(kTileGeom[V]);
     static constexpr uint32_t kBytes = tile_smem_bytes(kTileGeom[V]);
     static constexpr uint32_t kCtasPerSm = tile_ctas_per_sm(kTileGeom[V]);
+    static constexpr bool kSwizzle = kTileGeom[V].swizzle != 0;
+    static constexpr bool kFarDouble = kTileGeom[V].far_bufs == 2u;
+    static constexpr bool kProdInPlace = kTileGeom[V].prod_in_place != 0;
+    // chunk (16-byte unit from the start of shared memory) of the low half of term slot `slot` outside the window
+    static __device__ __forceinline__ uint32_t term_chunk(uint32_t slot) {
+        const uint32_t c = kOffTerms / 16u + 2u * slot;
+        return kSwizzle ? swz16(c) : c;
+    }
+    // .. and of the 32-byte value `j` of a blob section that starts `off` bytes (a multiple of 32) into the blob
+    static __device__ __forceinline__ uint32_t blob_chunk(uint32_t off, uint32_t j) {
+        const uint32_t c = off / 16u + 2u * j;
+        return kSwizzle ? swz16(c) : c;
+    }
 };
 
-__device__ __forceinline__ fr_t load_term(const uint4* terms, uint32_t slot) {
-    const uint4 a = terms[2u * slot], b = terms[2u * slot + 1u];
+// a term by the chunk of its low half (kernels.h swz16): the high half is the other chunk of the 32-byte unit
+__device__ __forceinline__ fr_t load_term(const uint4* smem16, uint32_t chunk) {
+    const uint4 a = smem16[chunk], b = smem16[chunk ^ 1u];
     fr_t r;
     r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
 }
-__device__ __forceinline__ void store_term(uint4* terms, uint32_t slot, const fr_t& v) {
-    terms[2u * slot] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-    terms[2u * slot + 1u] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
-}
-__device__ __forceinline__ fr_t load_fr16(const uint8_t* p) {  // 16-byte aligned shared-memory element
-    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);
-    fr_t r;
-    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
-    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
-    return r;
+__device__ __forceinline__ void store_term(uint4* smem16, uint32_t chunk, const fr_t& v) {
+    smem16[chunk] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    smem16[chunk ^ 1u] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 // p - x without the zero fix-up: the result is in (0, p] and only ever feeds fr_add, which accepts it
 template <class P>
@@ -397,6 +406,14 @@ __device__ __forceinline__ fr_t canonical(fr_t x) {
 
 // phase cycle counters of the TIMING instantiation (a measurement aid: ACG_TILED_TIMING=1)
 __device__ unsigned long long g_tiled_phase_cycles[2][8];
+// .. and per-CTA wall-clock marks (globaltimer, ns): kernel entry, first tile staged, last tile done, exit
+constexpr uint32_t kMaxTimedCtas = 2048;
+__device__ unsigned long long g_tiled_cta_marks[kMaxTimedCtas][6];  // [4] = SM id, [5] = tiles of the CTA
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // One CTA walks a contiguous run of tiles.  While tile i computes:
 //   * its far witness elements are already in the far buffer (i & 1): they were gathered with 16-byte cp.async
@@ -415,6 +432,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     __shared__ __align__(8) uint64_t full_bar;
     __shared__ unsigned long long ph[2][8];  // TIMING only: per-phase cycles seen by warp 0 and by the last warp
 
+    if (TIMING && threadIdx.x == 0 && blockIdx.x < kMaxTimedCtas) g_tiled_cta_marks[blockIdx.x][0] = globaltimer_ns();
     if (!ep.overlap) griddep_wait();   // (an overlapped launch reads only what the previous check also only read)
     griddep_launch_dependents();       // the next check may move in as CTAs of this one exit
     const uint32_t tid = threadIdx.x;
@@ -431,8 +449,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     };
     if (TIMING && tid < 16u) ph[tid >> 3][tid & 7u] = 0ull;
     uint8_t* blob = smem;
-    uint4* terms = reinterpret_cast<uint4*>(smem + C::kOffTerms);
-    const uint4* smem4 = reinterpret_cast<const uint4*>(smem);  // entry / operand words address 32-byte units from here
+    uint4* smem4 = reinterpret_cast<uint4*>(smem);  // entry / operand words address 16-byte chunks from here
     // this CTA's run of tiles
     const uint32_t t_begin = (uint32_t)((uint64_t)blockIdx.x * ts.n_tiles / gridDim.x);
     const uint32_t t_end = (uint32_t)((uint64_t)(blockIdx.x + 1u) * ts.n_tiles / gridDim.x);
@@ -448,14 +465,15 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     // start the gather of this thread's far witness elements of tile `tile` (far slot f = tid + k * threads)
     // from the column list `cols`
     auto gather_far_async = [&](uint32_t tile, uint32_t n_far, const uint32_t* cols) {
-        uint4* dst = terms + 2u * (C::kFar0 + (tile & 1u) * C::kFarN);
+        const uint32_t far0 = C::kFar0 + (C::kFarDouble ? (tile & 1u) * C::kFarN : 0u);
 #pragma unroll
         for (uint32_t k = 0; k < kFarPerThread; ++k) {
             const uint32_t f = tid + k * C::kThreads;
             if (f < n_far) {
                 const uint4* src = reinterpret_cast<const uint4*>(w + cols[f]);
-                cp_async16(dst + 2u * f, src);
-                cp_async16(dst + 2u * f + 1u, src + 1);
+                const uint32_t c = C::term_chunk(far0 + f);
+                cp_async16(smem4 + c, src);
+                cp_async16(smem4 + (c ^ 1u), src + 1);
             }
         }
     };
@@ -465,7 +483,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         if (tid == 0) {
             mbar_init(&full_bar, 1);
             mbar_fence_init();
-            store_term(terms, C::kZero, fr_zero<P>());
+            store_term(smem4, C::term_chunk(C::kZero), fr_zero<P>());
             issue_tile_load(ts, w, tm.blob_off16, tm.blob_bytes, tm.win_lo, tm.win_n, smem, smem + C::kOffTerms,
                             &full_bar);
             prefetch_behind(ts, w, tm.blob_off16, tm.blob_bytes, tm.win_lo, tm.win_n);
@@ -481,25 +499,29 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     for (uint32_t tile = t_begin; tile < t_end; ++tile, ++it) {
         mbar_wait(&full_bar, it & 1u);
         cp_async_wait_all();  // this thread's far gathers of the tile
+        if (TIMING && it == 0u && tid == 0u && blockIdx.x < kMaxTimedCtas)
+            g_tiled_cta_marks[blockIdx.x][1] = globaltimer_ns();
         mark(0);
         __syncthreads();      // .. and everybody else's
         mark(1);
         const TileHeader h = *reinterpret_cast<const TileHeader*>(blob);
         const uint32_t* words = reinterpret_cast<const uint32_t*>(blob + h.off_words);
         const uint16_t* gop = reinterpret_cast<const uint16_t*>(blob + h.off_gop);
-        uint8_t* gval = blob + h.off_gval;
         // the far witness elements of the NEXT tile start their way into the other far buffer
-        if (tile + 1u < t_end)
+        if (C::kFarDouble && tile + 1u < t_end)
             gather_far_async(tile + 1u, h.next_n_far, reinterpret_cast<const uint32_t*>(blob + h.off_next_far));
 
         // ---- P2: dense 256-bit Montgomery products, one general entry per lane (no divergence between
         //          coefficient kinds): product slot <- coefficient * operand slot
         for (uint32_t j = tid; j < h.n_general; j += C::kThreads)
-            store_term(terms, C::kProd0 + j, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), load_term(smem4, gop[j])));
+            store_term(smem4, C::kProdInPlace ? C::blob_chunk(h.off_gval, j) : C::term_chunk(C::kProd0 + j),
+                       fr_mul<P>(load_term(smem4, C::blob_chunk(h.off_gval, j)), load_term(smem4, gop[j])));
         if (!w0_is_one) {  // not a witness of the reference: coefficient * w[0] in place, inside the blob
             const fr_t w0 = ld_witness(w);
-            for (uint32_t j = h.n_general + tid; j < h.n_general + h.n_const; j += C::kThreads)
-                store_term(reinterpret_cast<uint4*>(gval), j, fr_mul<P>(load_fr16(gval + (size_t)j * 32u), w0));
+            for (uint32_t j = h.n_general + tid; j < h.n_general + h.n_const; j += C::kThreads) {
+                const uint32_t c = C::blob_chunk(h.off_gval, j);
+                store_term(smem4, c, fr_mul<P>(load_term(smem4, c), w0));
+            }
         }
         mark(2);
         __syncthreads();
@@ -535,11 +557,32 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         }
         mark(4);
         if (tile + 1u == t_end) break;
+        // one far buffer: this thread's far columns of the next tile leave the blob before it is refilled
+        uint32_t next_far_col[kFarPerThread];
+        if (!C::kFarDouble) {
+#pragma unroll
+            for (uint32_t k = 0; k < kFarPerThread; ++k) {
+                const uint32_t f = tid + k * C::kThreads;
+                next_far_col[k] = f < h.next_n_far ? reinterpret_cast<const uint32_t*>(blob + h.off_next_far)[f] : 0u;
+            }
+        }
         // blob and window were read (and the term array written) through the generic proxy; order that before
         // the TMA (async proxy) refill of the same bytes
         fence_proxy_async_smem();
         __syncthreads();
         mark(5);
+        if (!C::kFarDouble) {  // .. and are gathered now that every row of this tile has read the far buffer
+#pragma unroll
+            for (uint32_t k = 0; k < kFarPerThread; ++k) {
+                const uint32_t f = tid + k * C::kThreads;
+                if (f < h.next_n_far) {
+                    const uint4* src = reinterpret_cast<const uint4*>(w + next_far_col[k]);
+                    const uint32_t c = C::term_chunk(C::kFar0 + f);
+                    cp_async16(smem4 + c, src);
+                    cp_async16(smem4 + (c ^ 1u), src + 1);
+                }
+            }
+        }
         if (tid == 0)
             issue_tile_load(ts, w, next_off16, h.next_bytes, h.next_win_lo, h.next_win_n, smem, smem + C::kOffTerms,
                             &full_bar);
@@ -552,15 +595,27 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         for (int k = 0; k < 7; ++k) atomicAdd(&g_tiled_phase_cycles[rw][k], ph[rw][k]);
         atomicAdd(&g_tiled_phase_cycles[rw][7], (unsigned long long)it);
     }
+    if (TIMING && tid == 0u && blockIdx.x < kMaxTimedCtas) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_tiled_cta_marks[blockIdx.x][2] = globaltimer_ns();
+        g_tiled_cta_marks[blockIdx.x][4] = smid;
+        g_tiled_cta_marks[blockIdx.x][5] = t_end - t_begin;
+    }
     finish_check(ep);
+    if (TIMING && tid == 0u && blockIdx.x < kMaxTimedCtas) g_tiled_cta_marks[blockIdx.x][3] = globaltimer_ns();
 }
 
 template <class P>
 __global__ void k_to_mont_scattered(uint8_t* __restrict__ blobs, const uint32_t* __restrict__ offs, uint64_t n,
                                     int* __restrict__ bad_flag) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint4* p = reinterpret_cast<uint4*>(blobs + (size_t)offs[i] * 16u);
-        const uint4 a = p[0], b = p[1];
+        // offs[i]: chunk (16-byte unit of the stream) of the low half; bit 31: the high half is the chunk before it
+        // instead of the one after it (a swizzled value, kernels.h swz16)
+        const uint32_t o = offs[i];
+        uint4* lo = reinterpret_cast<uint4*>(blobs + (size_t)(o & 0x7FFFFFFFu) * 16u);
+        uint4* hi = (o >> 31) ? lo - 1 : lo + 1;
+        const uint4 a = *lo, b = *hi;
         fr_t x;
         x.l[0] = a.x; x.l[1] = a.y; x.l[2] = a.z; x.l[3] = a.w;
         x.l[4] = b.x; x.l[5] = b.y; x.l[6] = b.z; x.l[7] = b.w;
@@ -568,8 +623,8 @@ __global__ void k_to_mont_scattered(uint8_t* __restrict__ blobs, const uint32_t*
             *bad_flag = 1;
         } else {
             const fr_t y = fr_to_mont<P>(x);
-            p[0] = make_uint4(y.l[0], y.l[1], y.l[2], y.l[3]);
-            p[1] = make_uint4(y.l[4], y.l[5], y.l[6], y.l[7]);
+            *lo = make_uint4(y.l[0], y.l[1], y.l[2], y.l[3]);
+            *hi = make_uint4(y.l[4], y.l[5], y.l[6], y.l[7]);
         }
     }
 }
@@ -662,8 +717,32 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
             k_r1cs_tiled<P, false, 0, true><<<grid, kTileGeom[0].threads, C::kBytes, s>>>(ts, w, row_base, ep, Aw, Bw,
                                                                                           Cw);
             cudaMemcpyFromSymbolAsync(z, g_tiled_phase_cycles, sizeof z, 0, cudaMemcpyDeviceToHost, s);
+            static unsigned long long marks[kMaxTimedCtas][6];
+            cudaMemcpyFromSymbolAsync(marks, g_tiled_cta_marks, sizeof marks, 0, cudaMemcpyDeviceToHost, s);
             cudaStreamSynchronize(s);
             static int printed = 0;
+            if (printed < 3) {  // CTA timeline: percentiles over the CTAs, ns after the first CTA entered the kernel
+                const unsigned n = grid < kMaxTimedCtas ? grid : kMaxTimedCtas;
+                unsigned long long t0 = ~0ull;
+                for (unsigned i = 0; i < n; ++i) t0 = marks[i][0] < t0 ? marks[i][0] : t0;
+                if (const char* path = getenv("ACG_TILED_TIMING_DUMP")) {  // raw marks, one line per CTA
+                    if (FILE* f = fopen(path, printed ? "a" : "w")) {
+                        fprintf(f, "# launch %d: cta smid tiles entry first_staged last_done exit (ns)\n", printed);
+                        for (unsigned i = 0; i < n; ++i)
+                            fprintf(f, "%u %llu %llu %llu %llu %llu %llu\n", i, marks[i][4], marks[i][5], marks[i][0] - t0,
+                                    marks[i][1] - t0, marks[i][2] - t0, marks[i][3] - t0);
+                        fclose(f);
+                    }
+                }
+                static const char* mn[4] = {"entry", "first tile staged", "last tile done", "exit"};
+                for (int k = 0; k < 4; ++k) {
+                    std::vector<unsigned long long> v(n);
+                    for (unsigned i = 0; i < n; ++i) v[i] = marks[i][k] - t0;
+                    std::sort(v.begin(), v.end());
+                    fprintf(stderr, "[cta timeline ns, %s] min=%llu p10=%llu p50=%llu p90=%llu max=%llu\n", mn[k], v[0],
+                            v[n / 10], v[n / 2], v[(size_t)n * 9 / 10], v[n - 1]);
+                }
+            }
             if (printed++ < 3) {
                 static const char* nm[7] = {"tma_wait", "bar1", "p2", "bar2", "p3", "bar3", "refill"};
                 for (int wsel = 0; wsel < 2; ++wsel) {
@@ -707,6 +786,10 @@ cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w,
         case 1: ACG_TILED_V(1); break;
         case 2: ACG_TILED_V(2); break;
         case 3: ACG_TILED_V(3); break;
+        case 4: ACG_TILED_V(4); break;
+        case 5: ACG_TILED_V(5); break;
+        case 6: ACG_TILED_V(6); break;
+        case 7: ACG_TILED_V(7); break;
         default: ACG_TILED_V(0); break;
     }
 #undef ACG_TILED_V

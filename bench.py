@@ -57,7 +57,7 @@ def parse_args():
                     help="do not overlap consecutive checks (programmatic dependent launch of the next check kernel)")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: all-reduce of the result pair over peer memory (default) or by NCCL")
-    ap.add_argument("--variant", type=int, default=0, choices=[0, 1, 2, 3], help="tiled kernel geometry: rows per tile 128/256/64/32")
+    ap.add_argument("--variant", type=int, default=0, choices=list(range(8)), help="tiled kernel geometry (kernels.h kTileGeom): 0-3 rows per tile 128/256/64/32, 4/5 = 128/64 with the natural term layout, 6 = products in place, 7 = 6 + one far buffer (6 CTAs per SM)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
