@@ -35,6 +35,7 @@ PROTOTYPES = {
     "acg_ctx_set_overlap_checks": (C.c_int, [vp, C.c_int]),
     "acg_ctx_set_tiled_variant": (C.c_int, [vp, C.c_int]),
     "acg_r1cs_stream_bytes": (C.c_uint64, [vp]),
+    "acg_r1cs_set_row_offset": (C.c_int, [vp, C.c_uint64]),
     "acg_last_timing": (C.c_int, [vp, C.POINTER(AcgTiming)]),
     "acg_kernel_launch_count": (C.c_uint64, [vp]),
     "acg_profile_begin": (C.c_int, [vp, C.c_uint32]),
@@ -48,6 +49,9 @@ PROTOTYPES = {
     "acg_witness_upload": (C.c_int, [vp, vp, C.c_uint32, C.POINTER(vp)]),
     "acg_witness_update": (C.c_int, [vp, vp, vp, C.c_uint32]),
     "acg_witness_update_range": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32]),
+    "acg_witness_update_async": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32]),
+    "acg_vec_status": (C.c_int, [vp, vp]),
+    "acg_vec_stream_wait": (C.c_int, [vp, vp, vp]),
     "acg_vec_free": (None, [vp]),
     "acg_vec_len": (C.c_uint32, [vp]),
     "acg_vec_device_ptr": (vp, [vp]),
@@ -56,6 +60,11 @@ PROTOTYPES = {
     "acg_peer_free": (None, [vp]),
     "acg_r1cs_check_async_allreduce": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "acg_poly_combine": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp]),
+    "acg_qap_upload": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.POINTER(vp)]),
+    "acg_qap_free": (None, [vp]),
+    "acg_qap_quotient_len": (C.c_uint32, [vp]),
+    "acg_qap_verify": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32, u32p, C.POINTER(C.c_int)]),
+    "acg_fft_target": (C.c_int, [vp, C.c_uint32, vp]),
     "acg_circuit_plan_stats": (C.c_int, [vp, u32p, u32p]),
     "acg_vec_download": (C.c_int, [vp, vp, vp, C.c_uint32]),
     "acg_generate_assignment_device": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,

@@ -4,6 +4,7 @@
 // entry point needs a CUDA device and reports ACG_ERR_NO_DEVICE / ACG_ERR_CUDA otherwise.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -28,6 +29,13 @@ struct acg_ctx {
     int check_kernel = ACG_CHECK_AUTO;
     int tiled_variant = 0;  // index into kTileGeom, bound to a system at upload
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // acg_witness_update_async: H2D + conversion, overlapping the checks
+    fr_t* staging = nullptr;                 // acg_witness_update[_range]: a rejected update must not touch the vector
+    size_t staging_cap = 0;                  //   (elements)
+    // work buffers of acg_qap_witness, kept between calls (seven vectors of N elements: a fresh cudaMalloc / cudaFree
+    // pair per buffer and call cost more than the kernels at N = 2^22)
+    fr_t* work[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t work_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* d_result = nullptr;  // {n_violations, first_bad_row}
     unsigned long long* d_accum = nullptr;   // scratch pair the check kernels accumulate into + CTA ticket (u32)
@@ -49,9 +57,8 @@ struct acg_ctx {
     uint32_t prof_used = 0;
     // overlap of consecutive checks (CheckEpilogue::overlap): allowed when the previous operation of this context
     // was a single-launch tiled check of the same system and witness on the same stream
-    int overlap_checks = 1;
+    int overlap_checks = 0;
     const void* last_m = nullptr;
-    const void* last_w = nullptr;
     cudaStream_t last_stream = nullptr;
     uint64_t last_check_op = 0;  // value of `ops` right after that check
     uint64_t ops = 0;            // bumped by every entry point that enqueues device work
@@ -60,6 +67,7 @@ struct acg_ctx {
 struct acg_r1cs {
     acg_ctx* ctx = nullptr;
     uint32_t n_rows_total = 0, n_cols = 0, row_begin = 0, row_end = 0;
+    uint64_t row_offset = 0;  // added to reported rows: a shard uploaded as a system of its own (acg_r1cs_set_row_offset)
     uint64_t nnz[3] = {0, 0, 0};
     uint64_t distinct_cols = 0;  // witness columns referenced by the rows of this shard
     uint32_t* d_rowptr[3] = {nullptr, nullptr, nullptr};
@@ -75,12 +83,20 @@ struct acg_r1cs {
     uint32_t n_tiles = 0;
     int variant = 0;
     std::vector<std::pair<uint32_t, uint32_t>> long_ranges;  // local row ranges too wide for a tile
+    uint32_t* d_long_rows = nullptr;  // .. flattened: the rows the warp-per-row kernel handles in one launch
+    uint32_t n_long_rows = 0;
 };
 
 struct acg_vec {
     acg_ctx* ctx = nullptr;
     fr_t* d = nullptr;
     uint32_t n = 0;
+    // asynchronous updates (acg_witness_update_async): `ready` is recorded on the copy stream behind the update, every
+    // check of the vector waits for it and records `used` behind itself, which the next update waits for
+    cudaEvent_t ready = nullptr, used = nullptr;
+    int* d_bad = nullptr;          // set by the conversion kernel of an asynchronous update: an element was >= r
+    bool async_pending = false;    // an asynchronous update was enqueued and its verdict not yet read back
+    bool has_used = false;
 };
 
 struct acg_peer {  // exchange buffers of a group of row-shard ranks (one process per GPU, CUDA IPC)
@@ -99,6 +115,13 @@ int fail(acg_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
     return code;
 }
+int acg_guard_fail(acg_ctx* ctx, int code, const char* msg) noexcept {
+    try {
+        if (ctx) ctx->err = msg;
+    } catch (...) {
+    }
+    return code;
+}
 int fail_cuda(acg_ctx* ctx, cudaError_t e, const char* what) {
     char buf[256];
     snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
@@ -107,6 +130,17 @@ int fail_cuda(acg_ctx* ctx, cudaError_t e, const char* what) {
     if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return ACG_ERR_NO_DEVICE;
     return ACG_ERR_CUDA;
 }
+
+// No C++ exception crosses the C ABI (include/acg.h): every int-returning entry point runs inside ACG_TRY / ACG_CATCH,
+// which map std::bad_alloc to ACG_ERR_OOM and anything else to ACG_ERR_INTERNAL.
+#define ACG_TRY try {
+#define ACG_CATCH_IMPL(ctxp)                                                                            \
+    }                                                                                                   \
+    catch (const std::bad_alloc&) { return acg_guard_fail((ctxp), ACG_ERR_OOM, "out of host memory"); } \
+    catch (const std::exception& e__) { return acg_guard_fail((ctxp), ACG_ERR_INTERNAL, e__.what()); }  \
+    catch (...) { return acg_guard_fail((ctxp), ACG_ERR_INTERNAL, "unknown C++ exception"); }
+#define ACG_CATCH(ctxp) ACG_CATCH_IMPL(const_cast<acg_ctx*>(static_cast<const acg_ctx*>(ctxp)))
+#define ACG_CATCH_NOCTX() ACG_CATCH_IMPL(nullptr)
 #define CU(ctx, expr)                                              \
     do {                                                           \
         cudaError_t e__ = (expr);                                  \
@@ -213,6 +247,62 @@ int upload_canonical(acg_ctx* ctx, fr_t* d, const uint64_t* host, uint64_t n) {
     return ACG_OK;
 }
 
+// Same, but the destination is only written when every element is canonical: H2D into the context's staging buffer,
+// validation + conversion there, then a device-side commit (copy unless the flag is set).  One synchronisation.
+int upload_canonical_staged(acg_ctx* ctx, fr_t* d, const uint64_t* host, uint64_t n) {
+    if (n == 0) return ACG_OK;
+    if (ctx->staging_cap < n) {
+        if (ctx->staging) cudaFree(ctx->staging);
+        ctx->staging = nullptr;
+        ctx->staging_cap = 0;
+        CU(ctx, cudaMalloc(&ctx->staging, n * sizeof(fr_t)));
+        ctx->staging_cap = n;
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->staging, host, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    CU(ctx, launch_to_mont(ctx->field, ctx->staging, n, ctx->d_flag, ctx->stream));
+    CU(ctx, launch_copy_if_clean(d, ctx->staging, n, ctx->d_flag, ctx->stream));
+    ctx->launches += 2;
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_flag) return fail(ctx, ACG_ERR_NON_CANONICAL, "field element >= modulus (the vector was left unchanged)");
+    return ACG_OK;
+}
+
+// A check is about to read vector v on stream s / has been enqueued there (see acg_vec)
+int vec_acquire(acg_ctx* ctx, const acg_vec* v, cudaStream_t s) {
+    if (v->ready && v->async_pending) CU(ctx, cudaStreamWaitEvent(s, v->ready, 0));
+    return ACG_OK;
+}
+int vec_release(acg_ctx* ctx, const acg_vec* v, cudaStream_t s) {
+    if (v->used) {
+        CU(ctx, cudaEventRecord(v->used, s));
+        const_cast<acg_vec*>(v)->has_used = true;
+    }
+    return ACG_OK;
+}
+
+struct WorkBuf {  // a view of one of the context's work buffers (same accessors as DevBuf, no ownership)
+    fr_t* p = nullptr;
+    template <class T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+// work buffer `slot` of the context with room for n elements (contents undefined)
+int work_buffer(acg_ctx* ctx, int slot, size_t n, fr_t** out) {
+    if (ctx->work_cap[slot] < n) {
+        if (ctx->work[slot]) cudaFree(ctx->work[slot]);
+        ctx->work[slot] = nullptr;
+        ctx->work_cap[slot] = 0;
+        CU(ctx, cudaMalloc(&ctx->work[slot], std::max<size_t>(n, 1) * sizeof(fr_t)));
+        ctx->work_cap[slot] = n;
+    }
+    *out = ctx->work[slot];
+    return ACG_OK;
+}
+
 struct HostTile {
     uint32_t row0, nrows, e0[3], ne[3], width[3];
 };
@@ -291,9 +381,14 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
 // Enqueues one check of the shard: the kernels accumulate into the context's scratch pair and the LAST launch
 // finalises into d_result (kernels.h CheckEpilogue) -- including, when `peer` is given, the all-reduce over peer
 // memory.  No initialisation launch; one kernel for a system without over-long rows.
-int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long long* d_result, fr_t* Aw, fr_t* Bw,
+int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* wv, unsigned long long* d_result, fr_t* Aw, fr_t* Bw,
                   fr_t* Cw, cudaStream_t s, uint32_t* launches, acg_peer* peer = nullptr) {
     const uint32_t n_local = m->row_end - m->row_begin;
+    const fr_t* w = wv->d;
+    {   // an asynchronous update of the witness (copy stream) comes first
+        int rc = vec_acquire(ctx, wv, s);
+        if (rc) return rc;
+    }
     CheckEpilogue acc{ctx->d_accum, ctx->d_ticket, nullptr, PeerSlots{}, 0ull, 0u};  // accumulate only
     CheckEpilogue fin = acc;                                                     // .. and finalise
     fin.out = d_result;
@@ -307,7 +402,7 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long 
     if (which == ACG_CHECK_ROWWISE) {
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
         if (n_local) {
-            CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, 0, n_local, m->row_begin, fin, Aw, Bw, Cw, s));
+            CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, 0, n_local, m->row_begin + m->row_offset, fin, Aw, Bw, Cw, s));
             ++*launches;
             finalised = true;
         }
@@ -316,23 +411,33 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long 
             ++ctx->prof_used;
         }
     } else {
+        // rows too long for a tile first -- all of them in one warp-per-row launch (accumulate only) --, the tiled
+        // kernel last: it finalises the check.  At most two launches, however many Split gates the circuit has.
+        if (m->n_long_rows) {
+            const bool last = m->n_tiles == 0;
+            CU(ctx, launch_r1cs_longrows(ctx->field, m->dev, w, m->d_long_rows, m->n_long_rows, m->row_begin + m->row_offset,
+                                         last ? fin : acc, Aw, Bw, Cw, s));
+            ++*launches;
+            finalised = finalised || last;
+        }
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
         if (m->n_tiles) {
             DevTileStream ts{m->d_stream, m->d_meta, m->d_far_cols, m->n_tiles, (uint32_t)m->variant,
                              (uint32_t)(m->blob_bytes / 16), m->n_cols};
-            const bool last = m->long_ranges.empty();
-            // back-to-back checks of the same system and witness may overlap (see CheckEpilogue): every entry point
-            // bumps ctx->ops, so "the previous operation was that check" is ops == last_check_op + 1
+            // back-to-back checks of the same system may overlap (see CheckEpilogue): every entry point bumps ctx->ops,
+            // so "the previous operation was that check" is ops == last_check_op + 1 -- nothing, in particular no
+            // witness update, was enqueued through this context in between (the witnesses of the two checks may be
+            // different resident vectors)
             const bool emit = Aw || Bw || Cw;
-            const bool chain = last && !emit && !prof && ctx->overlap_checks && ctx->last_m == m && ctx->last_w == w &&
+            const bool single = m->long_ranges.empty();
+            const bool chain = single && !emit && !prof && ctx->overlap_checks && ctx->last_m == m &&
                                ctx->last_stream == s && ctx->ops == ctx->last_check_op + 1;
             if (chain) fin.overlap = 1u;
-            CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin, last ? fin : acc, Aw, Bw, Cw, ctx->sm_count, s));
+            CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin + m->row_offset, fin, Aw, Bw, Cw, ctx->sm_count, s));
             ++*launches;
-            finalised = last;
-            if (last && !emit && !prof) {
+            finalised = true;
+            if (single && !emit && !prof) {
                 ctx->last_m = m;
-                ctx->last_w = w;
                 ctx->last_stream = s;
                 ctx->last_check_op = ctx->ops;
             }
@@ -340,14 +445,6 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long 
         if (prof) {
             CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used + 1], s));
             ++ctx->prof_used;
-        }
-        for (size_t i = 0; i < m->long_ranges.size(); ++i) {
-            const auto& lr = m->long_ranges[i];
-            const bool last = i + 1 == m->long_ranges.size();
-            CU(ctx, launch_r1cs_rowwise(ctx->field, m->dev, w, lr.first, lr.second, m->row_begin, last ? fin : acc, Aw,
-                                        Bw, Cw, s));
-            ++*launches;
-            finalised = finalised || last;
         }
     }
     if (!finalised) {  // an empty shard: nothing ran, the result is {0, none} (and the peers still expect this rank)
@@ -358,7 +455,7 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const fr_t* w, unsigned long 
             ++*launches;
         }
     }
-    return ACG_OK;
+    return vec_release(ctx, wv, s);
 }
 
 float elapsed(cudaEvent_t a, cudaEvent_t b) {
@@ -393,6 +490,7 @@ const char* acg_strerror(int code) {
 const char* acg_last_error(const acg_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
 
 int acg_ctx_create(int field_id, int device, acg_ctx** out) {
+    ACG_TRY
     if (!out || (field_id != ACG_FIELD_BN254_FR && field_id != ACG_FIELD_BLS12_381_FR)) return ACG_ERR_BAD_ARG;
     *out = nullptr;
     int n_dev = 0;
@@ -425,6 +523,8 @@ int acg_ctx_create(int field_id, int device, acg_ctx** out) {
     }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
         return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(e, "cudaStreamCreate");
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc(&ctx->d_result, 2 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
@@ -441,6 +541,7 @@ int acg_ctx_create(int field_id, int device, acg_ctx** out) {
     if ((e = cudaMallocHost(&ctx->h_flag, sizeof(int))) != cudaSuccess) return bail(e, "cudaMallocHost");
     *out = ctx;
     return ACG_OK;
+    ACG_CATCH_NOCTX()
 }
 
 void acg_ctx_destroy(acg_ctx* ctx) {
@@ -461,37 +562,50 @@ void acg_ctx_destroy(acg_ctx* ctx) {
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto e : ctx->prof_ev) cudaEventDestroy(e);
+    if (ctx->staging) cudaFree(ctx->staging);
+    for (auto& p : ctx->work)
+        if (p) cudaFree(p);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 int acg_ctx_set_check_kernel(acg_ctx* ctx, int which) {
+    ACG_TRY
     if (!ctx || which < ACG_CHECK_AUTO || which > ACG_CHECK_TILED) return ACG_ERR_BAD_ARG;
     ctx->check_kernel = which;
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 int acg_ctx_set_overlap_checks(acg_ctx* ctx, int on) {
+    ACG_TRY
     if (!ctx) return ACG_ERR_BAD_ARG;
     ctx->overlap_checks = on ? 1 : 0;
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 int acg_ctx_set_tiled_variant(acg_ctx* ctx, int variant) {
+    ACG_TRY
     if (!ctx || variant < 0 || variant >= kNumTileVariants) return ACG_ERR_BAD_ARG;
     ctx->tiled_variant = variant;
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 
 int acg_last_timing(const acg_ctx* ctx, acg_timing* out) {
+    ACG_TRY
     if (!ctx || !out) return ACG_ERR_BAD_ARG;
     *out = ctx->timing;
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 uint64_t acg_kernel_launch_count(const acg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int acg_profile_begin(acg_ctx* ctx, uint32_t max_launches) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     while (ctx->prof_ev.size() < 2ull * max_launches) {
@@ -505,9 +619,11 @@ int acg_profile_begin(acg_ctx* ctx, uint32_t max_launches) {
     }
     ctx->prof_used = 0;
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 int acg_profile_end(acg_ctx* ctx, float* ms_out, uint32_t capacity, uint32_t* n_out) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     uint32_t n = ctx->prof_used < capacity ? ctx->prof_used : capacity;
@@ -520,10 +636,12 @@ int acg_profile_end(acg_ctx* ctx, float* ms_out, uint32_t capacity, uint32_t* n_
     ctx->prof_ev.clear();
     ctx->prof_used = 0;
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 int acg_field_constants(int field_id, uint64_t modulus[4], uint64_t mont_r[4], uint64_t mont_r2[4], uint64_t* ninv64,
                         uint32_t* two_adic) {
+    ACG_TRY
     return with_field(field_id, [&](auto p) {
         using P = decltype(p);
         if (modulus) limbs_from_fr(modulus, host_const<P>(&P::p));
@@ -533,9 +651,11 @@ int acg_field_constants(int field_id, uint64_t modulus[4], uint64_t mont_r[4], u
         if (two_adic) *two_adic = (uint32_t)P::TWO_ADICITY;
         return (int)ACG_OK;
     });
+    ACG_CATCH_NOCTX()
 }
 
 int acg_root_of_unity(int field_id, uint32_t k, uint64_t out[4]) {
+    ACG_TRY
     if (!out) return ACG_ERR_BAD_ARG;
     return with_field(field_id, [&](auto p) {
         using P = decltype(p);
@@ -543,6 +663,7 @@ int acg_root_of_unity(int field_id, uint32_t k, uint64_t out[4]) {
         limbs_from_fr(out, fr_from_mont<P>(host_root_of_unity<P>(k)));
         return (int)ACG_OK;
     });
+    ACG_CATCH_NOCTX()
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -559,11 +680,13 @@ void acg_r1cs_free(acg_r1cs* m) {
     cudaFree(m->d_stream);
     cudaFree(m->d_meta);
     cudaFree(m->d_far_cols);
+    cudaFree(m->d_long_rows);
     delete m;
 }
 
 int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_csr* A, const acg_csr* B,
                     const acg_csr* C, uint32_t row_begin, uint32_t row_end, acg_r1cs** out) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!out || !A || !B || !C || row_begin > row_end || row_end > n_rows || n_cols == 0)
@@ -881,6 +1004,16 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     }
     const uint32_t n_tiles_out = (uint32_t)metas.size();
     std::sort(m->long_ranges.begin(), m->long_ranges.end());
+    {   // the rows the tiles leave out, as one list
+        std::vector<uint32_t> long_rows;
+        for (const auto& lr : m->long_ranges)
+            for (uint32_t r = lr.first; r < lr.second; ++r) long_rows.push_back(r);
+        m->n_long_rows = (uint32_t)long_rows.size();
+        if (m->n_long_rows) {
+            CU(ctx, cudaMalloc(&m->d_long_rows, long_rows.size() * sizeof(uint32_t)));
+            CU(ctx, cudaMemcpy(m->d_long_rows, long_rows.data(), long_rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+    }
     align16();
     if (stream.size() / 16 > 0x7FFFFFF0ull) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_r1cs_upload: tile stream too large");
     m->n_tiles = n_tiles_out;
@@ -916,6 +1049,7 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     guard.p = nullptr;
     *out = m;
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 uint64_t acg_r1cs_algorithmic_bytes(const acg_r1cs* m) {
@@ -928,44 +1062,126 @@ uint64_t acg_r1cs_algorithmic_bytes(const acg_r1cs* m) {
 
 uint64_t acg_r1cs_stream_bytes(const acg_r1cs* m) { return m ? m->stream_bytes : 0; }
 
+int acg_r1cs_set_row_offset(acg_r1cs* m, uint64_t offset) {
+    if (!m) return ACG_ERR_BAD_ARG;
+    m->row_offset = offset;
+    return ACG_OK;
+}
+
 void acg_vec_free(acg_vec* v) {
     if (!v) return;
     if (v->ctx) cudaSetDevice(v->ctx->device);
+    if (v->async_pending && v->ctx) cudaStreamSynchronize(v->ctx->copy_stream);
     cudaFree(v->d);
+    cudaFree(v->d_bad);
+    if (v->ready) cudaEventDestroy(v->ready);
+    if (v->used) cudaEventDestroy(v->used);
     delete v;
 }
 uint32_t acg_vec_len(const acg_vec* v) { return v ? v->n : 0; }
 void* acg_vec_device_ptr(acg_vec* v) { return v ? v->d : nullptr; }
 
-int acg_witness_update(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t n_cols) {
-    int rc = activate(ctx);
-    if (rc) return rc;
-    if (!v || !w || v->n != n_cols) return fail(ctx, ACG_ERR_BAD_ARG, "acg_witness_update: bad argument");
-    CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    rc = upload_canonical(ctx, v->d, w, n_cols);
-    if (rc) return rc;
-    CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    CU(ctx, cudaEventSynchronize(ctx->ev[1]));
-    ctx->timing = acg_timing{elapsed(ctx->ev[0], ctx->ev[1]), 0.f, 0.f, 1, 0};
+// an asynchronous update of v is still in flight: let it finish before the vector is touched from the main stream
+static int vec_settle(acg_ctx* ctx, acg_vec* v) {
+    if (v->async_pending) {
+        CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        v->async_pending = false;
+    }
     return ACG_OK;
 }
 
+int acg_witness_update(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t n_cols) {
+    ACG_TRY
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!v || v->ctx != ctx || !w || v->n != n_cols) return fail(ctx, ACG_ERR_BAD_ARG, "acg_witness_update: bad argument");
+    if ((rc = vec_settle(ctx, v))) return rc;
+    CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = upload_canonical_staged(ctx, v->d, w, n_cols);
+    if (rc) return rc;
+    ctx->timing = acg_timing{elapsed(ctx->ev[0], ctx->ev[1]), 0.f, 0.f, 2, 0};
+    return ACG_OK;
+    ACG_CATCH(ctx)
+}
+
 int acg_witness_update_range(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t first, uint32_t count) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!v || v->ctx != ctx || (count && !w) || first > v->n || count > v->n - first)
         return fail(ctx, ACG_ERR_BAD_ARG, "acg_witness_update_range: bad argument");
     if (count == 0) return ACG_OK;
+    if ((rc = vec_settle(ctx, v))) return rc;
     CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    rc = upload_canonical(ctx, v->d + first, w, count);
+    rc = upload_canonical_staged(ctx, v->d + first, w, count);
     if (rc) return rc;
-    CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    CU(ctx, cudaEventSynchronize(ctx->ev[1]));
-    ctx->timing = acg_timing{elapsed(ctx->ev[0], ctx->ev[1]), 0.f, 0.f, 1, 0};
+    ctx->timing = acg_timing{elapsed(ctx->ev[0], ctx->ev[1]), 0.f, 0.f, 2, 0};
     return ACG_OK;
+    ACG_CATCH(ctx)
+}
+
+// Enqueue only, on the context's copy stream: H2D straight into the vector, validation + conversion in place.  The
+// update waits for the checks of v enqueued so far, and later checks of v wait for it -- so with two vectors the
+// upload of witness i + 1 overlaps the check of witness i.  A non-canonical element is reported by the next blocking
+// call that reads v (acg_r1cs_check, acg_vec_status) as ACG_ERR_NON_CANONICAL; the vector's contents are then
+// undefined.  `w` must stay valid (and should be pinned) until that call.
+int acg_witness_update_async(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t first, uint32_t count) {
+    ACG_TRY
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!v || v->ctx != ctx || (count && !w) || first > v->n || count > v->n - first)
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_witness_update_async: bad argument");
+    if (count == 0) return ACG_OK;
+    if (!v->ready) {
+        CU(ctx, cudaEventCreateWithFlags(&v->ready, cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&v->used, cudaEventDisableTiming));
+        CU(ctx, cudaMalloc(&v->d_bad, sizeof(int)));
+        CU(ctx, cudaMemsetAsync(v->d_bad, 0, sizeof(int), ctx->copy_stream));
+    }
+    cudaStream_t cs = ctx->copy_stream;
+    if (v->has_used) CU(ctx, cudaStreamWaitEvent(cs, v->used, 0));  // the checks of v enqueued so far
+    CU(ctx, cudaMemcpyAsync(v->d + first, w, (size_t)count * sizeof(fr_t), cudaMemcpyHostToDevice, cs));
+    CU(ctx, launch_to_mont(ctx->field, v->d + first, count, v->d_bad, cs));
+    CU(ctx, cudaEventRecord(v->ready, cs));
+    ++ctx->launches;
+    v->async_pending = true;
+    return ACG_OK;
+    ACG_CATCH(ctx)
+}
+
+// Enqueue only: `stream` waits for the asynchronous updates of v enqueued so far (for callers that read or complete the
+// vector with their own device work -- e.g. the NVLink all-gather of the slices of a row-sharded witness -- before a
+// check), and the next asynchronous update of v will wait for what `stream` holds when this vector is next checked.
+int acg_vec_stream_wait(acg_ctx* ctx, acg_vec* v, void* stream) {
+    ACG_TRY
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!v || v->ctx != ctx) return fail(ctx, ACG_ERR_BAD_ARG, "acg_vec_stream_wait: bad argument");
+    return vec_acquire(ctx, v, static_cast<cudaStream_t>(stream));
+    ACG_CATCH(ctx)
+}
+
+// Blocking: waits for the asynchronous updates of v and returns ACG_ERR_NON_CANONICAL if one of them met an element
+// >= r (the flag is cleared), ACG_OK otherwise.
+int acg_vec_status(acg_ctx* ctx, acg_vec* v) {
+    ACG_TRY
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!v || v->ctx != ctx) return fail(ctx, ACG_ERR_BAD_ARG, "acg_vec_status: bad argument");
+    if (!v->d_bad) return ACG_OK;
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, v->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    v->async_pending = false;
+    if (*ctx->h_flag) {
+        CU(ctx, cudaMemsetAsync(v->d_bad, 0, sizeof(int), ctx->copy_stream));
+        return fail(ctx, ACG_ERR_NON_CANONICAL, "an asynchronous witness update met a field element >= modulus");
+    }
+    return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 int acg_witness_upload(acg_ctx* ctx, const uint64_t* w, uint32_t n_cols, acg_vec** out) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!out || !w || n_cols == 0) return fail(ctx, ACG_ERR_BAD_ARG, "acg_witness_upload: bad argument");
@@ -986,12 +1202,15 @@ int acg_witness_upload(acg_ctx* ctx, const uint64_t* w, uint32_t n_cols, acg_vec
     }
     *out = v;
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 int acg_vec_download(acg_ctx* ctx, const acg_vec* v, uint64_t* out, uint32_t n) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!v || !out || v->ctx != ctx || n != v->n) return fail(ctx, ACG_ERR_BAD_ARG, "acg_vec_download: bad argument");
+    if ((rc = vec_settle(ctx, const_cast<acg_vec*>(v)))) return rc;
     DevBuf tmp;
     CU(ctx, tmp.alloc((size_t)n * sizeof(fr_t)));
     CU(ctx, cudaMemcpyAsync(tmp.p, v->d, (size_t)n * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1000,11 +1219,13 @@ int acg_vec_download(acg_ctx* ctx, const acg_vec* v, uint64_t* out, uint32_t n) 
     CU(ctx, cudaMemcpyAsync(out, tmp.p, (size_t)n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 int acg_generate_assignment_device(acg_ctx* ctx, const acg_circuit* c, const uint32_t* input_ix,
                                    const uint64_t* input_vals, uint32_t n_inputs, uint32_t n_in, uint32_t n_mid,
                                    uint32_t n_out, acg_vec** out, uint32_t* n_levels_out) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!c || !out || (n_inputs && (!input_ix || !input_vals)) || c->field != ctx->field)
@@ -1071,41 +1292,56 @@ int acg_generate_assignment_device(acg_ctx* ctx, const acg_circuit* c, const uin
     guard.p = nullptr;
     *out = v;
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 int acg_r1cs_check_async(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* d_result, void* stream) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!m || !w || !d_result || m->ctx != ctx || w->ctx != ctx || w->n != m->n_cols)
         return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_check_async: bad argument");
     uint32_t launches = 0;
-    rc = enqueue_check(ctx, m, w->d, reinterpret_cast<unsigned long long*>(d_result), nullptr, nullptr, nullptr,
+    rc = enqueue_check(ctx, m, w, reinterpret_cast<unsigned long long*>(d_result), nullptr, nullptr, nullptr,
                        static_cast<cudaStream_t>(stream), &launches);
     ctx->launches += launches;
     ctx->timing.kernel_launches = launches;
     return rc;
+    ACG_CATCH(ctx)
 }
 
 int acg_r1cs_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* n_violations,
                    uint64_t* first_bad_row) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!m || !w || m->ctx != ctx || w->ctx != ctx || w->n != m->n_cols)
         return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_check: bad argument");
     uint32_t launches = 0;
     CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    rc = enqueue_check(ctx, m, w->d, ctx->d_result, nullptr, nullptr, nullptr, ctx->stream, &launches);
+    rc = enqueue_check(ctx, m, w, ctx->d_result, nullptr, nullptr, nullptr, ctx->stream, &launches);
     if (rc) return rc;
     CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                             ctx->stream));
+    const bool async_verdict = w->async_pending && w->d_bad;  // (the check waited for that update: its flag is final)
+    if (async_verdict)
+        CU(ctx, cudaMemcpyAsync(ctx->h_flag, w->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->launches += launches;
     ctx->timing = acg_timing{0.f, elapsed(ctx->ev[1], ctx->ev[2]), elapsed(ctx->ev[2], ctx->ev[3]), launches, 0};
+    if (async_verdict) {
+        const_cast<acg_vec*>(w)->async_pending = false;
+        if (*ctx->h_flag) {
+            CU(ctx, cudaMemsetAsync(w->d_bad, 0, sizeof(int), ctx->stream));
+            return fail(ctx, ACG_ERR_NON_CANONICAL, "acg_r1cs_check: the witness update met a field element >= modulus");
+        }
+    }
     if (n_violations) *n_violations = ctx->h_result[0];
     if (first_bad_row) *first_bad_row = ctx->h_result[1];
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 // One-shot path: no host-side preprocessing (a single check cannot amortise it).  Plain copies from the
@@ -1113,6 +1349,7 @@ int acg_r1cs_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* 
 // device, stream-ordered allocations.
 int acg_r1cs_check_host(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_csr* A, const acg_csr* B,
                         const acg_csr* C, const uint64_t* w, uint64_t* n_violations, uint64_t* first_bad_row) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!A || !B || !C || !w || n_cols == 0 || n_cols > kColMask)
@@ -1189,9 +1426,11 @@ int acg_r1cs_check_host(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const ac
     if (n_violations) *n_violations = ctx->h_result[0];
     if (first_bad_row) *first_bad_row = ctx->h_result[1];
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 int acg_r1cs_eval(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* Aw, uint64_t* Bw, uint64_t* Cw) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!m || !w || m->ctx != ctx || w->ctx != ctx || w->n != m->n_cols)
@@ -1203,7 +1442,7 @@ int acg_r1cs_eval(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* A
     for (int k = 0; k < 3; ++k) CU(ctx, buf[k].alloc((size_t)n_local * sizeof(fr_t)));
     uint32_t launches = 0;
     CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    rc = enqueue_check(ctx, m, w->d, ctx->d_result, buf[0].as<fr_t>(), buf[1].as<fr_t>(), buf[2].as<fr_t>(),
+    rc = enqueue_check(ctx, m, w, ctx->d_result, buf[0].as<fr_t>(), buf[1].as<fr_t>(), buf[2].as<fr_t>(),
                        ctx->stream, &launches);
     if (rc) return rc;
     CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -1218,12 +1457,14 @@ int acg_r1cs_eval(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* A
     ctx->launches += launches;
     ctx->timing = acg_timing{0.f, elapsed(ctx->ev[1], ctx->ev[2]), elapsed(ctx->ev[2], ctx->ev[3]), launches, 0};
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 // --------------------------------------------------------------------------------------------------
 // NTT
 // --------------------------------------------------------------------------------------------------
 int acg_ntt_device(acg_ctx* ctx, acg_vec* v, uint32_t log_n, int inverse, void* stream) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!v || v->ctx != ctx || log_n > 31 || v->n != (1u << log_n))
@@ -1241,6 +1482,7 @@ int acg_ntt_device(acg_ctx* ctx, acg_vec* v, uint32_t log_n, int inverse, void* 
     ctx->timing.kernel_launches = launches;
     if (e != cudaSuccess) return fail_cuda(ctx, e, "ntt_run");
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 static int ntt_host_batched(acg_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t n_batch, bool inverse) {
@@ -1287,17 +1529,21 @@ static int ntt_host_batched(acg_ctx* ctx, uint64_t* data, uint32_t log_n, uint32
 }
 
 int acg_ntt(acg_ctx* ctx, uint64_t* data, uint32_t log_n, int inverse) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!data) return fail(ctx, ACG_ERR_BAD_ARG, "acg_ntt: null data");
     return ntt_host_batched(ctx, data, log_n, 1, inverse != 0);
+    ACG_CATCH(ctx)
 }
 
 int acg_interpolate_columns(acg_ctx* ctx, uint64_t* cols, uint32_t log_n, uint32_t n_cols_batch) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!cols && n_cols_batch) return fail(ctx, ACG_ERR_BAD_ARG, "acg_interpolate_columns: null data");
     return ntt_host_batched(ctx, cols, log_n, n_cols_batch, true);
+    ACG_CATCH(ctx)
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -1350,16 +1596,18 @@ static int qap_witness_impl(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, c
     }
     cudaStream_t s = ctx->stream;
     uint32_t launches = 0;
-    DevBuf ev[3], coef[2], hbuf, scratch;
+    WorkBuf ev[3], coef[2], hbuf, scratch;  // views of the context's work buffers
+    int rc = ACG_OK;
     for (int k = 0; k < 3; ++k) {
-        CU(ctx, ev[k].alloc(N * sizeof(fr_t)));
-        CU(ctx, cudaMemsetAsync(ev[k].p, 0, N * sizeof(fr_t), s));
+        if ((rc = work_buffer(ctx, k, N, &ev[k].p))) return rc;
+        // rows beyond the system (padding of the domain) evaluate to zero; the check kernel writes the others
+        if (N > n_rows) CU(ctx, cudaMemsetAsync(ev[k].p + n_rows, 0, (N - n_rows) * sizeof(fr_t), s));
     }
-    CU(ctx, hbuf.alloc(N * sizeof(fr_t)));
-    CU(ctx, scratch.alloc(N * sizeof(fr_t)));
+    if ((rc = work_buffer(ctx, 3, N, &hbuf.p))) return rc;
+    if ((rc = work_buffer(ctx, 4, N, &scratch.p))) return rc;
     CU(ctx, cudaEventRecord(ctx->ev[1], s));
-    int rc = enqueue_check(ctx, m, w->d, ctx->d_result, ev[0].as<fr_t>(), ev[1].as<fr_t>(), ev[2].as<fr_t>(), s,
-                           &launches);
+    rc = enqueue_check(ctx, m, w, ctx->d_result, ev[0].as<fr_t>(), ev[1].as<fr_t>(), ev[2].as<fr_t>(), s,
+                       &launches);
     if (rc) return rc;
     CU(ctx, cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
 
@@ -1386,7 +1634,7 @@ static int qap_witness_impl(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, c
     }
     if (any_delta) {  // keep a and b coefficients for h += d1*b + d2*a
         for (int k = 0; k < 2; ++k) {
-            CU(ctx, coef[k].alloc(N * sizeof(fr_t)));
+            if ((rc = work_buffer(ctx, 5 + k, N, &coef[k].p))) return rc;
             CU(ctx, cudaMemcpyAsync(coef[k].p, ev[k].p, N * sizeof(fr_t), cudaMemcpyDeviceToDevice, s));
         }
     }
@@ -1450,16 +1698,18 @@ extern "C" {
 
 int acg_qap_witness(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, const uint64_t* delta, uint64_t* a,
                     uint64_t* b, uint64_t* c, uint64_t* h, int* divisible) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!m || !w || m->ctx != ctx || w->ctx != ctx || w->n != m->n_cols)
         return fail(ctx, ACG_ERR_BAD_ARG, "acg_qap_witness: bad argument");
-    if (m->row_begin != 0 || m->row_end != m->n_rows_total || m->n_rows_total == 0)
+    if (m->row_begin != 0 || m->row_end != m->n_rows_total || m->n_rows_total == 0 || m->row_offset != 0)
         return fail(ctx, ACG_ERR_BAD_ARG, "acg_qap_witness: needs the full (non-empty) system, not a row shard");
     return with_field(ctx->field, [&](auto p) {
         using P = decltype(p);
         return qap_witness_impl<P>(ctx, m, w, delta, a, b, c, h, divisible);
     });
+    ACG_CATCH(ctx)
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -1467,6 +1717,7 @@ int acg_qap_witness(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, const uin
 // --------------------------------------------------------------------------------------------------
 int acg_lagrange(acg_ctx* ctx, const uint64_t* xs, const uint64_t* ys, uint32_t n, uint32_t n_polys,
                  uint64_t* coeffs, uint64_t* target) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!xs || n == 0 || n > 4096 || (n_polys && (!ys || !coeffs)))
@@ -1503,12 +1754,14 @@ int acg_lagrange(acg_ctx* ctx, const uint64_t* xs, const uint64_t* ys, uint32_t 
                              elapsed(ctx->ev[2], ctx->ev[3]), launches, 0};
     if (*ctx->h_flag) return fail(ctx, ACG_ERR_BAD_ARG, "acg_lagrange: interpolation nodes are not distinct");
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 // --------------------------------------------------------------------------------------------------
 // field ops self-test surface
 // --------------------------------------------------------------------------------------------------
 int acg_fr_binop(acg_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (op < 0 || op > 3 || !a || !out || (op != 3 && !b)) return fail(ctx, ACG_ERR_BAD_ARG, "acg_fr_binop: bad argument");
@@ -1525,10 +1778,12 @@ int acg_fr_binop(acg_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uin
     ctx->launches += 4;
     ctx->timing = acg_timing{0.f, 0.f, 0.f, 4, 0};
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 int acg_poly_combine(acg_ctx* ctx, const uint64_t* polys, const uint64_t* weights, uint32_t n_polys, uint32_t len,
                      uint64_t* out) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!out || (n_polys && len && (!polys || !weights))) return fail(ctx, ACG_ERR_BAD_ARG, "acg_poly_combine: bad argument");
@@ -1547,12 +1802,234 @@ int acg_poly_combine(acg_ctx* ctx, const uint64_t* polys, const uint64_t* weight
     ctx->launches += 4;
     ctx->timing = acg_timing{0.f, 0.f, 0.f, 4, 0};
     return ACG_OK;
+    ACG_CATCH(ctx)
+}
+
+// --------------------------------------------------------------------------------------------------
+// per-wire QAP value: verificationWitnessZk on a `QAP f` (src/QAP.hs:300-327), whole on the device
+// --------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct acg_qap {
+    acg_ctx* ctx = nullptr;
+    uint32_t n_wires = 0, len = 0, n_target = 0;  // n_target: coefficients of the target after stripping zeros
+    fr_t* d_polys[3] = {nullptr, nullptr, nullptr};  // left, right, out: n_wires * len coefficients each
+    fr_t* d_target = nullptr;
+    fr_t lc_inv{};       // 1 / leading coefficient of the target (Montgomery)
+    bool monic = false;
+};
+
+template <class P>
+static int qap_verify_impl(acg_ctx* ctx, const acg_qap* q, const uint64_t* w, const uint64_t* delta, uint64_t* h_out,
+                           uint32_t h_cap, uint32_t* h_len_out, int* divisible) {
+    fr_t d[3] = {fr_zero<P>(), fr_zero<P>(), fr_zero<P>()};
+    if (delta) {
+        for (int k = 0; k < 3; ++k) {
+            const fr_t x = fr_from_limbs(delta + 4 * k);
+            if (!fr_is_canonical<P>(x)) return fail(ctx, ACG_ERR_NON_CANONICAL, "delta >= modulus");
+            d[k] = fr_to_mont<P>(x);
+        }
+    }
+    // a = delta1 * T + sum_k w_k L_k and b, c likewise (src/QAP.hs:314-324): la coefficients each
+    const uint32_t n = q->n_target - 1u;  // degree of the target
+    const uint32_t la = std::max(q->len, q->n_target);
+    const uint64_t len_p = 2ull * la - 1ull;  // formal length of p = a * b - c
+    uint32_t log_m = 0;
+    while ((1ull << log_m) < len_p) ++log_m;
+    if ((int)log_m > P::TWO_ADICITY) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_qap_verify: polynomials too long for the field's 2-adicity");
+    const uint64_t M = 1ull << log_m;
+    const uint32_t h_len = len_p > n ? (uint32_t)(len_p - n) : 0u;
+    if (h_len_out) *h_len_out = h_len;
+    if (h_out && h_cap < h_len) return fail(ctx, ACG_ERR_BAD_ARG, "acg_qap_verify: h buffer too small (acg_qap_quotient_len)");
+    cudaStream_t s = ctx->stream;
+    uint32_t launches = 0;
+    DevBuf ev[3], pbuf, hbuf, scratch, dw;
+    for (int k = 0; k < 3; ++k) {
+        CU(ctx, ev[k].alloc(M * sizeof(fr_t)));
+        CU(ctx, cudaMemsetAsync(ev[k].p, 0, M * sizeof(fr_t), s));
+    }
+    CU(ctx, pbuf.alloc(M * sizeof(fr_t)));
+    CU(ctx, scratch.alloc(M * sizeof(fr_t)));
+    CU(ctx, hbuf.alloc((size_t)std::max(h_len, 1u) * sizeof(fr_t)));
+    CU(ctx, dw.alloc((size_t)std::max(q->n_wires, 1u) * sizeof(fr_t)));
+    CU(ctx, cudaEventRecord(ctx->ev[0], s));
+    int rc = upload_canonical(ctx, dw.as<fr_t>(), w, q->n_wires);  // rejects witness values >= r
+    if (rc) return rc;
+    ++launches;
+    CU(ctx, cudaEventRecord(ctx->ev[1], s));
+    for (int k = 0; k < 3; ++k) {
+        CU(ctx, launch_poly_combine(ctx->field, q->d_polys[k], dw.as<fr_t>(), q->n_wires, q->len, ev[k].as<fr_t>(), s));
+        ++launches;
+        if (!fr_is_zero(d[k])) {
+            CU(ctx, launch_axpy1(ctx->field, ev[k].as<fr_t>(), q->d_target, d[k], q->n_target, s));
+            ++launches;
+        }
+    }
+    // p = a * b - c through a product on M >= 2 la - 1 points
+    if (log_m > 0) {
+        NttPlan *fwd = nullptr, *inv = nullptr;
+        if ((rc = get_plan(ctx, log_m, false, &fwd))) return rc;
+        if ((rc = get_plan(ctx, log_m, true, &inv))) return rc;
+        for (int k = 0; k < 3; ++k) CU(ctx, ntt_run(fwd, ev[k].as<fr_t>(), scratch.as<fr_t>(), 1, s, &launches));
+        CU(ctx, launch_quotient_pointwise(ctx->field, ev[0].as<fr_t>(), ev[1].as<fr_t>(), ev[2].as<fr_t>(), pbuf.as<fr_t>(), M,
+                                          fr_one<P>(), s));
+        ++launches;
+        CU(ctx, ntt_run(inv, pbuf.as<fr_t>(), scratch.as<fr_t>(), 1, s, &launches));
+    } else {
+        CU(ctx, launch_quotient_pointwise(ctx->field, ev[0].as<fr_t>(), ev[1].as<fr_t>(), ev[2].as<fr_t>(), pbuf.as<fr_t>(), 1,
+                                          fr_one<P>(), s));
+        ++launches;
+    }
+    // (h, rem) = p divMod T (src/QAP.hs:327); valid <=> rem == 0
+    uint64_t rem_len = len_p;
+    if (h_len) {
+        CU(ctx, launch_poly_divmod(ctx->field, pbuf.as<fr_t>(), (uint32_t)len_p, q->d_target, n, q->lc_inv, q->monic,
+                                   hbuf.as<fr_t>(), s, &launches));
+        rem_len = n;
+    }
+    CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
+    CU(ctx, launch_any_nonzero(pbuf.as<fr_t>(), rem_len, ctx->d_flag, s));
+    if (rem_len) ++launches;
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaEventRecord(ctx->ev[2], s));
+    if (h_out && h_len) {
+        if ((rc = download_canonical(ctx, hbuf.as<fr_t>(), h_len, h_out))) return rc;
+        ++launches;
+    }
+    CU(ctx, cudaEventRecord(ctx->ev[3], s));
+    CU(ctx, cudaStreamSynchronize(s));
+    ctx->launches += launches;
+    ctx->timing = acg_timing{elapsed(ctx->ev[0], ctx->ev[1]), elapsed(ctx->ev[1], ctx->ev[2]), elapsed(ctx->ev[2], ctx->ev[3]),
+                             launches, 0};
+    if (divisible) *divisible = *ctx->h_flag ? 0 : 1;
+    return ACG_OK;
+}
+
+extern "C" {
+
+void acg_qap_free(acg_qap* q) {
+    if (!q) return;
+    if (q->ctx) cudaSetDevice(q->ctx->device);
+    for (auto& p : q->d_polys) cudaFree(p);
+    cudaFree(q->d_target);
+    delete q;
+}
+
+int acg_qap_upload(acg_ctx* ctx, const uint64_t* left, const uint64_t* right, const uint64_t* out, uint32_t n_wires,
+                   uint32_t len, const uint64_t* target, uint32_t n_target, acg_qap** out_q) {
+    ACG_TRY
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!out_q || !target || n_target == 0 || (n_wires && len && (!left || !right || !out)))
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_qap_upload: bad argument");
+    *out_q = nullptr;
+    while (n_target && (target[4ull * (n_target - 1)] | target[4ull * (n_target - 1) + 1] | target[4ull * (n_target - 1) + 2] |
+                        target[4ull * (n_target - 1) + 3]) == 0)
+        --n_target;  // VPoly normal form: no trailing zero coefficients
+    if (n_target == 0) return fail(ctx, ACG_ERR_BAD_ARG, "acg_qap_upload: the target polynomial is zero");
+    if (len == 0 || n_wires == 0) len = n_wires = 0;
+    acg_qap* q = new (std::nothrow) acg_qap();
+    if (!q) return ACG_ERR_OOM;
+    q->ctx = ctx;
+    q->n_wires = n_wires;
+    q->len = len;
+    q->n_target = n_target;
+    struct Guard {
+        acg_qap* p;
+        ~Guard() {
+            if (p) acg_qap_free(p);
+        }
+    } guard{q};
+    const uint64_t* src[3] = {left, right, out};
+    const uint64_t cnt = (uint64_t)n_wires * len;
+    for (int k = 0; k < 3; ++k) {
+        CU(ctx, cudaMalloc(&q->d_polys[k], std::max<uint64_t>(cnt, 1) * sizeof(fr_t)));
+        if ((rc = upload_canonical(ctx, q->d_polys[k], src[k], cnt))) return rc;
+    }
+    CU(ctx, cudaMalloc(&q->d_target, (size_t)n_target * sizeof(fr_t)));
+    if ((rc = upload_canonical(ctx, q->d_target, target, n_target))) return rc;
+    ctx->launches += 4;
+    rc = with_field(ctx->field, [&](auto p) {
+        using P = decltype(p);
+        const fr_t lc = fr_to_mont<P>(fr_from_limbs(target + 4ull * (n_target - 1)));
+        q->monic = fr_is_one<P>(lc);
+        q->lc_inv = fr_inv<P>(lc);
+        return (int)ACG_OK;
+    });
+    if (rc) return rc;
+    guard.p = nullptr;
+    *out_q = q;
+    return ACG_OK;
+    ACG_CATCH(ctx)
+}
+
+uint32_t acg_qap_quotient_len(const acg_qap* q) {
+    if (!q) return 0;
+    const uint64_t la = std::max(q->len, q->n_target);
+    const uint64_t len_p = 2 * la - 1, n = q->n_target - 1u;
+    return len_p > n ? (uint32_t)(len_p - n) : 0u;
+}
+
+int acg_qap_verify(acg_ctx* ctx, const acg_qap* q, const uint64_t* w, const uint64_t* delta, uint64_t* h,
+                   uint32_t h_capacity, uint32_t* h_len, int* divisible) {
+    ACG_TRY
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!q || q->ctx != ctx || (q->n_wires && !w)) return fail(ctx, ACG_ERR_BAD_ARG, "acg_qap_verify: bad argument");
+    return with_field(ctx->field, [&](auto p) {
+        using P = decltype(p);
+        return qap_verify_impl<P>(ctx, q, w, delta, h, h_capacity, h_len, divisible);
+    });
+    ACG_CATCH(ctx)
+}
+
+int acg_fft_target(acg_ctx* ctx, uint32_t n_roots, uint64_t* out) {
+    ACG_TRY
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (!out) return fail(ctx, ACG_ERR_BAD_ARG, "acg_fft_target: null output");
+    uint32_t log_n = 0;
+    while ((1ull << log_n) < n_roots) ++log_n;
+    if ((int)log_n > two_adicity(ctx->field)) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_fft_target: too many roots");
+    std::memset(out, 0, ((size_t)n_roots + 1) * 32);
+    if (n_roots == 0) {  // the empty product
+        out[0] = 1;
+        return ACG_OK;
+    }
+    if (n_roots == (1u << log_n)) {  // the whole domain: X^N - 1 (N = 1: X - 1)
+        uint64_t modulus[4];
+        acg_field_constants(ctx->field, modulus, nullptr, nullptr, nullptr, nullptr);
+        std::memcpy(out, modulus, 32);
+        out[0] -= 1;  // r - 1 (r is odd)
+        out[4ull * n_roots] = 1;
+        return ACG_OK;
+    }
+    if (n_roots > 4096) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_fft_target: a partial domain is limited to 4096 roots");
+    return with_field(ctx->field, [&](auto p) -> int {
+        using P = decltype(p);
+        DevBuf xs, tg, scratch;
+        CU(ctx, xs.alloc((size_t)n_roots * sizeof(fr_t)));
+        CU(ctx, tg.alloc(((size_t)n_roots + 1) * sizeof(fr_t)));
+        CU(ctx, scratch.alloc((3 * (size_t)n_roots + 2) * sizeof(fr_t)));
+        uint32_t launches = 1;
+        CU(ctx, launch_fill_powers(ctx->field, xs.as<fr_t>(), n_roots, host_root_of_unity<P>(log_n), 0, ctx->stream));
+        CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+        CU(ctx, launch_lagrange(ctx->field, xs.as<fr_t>(), nullptr, n_roots, 0, nullptr, tg.as<fr_t>(), scratch.as<fr_t>(),
+                                ctx->d_flag, ctx->stream, &launches));
+        int rc2 = download_canonical(ctx, tg.as<fr_t>(), (uint64_t)n_roots + 1, out);
+        if (rc2) return rc2;
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->launches += launches + 1;
+        return ACG_OK;
+    });
+    ACG_CATCH(ctx)
 }
 
 // --------------------------------------------------------------------------------------------------
 // multi-GPU: result all-reduce over peer memory
 // --------------------------------------------------------------------------------------------------
 int acg_peer_create(acg_ctx* ctx, uint32_t world, uint32_t rank, acg_peer** out, uint8_t* handle_out) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!out || !handle_out || world == 0 || world > kMaxPeers || rank >= world)
@@ -1576,9 +2053,11 @@ int acg_peer_create(acg_ctx* ctx, uint32_t world, uint32_t rank, acg_peer** out,
     std::memcpy(handle_out, &h, sizeof h);
     *out = p;
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 int acg_peer_connect(acg_ctx* ctx, acg_peer* p, const uint8_t* handles) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!p || p->ctx != ctx || !handles || p->connected) return fail(ctx, ACG_ERR_BAD_ARG, "acg_peer_connect: bad argument");
@@ -1596,6 +2075,7 @@ int acg_peer_connect(acg_ctx* ctx, acg_peer* p, const uint8_t* handles) {
     p->slots.rank = p->rank;
     p->connected = true;
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 void acg_peer_free(acg_peer* p) {
@@ -1609,6 +2089,7 @@ void acg_peer_free(acg_peer* p) {
 
 int acg_r1cs_check_async_allreduce(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, acg_peer* peer,
                                    uint64_t* d_result, void* stream) {
+    ACG_TRY
     int rc = activate(ctx);
     if (rc) return rc;
     if (!m || !w || !d_result || !peer || m->ctx != ctx || w->ctx != ctx || peer->ctx != ctx || w->n != m->n_cols ||
@@ -1616,12 +2097,13 @@ int acg_r1cs_check_async_allreduce(acg_ctx* ctx, const acg_r1cs* m, const acg_ve
         return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_check_async_allreduce: bad argument");
     uint32_t launches = 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    rc = enqueue_check(ctx, m, w->d, reinterpret_cast<unsigned long long*>(d_result), nullptr, nullptr, nullptr, s,
+    rc = enqueue_check(ctx, m, w, reinterpret_cast<unsigned long long*>(d_result), nullptr, nullptr, nullptr, s,
                        &launches, peer);
     if (rc) return rc;
     ctx->launches += launches;
     ctx->timing.kernel_launches = launches;
     return ACG_OK;
+    ACG_CATCH(ctx)
 }
 
 }  // extern "C"

@@ -16,6 +16,13 @@
 #include "../../../include/acg.h"
 #include "circuit.hpp"
 
+// No C++ exception crosses the C ABI (include/acg.h): std::bad_alloc -> ACG_ERR_OOM, anything else -> ACG_ERR_INTERNAL.
+#define ACG_TRY try {
+#define ACG_CATCH()                                         \
+    }                                                       \
+    catch (const std::bad_alloc&) { return ACG_ERR_OOM; }   \
+    catch (...) { return ACG_ERR_INTERNAL; }
+
 using namespace acg;
 using namespace acg::host;
 
@@ -386,9 +393,27 @@ int lower_impl(const acg_circuit* c, const Layout& lay, RowSink& sink) {
     std::vector<int> rcs(T, ACG_OK);
     std::vector<std::thread> workers;
     workers.reserve(T);
-    for (size_t t = 0; t < T; ++t)
-        workers.emplace_back([&, t]() { rcs[t] = lower_range<P>(c, lay, n * t / T, n * (t + 1) / T, parts[t]); });
+    bool spawn_failed = false;
+    for (size_t t = 0; t < T && !spawn_failed; ++t) {
+        try {  // nothing may escape a worker (std::terminate) or leave joinable threads behind
+            workers.emplace_back([&, t]() {
+                try {
+                    rcs[t] = lower_range<P>(c, lay, n * t / T, n * (t + 1) / T, parts[t]);
+                } catch (const std::bad_alloc&) {
+                    rcs[t] = ACG_ERR_OOM;
+                } catch (...) {
+                    rcs[t] = ACG_ERR_INTERNAL;
+                }
+            });
+        } catch (...) {  // the system refused another thread
+            spawn_failed = true;
+        }
+    }
     for (auto& w : workers) w.join();
+    if (spawn_failed) {  // fall back to the sequential pass (identical output)
+        parts.clear();
+        return lower_range<P>(c, lay, 0, n, sink);
+    }
     for (int rc : rcs)
         if (rc != ACG_OK) return rc;
     for (int k = 0; k < 3; ++k) {
@@ -520,6 +545,7 @@ int build_gate_plan(const acg_circuit* c, uint32_t n_in, uint32_t n_mid, uint32_
 extern "C" {
 
 int acg_circuit_parse(int field_id, const uint64_t* words, uint64_t n_words, acg_circuit** out) {
+    ACG_TRY
     if (!out || (!words && n_words)) return ACG_ERR_BAD_ARG;
     *out = nullptr;
     acg_circuit* c = new (std::nothrow) acg_circuit();
@@ -532,6 +558,7 @@ int acg_circuit_parse(int field_id, const uint64_t* words, uint64_t n_words, acg
     }
     *out = c;
     return ACG_OK;
+    ACG_CATCH()
 }
 void acg_circuit_free(acg_circuit* c) { delete c; }
 uint64_t acg_circuit_num_gates(const acg_circuit* c) { return c ? c->gates.size() : 0; }
@@ -539,6 +566,7 @@ uint64_t acg_circuit_num_roots(const acg_circuit* c) { return c ? c->n_roots : 0
 
 // validArithCircuit, src/Circuit/Arithmetic.hs:158-185
 int acg_circuit_valid(const acg_circuit* c) {
+    ACG_TRY
     if (!c) return 0;
     std::vector<uint8_t> defined_mid;
     auto is_defined = [&](uint64_t w) {
@@ -571,10 +599,12 @@ int acg_circuit_valid(const acg_circuit* c) {
             }
     }
     return ok ? 1 : 0;
+    ACG_CATCH()
 }
 
 int acg_generate_assignment(const acg_circuit* c, const uint32_t* input_ix, const uint64_t* input_vals,
                             uint32_t n_inputs, acg_assignment** out) {
+    ACG_TRY
     if (!c || !out || (n_inputs && (!input_ix || !input_vals))) return ACG_ERR_BAD_ARG;
     *out = nullptr;
     acg_assignment* a = new (std::nothrow) acg_assignment();
@@ -596,10 +626,12 @@ int acg_generate_assignment(const acg_circuit* c, const uint32_t* input_ix, cons
     }
     *out = a;
     return ACG_OK;
+    ACG_CATCH()
 }
 void acg_assignment_free(acg_assignment* a) { delete a; }
 
 int acg_circuit_plan_stats(const acg_circuit* c, uint32_t* n_levels, uint32_t* max_width) {
+    ACG_TRY
     if (!c) return ACG_ERR_BAD_ARG;
     acg::host::GatePlan plan;
     const int rc = acg::host::build_gate_plan(c, 0, 0, 0, plan);
@@ -607,9 +639,11 @@ int acg_circuit_plan_stats(const acg_circuit* c, uint32_t* n_levels, uint32_t* m
     if (n_levels) *n_levels = plan.level_ptr.empty() ? 0u : (uint32_t)plan.level_ptr.size() - 1u;
     if (max_width) *max_width = plan.max_width;
     return ACG_OK;
+    ACG_CATCH()
 }
 
 int acg_assignment_dims(const acg_assignment* a, uint32_t* n_in, uint32_t* n_mid, uint32_t* n_out) {
+    ACG_TRY
     if (!a) return ACG_ERR_BAD_ARG;
     uint32_t* outs[3] = {n_in, n_mid, n_out};
     for (int k = 0; k < 3; ++k) {
@@ -622,9 +656,11 @@ int acg_assignment_dims(const acg_assignment* a, uint32_t* n_in, uint32_t* n_mid
         if (outs[k]) *outs[k] = mx;
     }
     return ACG_OK;
+    ACG_CATCH()
 }
 
 int acg_assignment_lookup(const acg_assignment* a, uint64_t wire, uint64_t out[4]) {
+    ACG_TRY
     if (!a || !out || !wire_ok(wire)) return ACG_ERR_BAD_ARG;
     El v;
     if (!wm_get(a->part[wkind(wire)], wix(wire), v)) return 0;
@@ -634,9 +670,11 @@ int acg_assignment_lookup(const acg_assignment* a, uint64_t wire, uint64_t out[4
         return 0;
     });
     return 1;
+    ACG_CATCH()
 }
 
 int acg_assignment_update(acg_assignment* a, uint64_t wire, const uint64_t val[4]) {
+    ACG_TRY
     if (!a || !val || !wire_ok(wire)) return ACG_ERR_BAD_ARG;
     return dispatch(a->field, [&](auto p) {
         using P = decltype(p);
@@ -645,9 +683,11 @@ int acg_assignment_update(acg_assignment* a, uint64_t wire, const uint64_t val[4
         wm_set(a->part[wkind(wire)], wix(wire), Fr<P>::to_mont(v));
         return (int)ACG_OK;
     });
+    ACG_CATCH()
 }
 
 int acg_assignment_to_vector(const acg_assignment* a, uint32_t n_in, uint32_t n_mid, uint32_t n_out, uint64_t* w) {
+    ACG_TRY
     if (!a || !w) return ACG_ERR_BAD_ARG;
     const uint32_t dims[3] = {n_in, n_mid, n_out};
     for (int k = 0; k < 3; ++k)
@@ -670,10 +710,12 @@ int acg_assignment_to_vector(const acg_assignment* a, uint32_t n_in, uint32_t n_
         }
         return (int)ACG_OK;
     });
+    ACG_CATCH()
 }
 
 int acg_circuit_to_r1cs(const acg_circuit* c, const uint64_t* roots, uint64_t root_start, uint32_t n_in,
                         uint32_t n_mid, uint32_t n_out, acg_r1cs_host** out) {
+    ACG_TRY
     if (!c || !out) return ACG_ERR_BAD_ARG;
     *out = nullptr;
     uint32_t dims[3];
@@ -740,12 +782,14 @@ int acg_circuit_to_r1cs(const acg_circuit* c, const uint64_t* roots, uint64_t ro
     }
     *out = m;
     return ACG_OK;
+    ACG_CATCH()
 }
 
 void acg_r1cs_host_free(acg_r1cs_host* m) { delete m; }
 
 int acg_r1cs_host_dims(const acg_r1cs_host* m, uint32_t* n_rows, uint32_t* n_cols, uint32_t* n_in, uint32_t* n_mid,
                        uint32_t* n_out) {
+    ACG_TRY
     if (!m) return ACG_ERR_BAD_ARG;
     if (n_rows) *n_rows = m->n_rows;
     if (n_cols) *n_cols = m->n_cols;
@@ -753,15 +797,18 @@ int acg_r1cs_host_dims(const acg_r1cs_host* m, uint32_t* n_rows, uint32_t* n_col
     if (n_mid) *n_mid = m->n_mid;
     if (n_out) *n_out = m->n_out;
     return ACG_OK;
+    ACG_CATCH()
 }
 
 int acg_r1cs_host_csr(const acg_r1cs_host* m, int which, acg_csr* out) {
+    ACG_TRY
     if (!m || !out || which < 0 || which > 2) return ACG_ERR_BAD_ARG;
     out->rowptr = m->rowptr[which].data();
     out->col = m->col[which].data();
     out->val = m->val[which].data();
     out->nnz = m->col[which].size();
     return ACG_OK;
+    ACG_CATCH()
 }
 
 const uint64_t* acg_r1cs_host_roots(const acg_r1cs_host* m) { return m ? m->roots.data() : nullptr; }

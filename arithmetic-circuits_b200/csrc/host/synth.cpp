@@ -14,6 +14,13 @@
 #include "../../../include/acg.h"
 #include "circuit.hpp"
 
+// No C++ exception crosses the C ABI (include/acg.h): std::bad_alloc -> ACG_ERR_OOM, anything else -> ACG_ERR_INTERNAL.
+#define ACG_TRY try {
+#define ACG_CATCH()                                         \
+    }                                                       \
+    catch (const std::bad_alloc&) { return ACG_ERR_OOM; }   \
+    catch (...) { return ACG_ERR_INTERNAL; }
+
 using namespace acg;
 using namespace acg::host;
 
@@ -223,11 +230,14 @@ int synth_words_impl(uint32_t n, uint64_t seed, bool dense, std::vector<uint64_t
 extern "C" {
 
 int acg_synth_r1cs(int field_id, uint32_t n, uint64_t seed, int dense, acg_r1cs_host** out_m, uint64_t** out_w) {
+    ACG_TRY
     return acg_synth_r1cs_rows(field_id, n, seed, dense, 0, n, out_m, out_w);
+    ACG_CATCH()
 }
 
 int acg_synth_r1cs_rows(int field_id, uint32_t n, uint64_t seed, int dense, uint32_t row_begin, uint32_t row_end,
                         acg_r1cs_host** out_m, uint64_t** out_w) {
+    ACG_TRY
     if (!out_m || !out_w || n == 0 || n > 0xF0000000u - kInputs || row_begin > row_end || row_end > n)
         return ACG_ERR_BAD_ARG;
     *out_m = nullptr;
@@ -255,11 +265,13 @@ int acg_synth_r1cs_rows(int field_id, uint32_t n, uint64_t seed, int dense, uint
     *out_m = m;
     *out_w = w;
     return ACG_OK;
+    ACG_CATCH()
 }
 
 int acg_synth_circuit_words(int field_id, uint32_t n, uint64_t seed, int dense, uint64_t** out_words,
                             uint64_t* out_n_words, uint32_t** out_input_ix, uint64_t** out_input_vals,
                             uint32_t* out_n_inputs) {
+    ACG_TRY
     if (!out_words || !out_n_words || !out_input_ix || !out_input_vals || !out_n_inputs || n == 0)
         return ACG_ERR_BAD_ARG;
     std::vector<uint64_t> words, in_vals;
@@ -289,6 +301,7 @@ int acg_synth_circuit_words(int field_id, uint32_t n, uint64_t seed, int dense, 
     *out_input_vals = iv;
     *out_n_inputs = kInputs;
     return ACG_OK;
+    ACG_CATCH()
 }
 
 }  // extern "C"

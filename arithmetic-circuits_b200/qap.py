@@ -373,6 +373,64 @@ def synth_circuit(field: int, n: int, seed: int, dense: bool = False) -> Tuple[A
     return ArithCircuit.from_words(field, words), dict(zip((int(i) for i in ix), from_limbs(iv)))
 
 
+def synth_mixed_circuit(field: int, n_rows: int, seed: int, dist: Tuple[int, int, int] = (50, 10, 1),
+                        num_inputs: int = 1024, split_bits: int = 256) -> Tuple[ArithCircuit, Dict[int, int]]:
+    """A random circuit with the gate mix of the reference's own generator, arbArithCircuit
+    (test/Test/Circuit/Arithmetic.hs:77-126): Mul : Equal : Split drawn with frequencies `dist` (the reference's
+    property tests use 50 : 10 : 1), Split into 256 bits, gate inputs affine circuits of size 1 over the inputs and ALL
+    earlier intermediate wires (`elements mids`: no locality), every gate output a fresh intermediate wire.  Gates are
+    added until the circuit lowers to at least n_rows R1CS rows (Mul 1 row, Equal 2, Split 1 + 256).  Returns the
+    circuit and an input assignment."""
+    import random
+    rnd = random.Random(seed)
+    r = field_constants(field)["modulus"]
+    words: List[int] = []
+    n_mid, rows = 0, 0
+
+    def leaf() -> List[int]:
+        k = rnd.randrange(3 if n_mid else 2)
+        if k == 0:
+            return [1] + _limbs4(rnd.randrange(r))
+        if k == 1:
+            return [0, InputWire(rnd.randrange(num_inputs))]
+        return [0, IntermediateWire(rnd.randrange(n_mid))]
+
+    def affine() -> List[int]:   # arbAffineCircuitWithMids numInps mids 1
+        if rnd.randrange(2) == 0:
+            return leaf() + [3] + _limbs4(rnd.randrange(r))   # ScalarMul s leaf
+        return leaf() + leaf() + [2]                              # Add leaf leaf
+
+    total = sum(dist)
+    while rows < n_rows:
+        x = rnd.randrange(total) if n_mid else 0
+        if x < dist[0]:
+            l, rr = affine(), affine()
+            words += [1, IntermediateWire(n_mid), len(l)] + l + [len(rr)] + rr
+            n_mid += 1
+            rows += 1
+        elif x < dist[0] + dist[1]:
+            words += [2, IntermediateWire(rnd.randrange(n_mid)), IntermediateWire(n_mid), IntermediateWire(n_mid + 1)]
+            n_mid += 2
+            rows += 2
+        else:
+            words += [3, IntermediateWire(rnd.randrange(n_mid)), split_bits] + \
+                     [IntermediateWire(n_mid + i) for i in range(split_bits)]
+            n_mid += split_bits
+            rows += 1 + split_bits
+    inputs = {i: rnd.randrange(r) for i in range(num_inputs)}
+    return ArithCircuit.from_words(field, np.array(words, dtype=np.uint64)), inputs
+
+
+def synth_mixed_r1cs(field: int, n_rows: int, seed: int, dist: Tuple[int, int, int] = (50, 10, 1)):
+    """synth_mixed_circuit lowered through the host mirror (arithCircuitToGenQAP with roots 1, 2, 3, ... and
+    generateAssignment): (rows, honest witness vector)."""
+    circuit, inputs = synth_mixed_circuit(field, n_rows, seed, dist)
+    g = arith_circuit_to_gen_qap(circuit, None, 1)
+    w = witness_vector(generate_assignment(circuit, inputs), g.layout)
+    g._circuit = circuit
+    return g, w
+
+
 # ---------------------------------------------------------------------------------------------------
 # device side
 # ---------------------------------------------------------------------------------------------------
@@ -404,7 +462,7 @@ class Context:
         _check(_lib.lib().acg_ctx_set_check_kernel(self._h, which), self)
 
     def set_overlap_checks(self, on: bool):
-        """Overlap of back-to-back checks of the same system and witness (include/acg.h); on by default."""
+        """Overlap of back-to-back checks of the same system (include/acg.h); off by default."""
         _check(_lib.lib().acg_ctx_set_overlap_checks(self._h, int(on)), self)
 
     def set_tiled_variant(self, variant: int):
@@ -526,6 +584,12 @@ class Context:
         polys = [from_limbs(co[i * n:(i + 1) * n]) for i in range(len(ys))]
         return polys, (from_limbs(tg) if want_target else None)
 
+    def fft_target(self, n_roots: int) -> List[int]:
+        """FFT.fftTargetPoly primRoots n (src/QAP.hs:524): prod_{i < n} (X - omega^i), stripped."""
+        out = np.zeros((n_roots + 1, 4), np.uint64)
+        _check(_lib.lib().acg_fft_target(self._h, n_roots, _ptr(out)), self)
+        return strip(from_limbs(out))
+
     def fr_binop(self, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(a, np.uint64).reshape(-1, 4)
         b = np.ascontiguousarray(b, np.uint64).reshape(-1, 4)
@@ -575,6 +639,10 @@ class DeviceR1cs:
         if _lib is not None:
             self.free()
 
+    def set_row_offset(self, offset: int):
+        """Global index of this row block's first row (acg_r1cs_set_row_offset): added to reported first bad rows."""
+        _check(_lib.lib().acg_r1cs_set_row_offset(self._h, offset), self.ctx)
+
     @property
     def algorithmic_bytes(self) -> int:
         return _lib.lib().acg_r1cs_algorithmic_bytes(self._h)
@@ -608,6 +676,23 @@ class DeviceVec:
         """Overwrite elements [first, first + len(w_slice)) from host memory (canonical limbs)."""
         w_slice = np.ascontiguousarray(w_slice, np.uint64).reshape(-1, 4)
         _check(_lib.lib().acg_witness_update_range(self.ctx._h, self._h, _ptr(w_slice), first, len(w_slice)), self.ctx)
+
+    def update_async(self, w: np.ndarray, first: int = 0):
+        """Enqueue an update of elements [first, first + len(w)) on the context's copy stream (acg_witness_update_async):
+        no host synchronisation; later checks of this vector wait for it.  `w` must stay alive (ideally pinned) until
+        the next blocking call on this vector."""
+        w = np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4)
+        keep = getattr(self, "_async_src", [])   # keep the host buffers alive while the copies are in flight
+        self._async_src = (keep + [w])[-8:]
+        _check(_lib.lib().acg_witness_update_async(self.ctx._h, self._h, _ptr(w), first, w.shape[0]), self.ctx)
+
+    def stream_wait(self, stream: int):
+        """Make the CUDA stream `stream` wait for the asynchronous updates enqueued so far (acg_vec_stream_wait)."""
+        _check(_lib.lib().acg_vec_stream_wait(self.ctx._h, self._h, C.c_void_p(stream)), self.ctx)
+
+    def status(self):
+        """Wait for the asynchronous updates; raises AcgError(-2) if one of them met an element >= r."""
+        _check(_lib.lib().acg_vec_status(self.ctx._h, self._h), self.ctx)
 
     def as_torch_bytes(self):
         """A torch uint8 tensor aliasing the device storage (Montgomery form, 32 bytes per element) -- for
@@ -643,9 +728,25 @@ def strip(poly: Sequence[int]) -> List[int]:
     return p
 
 
+def witness_vector(assignment: QapSet, layout: Tuple[int, int, int]) -> np.ndarray:
+    """The assignment as the dense witness of a system with the given layout.  The reference pairs QAP and assignment
+    wire by wire with defaults on BOTH sides (combineWithDefaults, src/QAP.hs:163-181, 314): a wire the assignment
+    lacks counts as 0, and a wire the system does not know meets the zero polynomial -- so assignment keys beyond the
+    layout are dropped instead of being an error."""
+    dims = assignment.dims()
+    lay = tuple(max(a, b) for a, b in zip(dims, layout))
+    w = assignment.to_vector(lay)
+    if lay == tuple(layout):
+        return w
+    n_in, n_mid, n_out = layout
+    keep = np.concatenate([np.arange(0, 1 + n_in), 1 + lay[0] + np.arange(n_mid),
+                           1 + lay[0] + lay[1] + np.arange(n_out)]).astype(np.int64)
+    return np.ascontiguousarray(w[keep])
+
+
 def verify_assignment(ctx: Context, g: GenQAP, assignment: QapSet) -> bool:
     """verifyAssignment (src/QAP.hs:276-282) in R1CS form: one upload + one check."""
-    w = assignment.to_vector(g.layout)
+    w = witness_vector(assignment, g.layout)
     nv, _ = ctx.r1cs_check_host(g, w)
     return nv == 0
 
@@ -654,7 +755,7 @@ def verification_witness_zk(ctx: Context, d1: int, d2: int, d3: int, g: GenQAP, 
     """verificationWitnessZk (src/QAP.hs:300-327) on the FFT-built QAP: `Just h` (stripped coefficient
     list) or None."""
     m = ctx.upload_r1cs(g)
-    w = ctx.upload_witness(assignment.to_vector(g.layout))
+    w = ctx.upload_witness(witness_vector(assignment, g.layout))
     try:
         bufs, ok = ctx.qap_witness(m, w, (d1, d2, d3), want=("h",))
     finally:
@@ -702,6 +803,31 @@ class QAP:
         self.field, self.layout, self.n_rows = field, tuple(layout), n_rows
         self.left, self.right, self.out = left, right, out
         self.target, self.kind, self.roots = target, kind, roots
+        self._dev = None   # (Context, acg_qap handle): the value resident on the device, uploaded on first use
+
+    def device_handle(self, ctx: "Context"):
+        """The acg_qap handle of this value on `ctx` (acg_qap_upload on first use)."""
+        if self._dev is not None and self._dev[0] is ctx and ctx._h:
+            return self._dev[1]
+        self.free_device()
+        tgt = to_limbs(self.target)
+        h = C.c_void_p()
+        arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in (self.left, self.right, self.out)]
+        _check(_lib.lib().acg_qap_upload(ctx._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), arrs[0].shape[0],
+                                         arrs[0].shape[1], _ptr(tgt), len(self.target), C.byref(h)), ctx)
+        self._dev = (ctx, h)
+        return h
+
+    def free_device(self):
+        if getattr(self, "_dev", None) is not None:
+            ctx, h = self._dev
+            if ctx._h and _lib is not None:
+                _lib.lib().acg_qap_free(h)
+            self._dev = None
+
+    def __del__(self):
+        if _lib is not None:
+            self.free_device()
 
     @property
     def n_cols(self) -> int:
@@ -746,18 +872,9 @@ def create_polynomials_fft_qap(ctx: Context, g: GenQAP, target_full_domain: bool
         N <<= 1
     cols = _dense_columns(g, N)
     polys = [ctx.interpolate_columns(c) if N > 1 else c for c in cols]
-    r = field_constants(g.field)["modulus"]
-    if target_full_domain or g.n_rows == N:
-        target = strip([r - 1] + [0] * (N - 1) + [1])
-    else:  # prod_{i < n} (X - omega^i)  (the convention switch of DESIGN.md section 3)
-        k = N.bit_length() - 1
-        omega, x, target = get_root_of_unity(g.field, k), 1, [1]
-        for _ in range(g.n_rows):
-            nxt = [0] * (len(target) + 1)
-            for i, c in enumerate(target):
-                nxt[i] = (nxt[i] - x * c) % r
-                nxt[i + 1] = (nxt[i + 1] + c) % r
-            target, x = nxt, x * omega % r
+    # FFT.fftTargetPoly (src/QAP.hs:524): prod_{i < n} (X - omega^i), or X^N - 1 with the convention switch of
+    # DESIGN.md section 3 (identical when n is a power of two)
+    target = ctx.fft_target(N if target_full_domain else g.n_rows)
     return QAP(g.field, g.layout, g.n_rows, polys[0], polys[1], polys[2], target, "fft")
 
 
@@ -790,65 +907,21 @@ def arith_circuit_to_qap(ctx: Context, circuit: ArithCircuit, roots: Optional[Se
     return create_polynomials_qap(ctx, arith_circuit_to_gen_qap(circuit, roots, root_start))
 
 
-def _combine(ctx: Context, arr: np.ndarray, w: np.ndarray) -> np.ndarray:
-    out = np.zeros((arr.shape[1], 4), np.uint64)
-    _check(_lib.lib().acg_poly_combine(ctx._h, _ptr(np.ascontiguousarray(arr)), _ptr(np.ascontiguousarray(w)),
-                                       arr.shape[0], arr.shape[1], _ptr(out)), ctx)
-    return out
-
-
 def verification_witness_zk_qap(ctx: Context, d1: int, d2: int, d3: int, qap: QAP, assignment: QapSet):
-    """verificationWitnessZk (src/QAP.hs:300-327) on a per-wire QAP value: a = d1*T + sum_k w_k L_k (device scale-and-sum,
-    acg_poly_combine), likewise b, c; then p = a*b - c and the exact division by T.
-      * FFT-built QAP whose row count is a power of two (T = X^N - 1): evaluations by forward NTT, the product on a
-        2N-point domain, p = h*X^N - h  =>  h is the upper half; the delta terms enter as
-        h_zk = h + d2*a + d1*b + d1*d2*T - d3 (expand (a + d1 T)(b + d2 T) - (c + d3 T)).
-      * otherwise (Lagrange build, or a padded FFT build): validity by evaluating a, b, c at the target's roots on the
-        host (small systems only: n_rows <= 512); h is then not produced here -- use the GenQAP form.
-    Returns `h` (stripped coefficient list), or None when T does not divide p; for the second case True/None."""
-    r = field_constants(qap.field)["modulus"]
-    w = assignment.to_vector(qap.layout)
-    a, b, c = (_combine(ctx, arr, w) for arr in (qap.left, qap.right, qap.out))
-    N = a.shape[0]
-    if qap.kind == "fft" and qap.n_rows == N:
-        if N == 1:
-            av, bv, cv = from_limbs(a)[0], from_limbs(b)[0], from_limbs(c)[0]
-            if (av * bv - cv) % r:
-                return None
-            h = []
-        else:
-            ea, eb, ec = ctx.ntt(a, False), ctx.ntt(b, False), ctx.ntt(c, False)
-            resid = ctx.fr_binop(1, ctx.fr_binop(2, ea, eb), ec)
-            if resid.any():
-                return None
-            pad = lambda v: np.concatenate([v, np.zeros_like(v)])
-            e2 = [ctx.ntt(pad(v), False) for v in (a, b, c)]
-            p = ctx.ntt(ctx.fr_binop(1, ctx.fr_binop(2, e2[0], e2[1]), e2[2]), True)
-            h = from_limbs(p[N:])
-        ai, bi = from_limbs(a), from_limbs(b)
-        hz = [0] * (N + 1)
-        for i in range(N):
-            hz[i] = ((h[i] if i < len(h) else 0) + d2 * ai[i] + d1 * bi[i]) % r
-        hz[0] = (hz[0] - d3 - d1 * d2) % r      # d1*d2*T = d1*d2*(X^N - 1)
-        hz[N] = (hz[N] + d1 * d2) % r
-        return strip(hz)
-    if qap.n_rows > 512:
-        raise AcgError(-6, "verification on a per-wire QAP with arbitrary roots is limited to 512 rows; use the GenQAP form")
-    if qap.kind == "fft":
-        omega = get_root_of_unity(qap.field, N.bit_length() - 1)
-        roots = [pow(omega, i, r) for i in range(qap.n_rows)]
-    else:
-        roots = [x % r for x in qap.roots]
-    ai, bi, ci = from_limbs(a), from_limbs(b), from_limbs(c)
-
-    def horner(p, x):
-        acc = 0
-        for coef in reversed(p):
-            acc = (acc * x + coef) % r
-        return acc
-    # T vanishes on its roots, so the delta terms do not change the verdict
-    ok = all((horner(ai, x) * horner(bi, x) - horner(ci, x)) % r == 0 for x in roots)
-    return True if ok else None
+    """verificationWitnessZk (src/QAP.hs:300-327) on a per-wire QAP value, one C call (acg_qap_verify), everything on
+    the device: a = d1*T + sum_k w_k L_k (scale-and-sum), likewise b, c; p = a*b - c by an NTT product; (h, rem) =
+    p divMod T by long division for a target of any shape (prod (X - root) of the Lagrange build, fftTargetPoly,
+    X^N - 1).  Returns `h` (stripped coefficient list, the reference's `Just quotient`) or None when rem != 0.
+    A wire the assignment lacks counts as 0 and a wire the QAP lacks as the zero polynomial (combineWithDefaults,
+    src/QAP.hs:163-181): assignment keys beyond the QAP's layout are dropped."""
+    w = witness_vector(assignment, qap.layout)
+    h_dev = qap.device_handle(ctx)
+    cap = _lib.lib().acg_qap_quotient_len(h_dev)
+    h = np.zeros((max(cap, 1), 4), np.uint64)
+    delta = to_limbs([d1, d2, d3])
+    n, div = C.c_uint32(), C.c_int()
+    _check(_lib.lib().acg_qap_verify(ctx._h, h_dev, _ptr(w), _ptr(delta), _ptr(h), cap, C.byref(n), C.byref(div)), ctx)
+    return strip(from_limbs(h[:n.value])) if div.value else None
 
 
 def verify_assignment_qap(ctx: Context, qap: QAP, assignment: QapSet) -> bool:

@@ -76,6 +76,38 @@ def upload_witness_sliced(dw, w_host: np.ndarray, group=None, dw_bytes=None):
             dist.broadcast(t[a * 32:b * 32], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
 
 
+def gather_plan(n: int, world: int):
+    """How a vector of n elements is exchanged between `world` ranks with ONE all-gather: equal slices of
+    n // world elements (rank r owns [r * s, (r + 1) * s)) plus a remainder of n % world elements at the end that every
+    rank uploads itself.  Returns (slice length, remainder start)."""
+    s = n // world
+    return s, s * world
+
+
+def upload_witness_allgather(dw, w_host: np.ndarray, stream, group=None, dw_bytes=None):
+    """New witness for every rank of a row-sharded check, enqueue only: rank r copies ITS slice of `w_host` (canonical
+    limbs, pinned, the same array on every rank) to its device vector over its own PCIe link on the library's copy
+    stream (acg_witness_update_async: range check + Montgomery conversion on the device), `stream` (a torch CUDA stream)
+    waits for that copy, and ONE in-place NCCL all-gather over NVLink completes the vector on every rank.  With two
+    device vectors used alternately the host-to-device copy of witness i + 1 overlaps the all-gather and the check of
+    witness i.  The check that follows must be enqueued on `stream`."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = len(dw)
+    t = dw_bytes if dw_bytes is not None else dw.as_torch_bytes()
+    s, rem0 = gather_plan(n, world)
+    if s:
+        dw.update_async(w_host[rank * s:(rank + 1) * s], rank * s)
+    if rem0 < n:
+        dw.update_async(w_host[rem0:], rem0)
+    dw.stream_wait(stream.cuda_stream)
+    if s:
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(t[:world * s * 32], t[rank * s * 32:(rank + 1) * s * 32], group=group)
+
+
 def reduce_check_result(result, group=None):
     """result: int64 tensor [n_violations, first_bad_row] (first_bad_row = -1, i.e. UINT64_MAX, when the
     shard is clean), on the device of the process group's backend.  Returns (total violations, first bad

@@ -2,28 +2,37 @@
 """Benchmark of the hot path: R1CS witness check (A.w o B.w - C.w == 0 over BN254 Fr) on synthetic
 circuits S(n, seed, field) of SURVEY.md 8(d).  Metric: R1CS constraints / second.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log-rows 20] [--field bn254]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log-rows L] [--field bn254]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-One "step" = one check of every constraint of the (sharded) system.  Weak scaling: each rank owns
-2^log_rows consecutive rows of a global system of N * 2^log_rows rows (witness replicated), checks
-them with the tiled CUDA kernel -- ONE kernel launch per step: the kernel's last CTA finalises the result pair
-and, for N > 1, all-reduces it over peer memory (NVLink P2P stores; `--collective nccl` uses one NCCL all-reduce).
+Workload.  N = 1: BASELINE configs[1], S(2^20, 20260002, BN254) on one GPU.  N > 1: BASELINE configs[3], STRONG
+scaling: S(2^24, 20260004, BN254), rows split in N contiguous blocks, witness replicated (`--scaling weak --log-rows L`
+gives 2^L rows per GPU instead).  `--workload mix`: a circuit with the reference generator's gate mix (Mul : Equal :
+Split = 50 : 10 : 1, 256-bit Split rows) instead of the Split-free family.
 
-  value     device-resident throughput: K steps timed with CUDA events on the launching stream, barrier +
-            synchronize on both sides, max over ranks.
-  e2e       same metric end to end per witness: the system stays resident on the device (the reference keeps its
-            QAP value in memory between calls, too) and every step copies a new witness from pinned host memory
-            (acg_witness_update: H2D, range check, Montgomery conversion), checks it and reads the result pair back.
-            e2e.one_shot: everything from host buffers every step (acg_r1cs_check_host: pinned host CSR + witness
-            -> H2D -> kernels -> D2H), PCIe-bound.
-  roofline  tiled check kernel: SURVEY 8(d) algorithmic bytes of the shard / average per-launch duration (CUDA
-            event pairs around every 8th launch inside the timed region; bounded by the step time, a step being
-            exactly one launch) vs MEASURED_PEAKS.json.
+One "step" = one check of every constraint of the (sharded) system = ONE launch of the tiled CUDA kernel per rank (the
+kernel's last CTA finalises the result pair and, for N > 1, all-reduces it over peer memory -- NVLink P2P stores;
+`--collective nccl` uses one NCCL all-reduce instead).
+
+  value     device-resident throughput: K steps between CUDA events on the launching stream, barrier + synchronize on
+            both sides, max over ranks.  The steps alternate between two resident witnesses and consecutive checks
+            overlap (acg_ctx_set_overlap_checks, opt-in: the next check kernel is a programmatic dependent launch).
+  roofline  k_r1cs_tiled: SURVEY 8(d) algorithmic bytes of the shard / the ISOLATED per-launch duration -- a second
+            timed region of K plain launches, each bracketed by its own CUDA event pair on the launching stream
+            (acg_profile_begin/end) -- vs MEASURED_PEAKS.json.  frac_overlapped is the same with the step time of the
+            first region.
+  e2e       same metric end to end per witness through the C ABI with HOST buffers: the system stays resident on the
+            device (the reference keeps its QAP value in memory between calls, too); every step copies a new witness
+            from pinned host memory (acg_witness_update_async on the copy stream: H2D, range check, Montgomery
+            conversion; two device vectors, so the copy of witness i + 1 overlaps the check of witness i), checks it
+            and reads the result pair back.  N > 1: every rank copies 1/N of the witness over its own PCIe link and one
+            NCCL all-gather over NVLink completes it.  e2e.one_shot: everything from host buffers every step.
   cpu_baseline / --impl reference
             the oracle's C restatement of the reference algorithm (oracle/r1cs_oracle.c, "port": the Haskell
             reference cannot be built in this image) on the host cores.
+  qap       (N = 1) BASELINE configs[2] as a secondary object: acg_qap_witness on S(2^22, 20260003): wall and kernel
+            time of the call, h checked against the C oracle.
 """
 from __future__ import annotations
 
@@ -49,25 +58,48 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--log-rows", type=int, default=20, help="log2 of constraints per GPU")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"],
+                    help="auto: N = 1 -> 2^20 rows; N > 1 -> strong scaling of 2^24 rows (BASELINE configs[3])")
+    ap.add_argument("--log-rows", type=int, default=0,
+                    help="log2 of constraints: per GPU (weak) or in total (strong); 0 = 20 / 24 per --scaling")
     ap.add_argument("--field", default="bn254", choices=list(FIELD_IDS))
+    ap.add_argument("--workload", default="s", choices=["s", "mix"],
+                    help="s: family S(n) of SURVEY 8(d); mix: the reference generator's gate mix with 256-bit Split gates")
     ap.add_argument("--dense", action="store_true", help="all coefficients uniform (stress variant)")
     ap.add_argument("--kernel", default="tiled", choices=["tiled", "rowwise"])
     ap.add_argument("--no-overlap", action="store_true",
-                    help="do not overlap consecutive checks (programmatic dependent launch of the next check kernel)")
+                    help="first timed region: do not overlap consecutive checks (plain launches)")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: all-reduce of the result pair over peer memory (default) or by NCCL")
     ap.add_argument("--variant", type=int, default=0, choices=list(range(8)), help="tiled kernel geometry (kernels.h kTileGeom): 0-3 rows per tile 128/256/64/32, 4/5 = 128/64 with the natural term layout, 6 = products in place, 7 = 6 + one far buffer (6 CTAs per SM)")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = max(steps, 20) capped at 50")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-qap", action="store_true", help="skip the secondary configs[2] measurement (N = 1)")
+    ap.add_argument("--no-one-shot", action="store_true", help="skip e2e.one_shot")
     return ap.parse_args()
 
 
+def plan(args, world):
+    """(rows in total, rows per rank or None, seed, scaling label)"""
+    scaling = args.scaling
+    if scaling == "auto":
+        scaling = "strong" if world > 1 else "weak"
+    if scaling == "strong":
+        log_total = args.log_rows or (24 if world > 1 else 20)
+        total = 1 << log_total
+        return total, SEEDS.get(log_total, 20260000 + log_total), scaling
+    log_per = args.log_rows or 20
+    total = world << log_per
+    return total, SEEDS.get(log_per, 20260000 + log_per), scaling
+
+
 def workload_name(args, world):
-    total = world << args.log_rows
-    return "S(n=%d, seed=%d, %s%s): %d Mul-gate R1CS rows, ~5.5 nnz/row, %d rows/GPU, witness replicated" % (
-        total, SEEDS.get(args.log_rows, 20260000 + args.log_rows), args.field, ", dense" if args.dense else "", total,
-        1 << args.log_rows)
+    total, seed, scaling = plan(args, world)
+    if args.workload == "mix":
+        return "M(n>=%d, seed=%d, %s): gate mix of the reference generator (Mul:Equal:Split = 50:10:1, 256-bit Split rows), %d GPU(s)" % (
+            total, seed, args.field, world)
+    return "S(n=%d, seed=%d, %s%s): %d Mul-gate R1CS rows, ~5.5 nnz/row, split in %d contiguous row block(s) (%s scaling), witness replicated" % (
+        total, seed, args.field, ", dense" if args.dense else "", total, world, scaling)
 
 
 def host_threads():
@@ -158,6 +190,22 @@ def cpu_check_throughput(g, w, field_id, n_threads, min_seconds, max_reps):
     return g.n_rows / min(times), times
 
 
+def make_workload(acg, args, world, rank):
+    """-> (GenQAP of this rank's rows, full honest witness, (row_begin, row_end), total rows, generate seconds)"""
+    from arithmetic_circuits_b200 import sharding
+    field_id = FIELD_IDS[args.field]
+    total, seed, _ = plan(args, world)
+    t0 = time.perf_counter()
+    if args.workload == "mix":
+        if world > 1:
+            raise SystemExit("bench.py: --workload mix is a single-GPU workload")
+        g, w = acg.synth_mixed_r1cs(field_id, total, seed)
+        return g, w, (0, g.n_rows), g.n_rows, time.perf_counter() - t0
+    rb, re = sharding.row_shard(total, world, rank)
+    g, w = acg.synth_r1cs(field_id, total, seed, args.dense, rows=(rb, re))
+    return g, w, (rb, re), total, time.perf_counter() - t0
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port; the Haskell original has no toolchain
     here) on rank 0's host cores, all threads, same workload and metric."""
@@ -167,11 +215,8 @@ def run_reference(args, rank, world):
     from oracle import c_oracle as CO
     CO.build()
     field_id = FIELD_IDS[args.field]
-    n = 1 << args.log_rows
-    total = world * n
-    seed = SEEDS.get(args.log_rows, 20260000 + args.log_rows)
-    # the bounded sample: rank 0's shard of the global system (all of it at N = 1)
-    g, w = acg.synth_r1cs(field_id, total, seed, args.dense, rows=(0, n))
+    # the bounded sample: rank 0's row block of the system (all of it at N = 1)
+    g, w, (rb, re), total, _ = make_workload(acg, args, world, 0)
     threads = host_threads()   # torchrun exports OMP_NUM_THREADS=1: ask for every host thread explicitly
     mats = [(m[0], m[1], m[2]) for m in g.mats]
     for _ in range(max(1, min(args.warmup, 3))):
@@ -186,11 +231,12 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "R1CS constraints/sec (BN254 Fr)" if field_id == 0 else "R1CS constraints/sec (BLS12-381 Fr)",
         "value": value, "unit": "constraints/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": plan(args, world)[2], "vs_baseline": None,
         "dtype": "u256 (4x64-bit Montgomery, unsigned __int128)", "data": "synthetic",
-        "config": {"workload": workload_name(args, world), "note": "CPU arm checks one shard (2^%d rows) per step on rank 0" % args.log_rows},
+        "config": {"workload": workload_name(args, world),
+                   "note": "CPU arm checks one row block (%d rows: 1/%d of the system) per step on rank 0" % (g.n_rows, world)},
         "cpu_baseline": {"value": value, "unit": "constraints/s", "cores": threads, "kind": "port",
-                         "sample": "%d full checks of a 2^%d-row shard, OpenMP over rows" % (steps, args.log_rows)},
+                         "sample": "%d full checks of a %d-row block, OpenMP over rows" % (steps, g.n_rows)},
         "e2e": {"value": value, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -200,6 +246,58 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+def qap_secondary(acg, ctx, field_id):
+    """BASELINE configs[2]: S(2^22, 20260003) -- acg_qap_witness (check + A.w, B.w, C.w + 7 NTTs of 2^22 points + coset
+    quotient): wall and kernel time of the call with pinned host outputs, h compared with the C oracle."""
+    import numpy as np
+    import torch
+    from oracle import c_oracle as CO
+    n = 1 << 22
+    g, w = acg.synth_r1cs(field_id, n, SEEDS[22])
+    m, dw = ctx.upload_r1cs(g), ctx.upload_witness(w)
+    h_pin = torch.empty((n + 1, 4), dtype=torch.int64).pin_memory()
+    L = acg._lib.lib()
+    import ctypes as C
+    div = C.c_int()
+    hp = C.c_void_p(h_pin.data_ptr())
+
+    def call():
+        acg.qap._check(L.acg_qap_witness(ctx._h, m._h, dw._h, None, None, None, None, hp, C.byref(div)), ctx)
+    call()
+    walls, kernels = [], []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        call()
+        walls.append(1e3 * (time.perf_counter() - t0))
+        kernels.append(ctx.last_timing()["kernel_ms"])
+    ref = CO.r1cs_eval_check(field_id, g.n_rows, g.n_cols, *[(x[0], x[1], x[2]) for x in g.mats], w, True, host_threads())
+    t0 = time.perf_counter()
+    _a, _b, _c, h_ref, ok_ref = CO.qap_witness(field_id, ref["Aw"], ref["Bw"], ref["Cw"], (0, 0, 0), host_threads())
+    cpu_s = time.perf_counter() - t0
+    exact = bool(div.value) and ok_ref and bool((h_pin.numpy().view(np.uint64) == h_ref).all())
+    # isolated 2^22-point NTT (device resident, natural order in and out)
+    stream = torch.cuda.current_stream()
+    dv = ctx.upload_witness(w[:n])
+    ntt_ms = []
+    for i in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        acg.qap._check(L.acg_ntt_device(ctx._h, dv._h, 22, i & 1, C.c_void_p(stream.cuda_stream)), ctx)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ntt_ms.append(e0.elapsed_time(e1))
+    dv.free()
+    out = {"workload": "S(n=%d, seed=%d): acg_qap_witness = R1CS check + A.w, B.w, C.w + 7 NTTs of 2^22 points + coset quotient -> h" % (n, SEEDS[22]),
+           "wall_ms": min(walls), "kernel_ms": min(kernels), "wall_over_kernel": min(walls) / min(kernels),
+           "d2h_bytes": int(h_pin.numel() * 8), "h_bit_exact_vs_oracle": exact,
+           "ntt_2p22_ms": min(ntt_ms[1:]), "cpu_oracle_s": cpu_s, "cpu_threads": host_threads(),
+           "constraints_per_s": n / (min(walls) * 1e-3)}
+    dw.free()
+    m.free()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -214,20 +312,17 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     field_id = FIELD_IDS[args.field]
-    n = 1 << args.log_rows
-    total = world * n
-    seed = SEEDS.get(args.log_rows, 20260000 + args.log_rows)
-    rb, re = sharding.row_shard(total, world, rank)
-    t_gen = time.perf_counter()
-    g, w = acg.synth_r1cs(field_id, total, seed, args.dense, rows=(rb, re))
-    t_gen = time.perf_counter() - t_gen
+    scaling = plan(args, world)[2]
+    g, w, (rb, re), total, t_gen = make_workload(acg, args, world, rank)
 
     ctx = acg.Context(field_id, local_rank)
     ctx.set_check_kernel(acg.CHECK_TILED if args.kernel == "tiled" else acg.CHECK_ROWWISE)
     ctx.set_tiled_variant(args.variant)
-    ctx.set_overlap_checks(not args.no_overlap)
+    t_up = time.perf_counter()
     m = ctx.upload_r1cs(g)
-    dw = ctx.upload_witness(w)
+    m.set_row_offset(rb)   # this rank's rows are [rb, re) of the global system
+    t_up = time.perf_counter() - t_up
+    dws = [ctx.upload_witness(w), ctx.upload_witness(w)]   # two resident witnesses, checked alternately
     algo_bytes = m.algorithmic_bytes
     if world > 1:  # shards differ (later rows reference a larger part of the witness): the mean over the ranks
         tb = torch.tensor([float(algo_bytes)], dtype=torch.float64, device=dev)
@@ -253,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
             if int(ok.item()) == 0:
                 peer, collective = None, "nccl"
 
-    def step():
+    def step(dw):
         if peer is not None:
             ctx.r1cs_check_async_allreduce(m, dw, peer, result.data_ptr(), stream.cuda_stream)
             return
@@ -261,20 +356,41 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(result[0:1], op=dist.ReduceOp.SUM)
 
+    # ---- N > 1: correctness of the fused all-reduce before anything is timed: a tampered witness must give, on every
+    # rank, the global (count, first bad row) the CPU oracle finds over the shards
+    peer_check = None
+    if world > 1:
+        from oracle import c_oracle as CO
+        CO.build()
+        wb = w.copy()
+        wb[1025 + total // 3, 0] += np.uint64(1)      # SURVEY 8(d) negative variant
+        wb[1025 + 7, 1] ^= np.uint64(1 << 5)          # .. and one wire every shard references
+        ref = CO.r1cs_eval_check(field_id, g.n_rows, g.n_cols, *[(x[0], x[1], x[2]) for x in g.mats], wb, False, 8)
+        loc = torch.tensor([ref["n_violations"], (rb + ref["first_bad_row"]) if ref["first_bad_row"] >= 0 else (1 << 62)],
+                           dtype=torch.int64, device=dev)
+        cnt, first = loc[0:1].clone(), loc[1:2].clone()
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(first, op=dist.ReduceOp.MIN)
+        dws[1].update(wb)
+        step(dws[1])
+        torch.cuda.synchronize()
+        want = (int(cnt.item()), int(first.item()))
+        got = (int(result[0].item()), int(result[1].item()) if peer is not None else want[1])  # (NCCL path: count only)
+        assert got == want and want[0] > 0, "rank %d: all-reduced result %r != oracle %r" % (rank, got, want)
+        peer_check = {"tampered_witness": {"violations": got[0], "first_bad_row": got[1]},
+                      "cpu_oracle_over_all_shards": {"violations": want[0], "first_bad_row": want[1]},
+                      "asserted_equal_on_every_rank": True, "collective": collective}
+        dws[1].update(w)
+
     sampler = ClockSampler(local_rank)
-    for _ in range(max(args.warmup, 3)):
-        step()
+    ctx.set_overlap_checks(not args.no_overlap)
+    for i in range(max(args.warmup, 3)):
+        step(dws[i & 1])
     torch.cuda.synchronize()
     assert int(result[0].item()) == 0, "honest witness must verify"
 
-    # ---- device-resident timed region.  One step is ONE kernel launch (the check kernel finalises its own result
-    # and, for N > 1, all-reduces it over peer memory in its last CTA), so consecutive steps run back to back.
-    # Per-launch durations are sampled with CUDA event pairs on the launching stream around every 8th step: an
-    # event pair around EVERY launch costs ~6 us of front-end time per step (measured), i.e. it would perturb the
-    # very number it measures.
+    # ---- timed region 1 (value): K steps back to back, alternating the two resident witnesses; one launch per step
     launches0 = ctx.kernel_launch_count()
-    sample_every = 8
-    pairs = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
@@ -282,20 +398,12 @@ def run_ours(args, rank, world, local_rank):
     sampler.start()
     e0.record(stream)
     for i in range(args.steps):
-        if i % sample_every == sample_every // 2:
-            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ea.record(stream)
-            step()
-            eb.record(stream)
-            pairs.append((ea, eb))
-        else:
-            step()
+        step(dws[i & 1])
     e1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     total_ms = e0.elapsed_time(e1)
-    kernel_ms = [a.elapsed_time(b) for a, b in pairs]
     launches = ctx.kernel_launch_count() - launches0
     assert int(result[0].item()) == 0
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -304,152 +412,192 @@ def run_ours(args, rank, world, local_rank):
     total_ms = float(t.item())
     value = total * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the host-buffer call (pinned host inputs, H2D + D2H every step)
-    e2e_steps = args.e2e_steps or max(1, min(args.steps, 5))
+    # ---- timed region 2 (roofline): the ISOLATED launch duration of the check kernel -- K plain launches (no overlap of
+    # consecutive checks) of the local shard, back to back between two CUDA events on the launching stream: the average
+    # launch duration over the timed region, launch gaps included.  For N > 1 this is the local shard without the peer
+    # exchange, i.e. the per-rank kernel time without the epilogue spin.  A few launches are also bracketed one by one
+    # by their own event pair (acg_profile_begin/end; the pair adds ~3 us of event latency to what it brackets).
+    ctx.set_overlap_checks(False)
+    k_iso = max(args.steps, 10)
+    for i in range(3):
+        ctx.r1cs_check_async(m, dws[i & 1], result.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    l_iso0 = ctx.kernel_launch_count()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for i in range(k_iso):
+        ctx.r1cs_check_async(m, dws[i & 1], result.data_ptr(), stream.cuda_stream)
+    f1.record(stream)
+    torch.cuda.synchronize()
+    iso_ms = f0.elapsed_time(f1) / k_iso
+    launches_per_check = (ctx.kernel_launch_count() - l_iso0) / k_iso
+    k_pair = min(k_iso, 16)
+    ctx.profile_begin(k_pair)
+    for i in range(k_pair):
+        ctx.r1cs_check_async(m, dws[i & 1], result.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    kernel_ms = ctx.profile_end(k_pair)
+    per_rank_ms = [iso_ms]
+    if world > 1:
+        tt = torch.tensor([iso_ms], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allr, tt)
+        per_rank_ms = [float(x.item()) for x in allr]
+        iso_ms = max(per_rank_ms)   # the slowest shard bounds the step
+
+    # ---- end to end, one shot: everything from pinned host buffers every step (PCIe-bound)
+    e2e_steps = min(max(args.e2e_steps or max(args.steps, 20), 1), 50)
     pinned = []
-    mats = []
-    for rp, col, val in g.mats:
-        trip = []
-        for a in (rp, col, val):
-            tt = torch.from_numpy(np.ascontiguousarray(a).view(np.int32 if a.dtype == np.uint32 else np.int64)).pin_memory()
-            pinned.append(tt)
-            trip.append(tt.numpy().view(a.dtype).reshape(a.shape))
-        mats.append(tuple(trip))
+    one_shot = None
     wt = torch.from_numpy(w.view(np.int64)).pin_memory()
     pinned.append(wt)
-    gp = acg.GenQAP(field_id, g.n_rows, g.n_cols, g.layout, mats)
     wp = wt.numpy().view(np.uint64)
-    h2d_bytes = sum(int(a.nbytes) for tr in mats for a in tr) + int(wp.nbytes)
-    ctx.r1cs_check_host(gp, wp)  # warm-up (allocator, page tables)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    l_e2e0 = ctx.kernel_launch_count()
-    for _ in range(e2e_steps):
-        nv, _fb = ctx.r1cs_check_host(gp, wp)
-        assert nv == 0
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    l_e2e = ctx.kernel_launch_count() - l_e2e0
-    sampler.stop()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_value = total * e2e_steps / e2e_s
-    # the end-to-end step of a prover: the circuit (the R1CS) is resident on the device -- as the reference keeps its QAP
-    # value in memory between calls of verifyAssignment -- and every step brings a new witness from pinned host memory
-    # (H2D + canonical-range check + Montgomery conversion), checks it and reads the result pair back (D2H).
-    # N > 1: every rank uploads only its slice of the new witness over its own PCIe link and the slices are exchanged
-    # over NVLink (sharding.upload_witness_sliced); falls back to a full upload per rank if that is unavailable
+    if not args.no_one_shot and world == 1:
+        mats = []
+        for rp, col, val in g.mats:
+            trip = []
+            for a in (rp, col, val):
+                tt = torch.from_numpy(np.ascontiguousarray(a).view(np.int32 if a.dtype == np.uint32 else np.int64)).pin_memory()
+                pinned.append(tt)
+                trip.append(tt.numpy().view(a.dtype).reshape(a.shape))
+            mats.append(tuple(trip))
+        gp = acg.GenQAP(field_id, g.n_rows, g.n_cols, g.layout, mats)
+        h2d_bytes = sum(int(a.nbytes) for tr in mats for a in tr) + int(wp.nbytes)
+        ctx.r1cs_check_host(gp, wp)  # warm-up (allocator, page tables)
+        torch.cuda.synchronize()
+        os_steps = min(e2e_steps, 5)
+        t0 = time.perf_counter()
+        l0 = ctx.kernel_launch_count()
+        for _ in range(os_steps):
+            nv, _fb = ctx.r1cs_check_host(gp, wp)
+            assert nv == 0
+        torch.cuda.synchronize()
+        os_s = time.perf_counter() - t0
+        one_shot = {"value": total * os_steps / os_s, "unit": "constraints/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 16, "steps": os_steps, "ms_per_step": 1e3 * os_s / os_steps,
+                    "gpu_launches": ctx.kernel_launch_count() - l0,
+                    "call": "acg_r1cs_check_host: CSR matrices AND witness from pinned host memory every step (PCIe-bound)"}
+
+    # ---- end to end per witness (the headline): the circuit is resident on the device -- as the reference keeps its QAP
+    # value in memory between calls of verifyAssignment -- and every step brings a NEW witness from pinned host memory
+    # through the C ABI (H2D + range check + Montgomery conversion), checks it and reads the result pair back (D2H).
+    # Two device vectors: the copy of witness i + 1 (copy stream) overlaps the check of witness i.
+    # N > 1: every rank copies only its 1/N slice over its own PCIe link; one NCCL all-gather over NVLink completes it.
+    wt2 = torch.from_numpy(w.view(np.int64).copy()).pin_memory()   # a second host witness (same values, other buffer)
+    pinned.append(wt2)
+    hosts = [wp.reshape(-1, 4), wt2.numpy().view(np.uint64).reshape(-1, 4)]
     sliced = world > 1
-    dw_bytes = None
-    if sliced:
-        try:
-            dw_bytes = dw.as_torch_bytes()
-            sharding.upload_witness_sliced(dw, wp.reshape(-1, 4), None, dw_bytes)
-            torch.cuda.synchronize()
-        except Exception as e:
-            sys.stderr.write("bench.py: sliced witness upload unavailable (%s); every rank uploads the whole witness\n" % (e,))
-            sliced = False
-        ok = torch.tensor([1 if sliced else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        sliced = bool(int(ok.item()))
+    views = [d.as_torch_bytes() for d in dws] if sliced else None
 
-    def e2e_witness_step():
+    def e2e_upload(i):
         if sliced:
-            sharding.upload_witness_sliced(dw, wp.reshape(-1, 4), None, dw_bytes)
+            sharding.upload_witness_allgather(dws[i & 1], hosts[i & 1], stream, None, views[i & 1])
         else:
-            dw.update(wp)
-        if peer is not None:
-            ctx.r1cs_check_async_allreduce(m, dw, peer, result.data_ptr(), stream.cuda_stream)
-            return int(result[0].item())
-        if world > 1:
-            ctx.r1cs_check_async(m, dw, result.data_ptr(), stream.cuda_stream)
-            dist.all_reduce(result[0:1], op=dist.ReduceOp.SUM)
-            return int(result[0].item())
-        return ctx.r1cs_check(m, dw)[0]
+            dws[i & 1].update_async(hosts[i & 1])
 
-    e2e_w_steps = max(e2e_steps, 20) if not args.e2e_steps else e2e_steps
-    assert e2e_witness_step() == 0
+    host_res = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(2)]
+    done_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_enqueue_check(i):   # check of witness i + read-back of the result pair, enqueue only
+        if peer is not None:
+            ctx.r1cs_check_async_allreduce(m, dws[i & 1], peer, result.data_ptr(), stream.cuda_stream)
+        else:
+            ctx.r1cs_check_async(m, dws[i & 1], result.data_ptr(), stream.cuda_stream)
+            if world > 1:
+                dist.all_reduce(result[0:1], op=dist.ReduceOp.SUM)
+        host_res[i & 1].copy_(result, non_blocking=True)
+        done_ev[i & 1].record(stream)
+
+    def e2e_run(k):
+        e2e_upload(0)
+        for i in range(k):
+            e2e_enqueue_check(i)
+            if i + 1 < k:
+                e2e_upload(i + 1)       # enqueue only: the copy overlaps the check just enqueued
+            done_ev[i & 1].synchronize()   # the step's result is on the host
+            assert int(host_res[i & 1][0]) == 0
+    e2e_run(3)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     l_w0 = ctx.kernel_launch_count()
     t0 = time.perf_counter()
-    for _ in range(e2e_w_steps):
-        assert e2e_witness_step() == 0
+    e2e_run(e2e_steps)
     torch.cuda.synchronize()
     e2e_w_s = time.perf_counter() - t0
     l_w = ctx.kernel_launch_count() - l_w0
+    for d in dws:
+        d.status()   # (raises if an asynchronous update had met a non-canonical element)
+    sampler.stop()
     t = torch.tensor([e2e_w_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_w_s = float(t.item())
-    e2e_w_value = total * e2e_w_steps / e2e_w_s
+    e2e_w_value = total * e2e_steps / e2e_w_s
 
     if rank == 0:
         peak, peak_src, sm_max = measured_peaks()
         # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of this same command
-        # (profiles/r01_ncu_summary.json; never measured under the profiler here), only for the default workload
-        traffic = None
-        if world == 1 and args.log_rows == 20 and args.field == "bn254" and not args.dense and args.kernel == "tiled":
-            try:
-                with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as f:
-                    k2 = json.load(f)["k2_r1cs_tiled"][0]
-                traffic = (float(k2["dram__bytes_read.sum"]) + float(k2["dram__bytes_write.sum"])) * 1e6
-            except Exception:
-                traffic = None
-        # average launch duration of the dominant kernel: the sampled event pairs (each pair adds ~3 us of event
-        # latency to what it brackets), bounded by the step time when a step is exactly one launch of that kernel
-        k_ms = statistics.mean(kernel_ms) if kernel_ms else float("nan")
-        one_launch_per_step = launches == args.steps
-        if one_launch_per_step and (not kernel_ms or total_ms / args.steps < k_ms):
-            k_ms = total_ms / args.steps
-        achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+        # (never measured under the profiler here), only for the default workload
+        traffic, traffic_src = None, None
+        if world == 1 and total == (1 << 20) and args.field == "bn254" and not args.dense and args.kernel == "tiled" \
+                and args.workload == "s":
+            for name in ("r02_ncu_summary.json", "r01_ncu_summary.json"):
+                try:
+                    with open(os.path.join(ROOT, "profiles", name)) as f:
+                        k2 = json.load(f)["k2_r1cs_tiled"][0]
+                    traffic = (float(k2["dram__bytes_read.sum"]) + float(k2["dram__bytes_write.sum"])) * 1e6
+                    traffic_src = "profiles/%s (committed ncu --set full capture of this command; not measured in this run)" % name
+                    break
+                except Exception:
+                    continue
+        step_ms = total_ms / args.steps
+        achieved = algo_bytes / (iso_ms * 1e-3) / 1e9
+        achieved_ovl = algo_bytes / (step_ms * 1e-3) / 1e9
         line = {
             "metric": "R1CS constraints/sec (BN254 Fr)" if field_id == 0 else "R1CS constraints/sec (BLS12-381 Fr)",
             "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "u256 (8x32-bit-limb Montgomery Fr, integer)", "data": "synthetic",
             "config": {"workload": workload_name(args, world), "kernel": args.kernel, "tiled_variant": args.variant,
-                       "overlap": "consecutive checks overlap (next check kernel launched as a programmatic dependent)"
-                                  if not args.no_overlap else "off",
+                       "rows_per_gpu": g.n_rows,
+                       "timed_region": "K checks back to back, alternating two resident witnesses; "
+                                       + ("consecutive checks overlap (opt-in acg_ctx_set_overlap_checks: programmatic dependent launch)"
+                                          if not args.no_overlap else "plain launches (no overlap)"),
                        "l2": "inputs streamed per step (%.0f MB CSR + %.0f MB witness per GPU) exceed the 126 MB L2; no explicit flush"
                              % ((sum(36 * k for k in g.nnz) + 12 * (g.n_rows + 1)) / 1e6, 32 * g.n_cols / 1e6),
-                       "parallelism": "rows sharded over %d rank(s), 1 all-reduce of the result pair per step (%s)" % (
+                       "parallelism": "rows split over %d rank(s), 1 all-reduce of the result pair per step (%s)" % (
                            world, {"p2p": "fused: the check kernel's last CTA stores the pair into every peer's memory over NVLink (CUDA IPC) and reduces", "nccl": "NCCL",
                                    "none": "single GPU: none"}[collective]),
-                       "setup_s": {"generate": round(t_gen, 2)}},
+                       "setup_s": {"generate": round(t_gen, 2), "upload": round(t_up, 2)}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "kernel": "k_r1cs_tiled" if args.kernel == "tiled" else "k_r1cs_rowwise",
                          "algorithmic_bytes_per_launch": algo_bytes, "device_stream_bytes_per_launch": m.stream_bytes + 32 * g.n_cols,
-                         "frac_isolated_launch": (algo_bytes / (statistics.mean(kernel_ms) * 1e-3) / 1e9 / peak) if kernel_ms else None,
-                         "kernel_ms_mean": k_ms,
-                         "kernel_ms_sampled_mean": statistics.mean(kernel_ms) if kernel_ms else None,
-                         "kernel_ms_min": min(kernel_ms) if kernel_ms else None,
-                         "timing": "kernel_ms_mean = min(sampled mean, step time): a step is exactly one launch of this kernel, "
-                                   "and consecutive launches overlap (the next check moves onto the SMs as this one's CTAs "
-                                   "run out of tiles), so the steady-state duration per launch is the step time; "
-                                   "kernel_ms_sampled_mean / frac_isolated_launch = event pairs around every 8th launch "
-                                   "(%d samples), which serialise that launch and add ~3 us of event latency" % len(kernel_ms)
-                                   if one_launch_per_step else "event pairs around every 8th step (%d samples)" % len(kernel_ms)},
+                         "kernel_ms_mean": iso_ms, "launches_timed": k_iso, "launches_per_check": launches_per_check,
+                         "kernel_ms_event_pair_mean": statistics.mean(kernel_ms), "kernel_ms_event_pair_min": min(kernel_ms),
+                         "frac_overlapped": achieved_ovl / peak, "step_ms_overlapped": step_ms,
+                         "per_rank_kernel_ms": per_rank_ms,
+                         "timing": "frac = algorithmic bytes / mean ISOLATED launch duration: %d plain launches of the check kernel back "
+                                   "to back (no overlap of consecutive checks) between two CUDA events on the launching stream "
+                                   "(second timed region; for N > 1 the local shard without the peer exchange, slowest rank); "
+                                   "kernel_ms_event_pair_*: %d launches bracketed one by one by their own event pair; frac_overlapped "
+                                   "= the same bytes / the step time of the first timed region, where consecutive checks overlap"
+                                   % (k_iso, len(kernel_ms))},
             "e2e": {"value": e2e_w_value, "unit": "constraints/s",
-                    "h2d_bytes_per_step": int(wp.nbytes) // world if sliced else int(wp.nbytes), "d2h_bytes_per_step": 16,
-                    "witness_upload": ("each rank uploads 1/%d of the witness over its own PCIe link, slices exchanged over "
-                                       "NVLink (one NCCL broadcast per rank)" % world) if sliced else "whole witness per rank",
-                    "steps": e2e_w_steps, "ms_per_step": 1e3 * e2e_w_s / e2e_w_steps,
-                    "call": "acg_witness_update (new witness from pinned host memory) + acg_r1cs_check against the system "
+                    "h2d_bytes_per_step": (int(wp.nbytes) // world) if sliced else int(wp.nbytes), "d2h_bytes_per_step": 16,
+                    "witness_upload": ("each rank copies 1/%d of the witness over its own PCIe link (copy stream), one NCCL "
+                                       "all-gather over NVLink completes it; two device vectors, copy i+1 overlaps all-gather + check i" % world)
+                                      if sliced else "whole witness, copy stream; two device vectors, copy i+1 overlaps check i",
+                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_w_s / e2e_steps,
+                    "call": "acg_witness_update_async (new witness from pinned host memory) + acg_r1cs_check against the system "
                             "resident on the device -- the reference, too, keeps its QAP value in memory between calls",
-                    "one_shot": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": h2d_bytes,
-                                 "d2h_bytes_per_step": 16, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                                 "call": "acg_r1cs_check_host: CSR matrices AND witness from pinned host memory every step "
-                                         "(PCIe-bound)"}},
-            "gpu_launches": launches, "gpu_launches_e2e": l_w, "gpu_launches_e2e_one_shot": l_e2e,
+                    "one_shot": one_shot},
+            "gpu_launches": launches, "gpu_launches_isolated_region": int(launches_per_check * k_iso), "gpu_launches_e2e": l_w,
             "clocks": sampler.summary(),
         }
+        if peer_check is not None:
+            line["config"]["peer_allreduce_check"] = peer_check
         if world == 1 and not args.no_cpu_baseline:
             from oracle import c_oracle as CO
             CO.build()
@@ -457,11 +605,22 @@ def run_ours(args, rank, world, local_rank):
             v_all, times = cpu_check_throughput(g, w, field_id, threads, 6.0, 20)
             v_one, _ = cpu_check_throughput(g, w, field_id, 1, 4.0, 5)
             line["cpu_baseline"] = {"value": v_all, "unit": "constraints/s", "cores": threads, "kind": "port",
-                                    "sample": "%d full checks of the same 2^%d-row system, best of" % (len(times), args.log_rows),
+                                    "sample": "%d full checks of the same %d-row system, best of" % (len(times), g.n_rows),
                                     "single_thread_value": v_one}
+        if world == 1 and not args.no_qap and args.workload == "s" and not args.dense:
+            for d in dws:
+                d.free()
+            m.free()
+            dws, m = [], None
+            try:
+                line["qap"] = qap_secondary(acg, ctx, field_id)
+            except Exception as e:  # secondary: never lose the main line
+                line["qap"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
-    dw.free()
-    m.free()
+    for d in dws:
+        d.free()
+    if m is not None:
+        m.free()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -84,12 +84,13 @@ int acg_ctx_set_check_kernel(acg_ctx* ctx, int which);
 /* Tiled kernel tuning: tile geometry, bound to a system when it is uploaded.  0 = 128-row tiles (default),
  * 1 = 256, 2 = 64, 3 = 32 rows per tile. */
 int acg_ctx_set_tiled_variant(acg_ctx* ctx, int variant);
-/* Back-to-back checks (acg_r1cs_check*, tiled kernel) of the SAME system and witness on the same stream overlap by
- * default: the later check is launched as a programmatic dependent of the earlier one, moves onto the SMs as the
- * earlier one's CTAs run out of tiles, and waits for it only before it touches the shared result scratch.  The library
- * tracks its own operations (any other call on the context between two checks disables the overlap for that pair).
- * A caller that rewrites the witness through acg_vec_device_ptr with its own kernels between two checks must switch
- * this off (on = 0). */
+/* Opt-in (default off): back-to-back checks (acg_r1cs_check*, tiled kernel) of the SAME system on the same stream
+ * overlap -- the later check is launched as a programmatic dependent of the earlier one, moves onto the SMs as the
+ * earlier one's CTAs run out of tiles, and waits for it only before it touches the shared result scratch.  The
+ * witnesses may differ (a prover checking a stream of resident witnesses).  The library tracks its own operations: any
+ * other call on the context between two checks -- in particular acg_witness_update* -- breaks the chain for that
+ * pair.  What it cannot see is a caller rewriting a witness through acg_vec_device_ptr with its own kernels between
+ * two checks: such a caller must leave this off. */
 int acg_ctx_set_overlap_checks(acg_ctx* ctx, int on);
 int acg_last_timing(const acg_ctx* ctx, acg_timing* out);
 /* Total launches of this library's kernels on this context since creation. */
@@ -124,15 +125,34 @@ uint64_t acg_r1cs_algorithmic_bytes(const acg_r1cs* m);
  * header, one 32-bit word per ELL slot, the far witness columns, and the values of the general coefficients only;
  * +-1 coefficients are sign bits of the words). */
 uint64_t acg_r1cs_stream_bytes(const acg_r1cs* m);
+/* A row block uploaded as a system of its own (CSR arrays of the block's rows only, row_begin = 0): `offset` = global
+ * index of its first row, added to every first_bad_row this system reports -- so that the all-reduced minimum over
+ * row-sharded ranks is a global row.  (The alternative is to pass the full matrices and a row range to
+ * acg_r1cs_upload.) */
+int acg_r1cs_set_row_offset(acg_r1cs* m, uint64_t offset);
 
 /* w: n_cols canonical elements in qapSetToMap order (src/QAP.hs:605-620). */
 int acg_witness_upload(acg_ctx* ctx, const uint64_t* w, uint32_t n_cols, acg_vec** out);
-/* Overwrite an existing device witness from host memory (same length). */
+/* Overwrite an existing device witness from host memory (same length).  Blocking; a rejected update (an element >= r)
+ * leaves the vector unchanged. */
 int acg_witness_update(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t n_cols);
 /* Overwrite elements [first, first + count) only.  With row shards on several GPUs every rank uploads its own slice
  * of a new witness over its own PCIe link and the slices are then exchanged device to device over NVLink
  * (sharding.upload_witness_sliced), instead of every rank pulling the whole vector from the host. */
 int acg_witness_update_range(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t first, uint32_t count);
+/* Enqueue-only variant for pipelining: elements [first, first + count) are copied on the context's COPY stream (H2D
+ * straight into the vector, range check + Montgomery conversion in place).  The update waits for the checks of v that
+ * were enqueued before it, and checks of v enqueued after it wait for the update -- with two vectors the upload of
+ * witness i + 1 overlaps the check of witness i.  `w` must stay valid (pinned memory, or the copy is staged by the
+ * driver) until the next blocking call on v.  An element >= r is reported by that call (acg_r1cs_check,
+ * acg_vec_status) as ACG_ERR_NON_CANONICAL; the vector's contents are then undefined -- acg_witness_update[_range],
+ * by contrast, leave the vector untouched when they reject an update. */
+int acg_witness_update_async(acg_ctx* ctx, acg_vec* v, const uint64_t* w, uint32_t first, uint32_t count);
+/* Enqueue only: `stream` (a cudaStream_t) waits for the asynchronous updates of v enqueued so far -- for callers that
+ * complete the vector with their own device work (the NVLink all-gather of a row-sharded witness) before a check. */
+int acg_vec_stream_wait(acg_ctx* ctx, acg_vec* v, void* stream);
+/* Blocking: waits for the asynchronous updates of v; ACG_ERR_NON_CANONICAL if one of them met an element >= r. */
+int acg_vec_status(acg_ctx* ctx, acg_vec* v);
 void acg_vec_free(acg_vec* v);
 uint32_t acg_vec_len(const acg_vec* v);
 /* Raw device pointer of the vector's storage (Montgomery form), for zero-copy interop. */
@@ -212,6 +232,30 @@ int acg_lagrange(acg_ctx* ctx, const uint64_t* xs, const uint64_t* ys, uint32_t 
  * weights: the witness value of each wire.  Canonical limbs in and out; blocking. */
 int acg_poly_combine(acg_ctx* ctx, const uint64_t* polys, const uint64_t* weights, uint32_t n_polys, uint32_t len,
                      uint64_t* out);
+
+/* ---- verificationWitnessZk on a per-wire `QAP f` value (src/QAP.hs:74-79, 300-327), whole on the device --------
+ * acg_qap_upload keeps the three polynomial sets and the target resident: left / right / out are n_wires coefficient
+ * vectors of `len` canonical elements each (little-endian degree, zero padded), wires in qapSetToMap order
+ * (src/QAP.hs:605-620; a wire the QAP lacks is the zero polynomial, as combineWithDefaults treats it, :163-181);
+ * target: n_target coefficients of qapTarget -- prod (X - root) of createPolynomials (:492), FFT.fftTargetPoly of
+ * createPolynomialsFFT (:524), or any other non-zero polynomial (trailing zeros are stripped).
+ * acg_qap_verify: a = delta1*T + sum_k w_k L_k, b, c likewise (scale-and-sum, :314-324), p = a*b - c by a product on
+ * >= 2*max(len, n_target) - 1 points (NTT), then (h, rem) = p divMod T by long division on the device (:327, K7).
+ * w: n_wires canonical witness values (missing wires 0); delta: 12 limbs or NULL.  *divisible = 1 iff rem == 0 -- then
+ * h[0 .. *h_len) (canonical, little-endian, NOT stripped; *h_len = acg_qap_quotient_len) is the reference's
+ * `Just quotient`; otherwise the reference returns Nothing.  h may be NULL (verifyAssignment only needs the flag). */
+typedef struct acg_qap acg_qap;
+int acg_qap_upload(acg_ctx* ctx, const uint64_t* left, const uint64_t* right, const uint64_t* out, uint32_t n_wires,
+                   uint32_t len, const uint64_t* target, uint32_t n_target, acg_qap** out_qap);
+void acg_qap_free(acg_qap* q);
+uint32_t acg_qap_quotient_len(const acg_qap* q);
+int acg_qap_verify(acg_ctx* ctx, const acg_qap* q, const uint64_t* w, const uint64_t* delta, uint64_t* h,
+                   uint32_t h_capacity, uint32_t* h_len, int* divisible);
+/* FFT.fftTargetPoly primRoots n (src/QAP.hs:524; galois-fft-0.1.0, not vendored): prod_{i < n_roots} (X - w^i) with w
+ * the primitive 2^ceil(log2 n_roots)-th root of unity of the field -- X^N - 1 when n_roots is a power of two.
+ * out: n_roots + 1 canonical coefficients.  A partial domain is built on the device (K5 master polynomial) and is
+ * limited to 4096 roots. */
+int acg_fft_target(acg_ctx* ctx, uint32_t n_roots, uint64_t* out);
 
 /* ---- field ops on the device (K1 self-test surface) ------------------------------------------------
  * op: 0 add, 1 sub, 2 mul, 3 inverse of a (inv 0 = 0, as evalGate treats it, Arithmetic.hs:130).

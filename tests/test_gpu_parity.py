@@ -12,6 +12,7 @@ from oracle import qap_oracle as O
 from helpers import FIELDS, csr_from_json, gates_acg, gates_oracle, golden, make_genqap, oracle_check, unhex
 
 pytestmark = pytest.mark.gpu
+F_R_MINUS_1 = O.BN254.r - 1
 
 
 # ------------------------------------------------------------------------------------------------ K1
@@ -178,13 +179,10 @@ def test_per_wire_qap_matches_oracle(acg, ctx_bn):
             want = _oracle_sets_as_columns(F, osets, q.layout)
             assert [q.wire_poly(which, k) for k in range(q.n_cols)] == want, which
         assert q.target == O.p_norm(F, oq.target)
+        # h from the device division (acg_qap_verify), for T = X^4 - 1 and for the padded domain's prod (X - w^i)
         oh = O.verification_witness_zk(F, 3, 5, 7, oq, oa)[0]
-        got = acg.verification_witness_zk_qap(ctx_bn, 3, 5, 7, q, a)
-        if len(gates_o) == 4:
-            assert oh is not None and got == O.p_norm(F, oh)
-            assert acg.verification_witness_zk_qap(ctx_bn, 0, 0, 0, q, a) == O.p_norm(F, O.verification_witness(F, oq, oa))
-        else:
-            assert oh is not None and got is True
+        assert oh is not None and acg.verification_witness_zk_qap(ctx_bn, 3, 5, 7, q, a) == O.p_norm(F, oh)
+        assert acg.verification_witness_zk_qap(ctx_bn, 0, 0, 0, q, a) == O.p_norm(F, O.verification_witness(F, oq, oa))
         assert acg.verify_assignment_qap(ctx_bn, q, a)
         # JSON of the QAP value round-trips (N2)
         from arithmetic_circuits_b200 import json_io as J
@@ -198,11 +196,68 @@ def test_per_wire_qap_matches_oracle(acg, ctx_bn):
             assert ql.target == O.p_norm(F, oql.target)        # KAT-1: X^3 - 24X^2 + 191X - 504
             assert ql.target == [F.r - 504, 191, F.r - 24, 1]
             assert acg.verify_assignment_qap(ctx_bn, ql, a)
+            # KAT-1: h of the Lagrange QAP, divided by prod (X - root) on the device
+            assert acg.verification_witness_zk_qap(ctx_bn, 0, 0, 0, ql, a) == unhex(golden("kats.json")["kat1"]["h"])
+            ohl = O.verification_witness_zk(F, 3, 5, 7, oql, oa)[0]
+            assert ohl is not None and acg.verification_witness_zk_qap(ctx_bn, 3, 5, 7, ql, a) == O.p_norm(F, ohl)
+            badl = acg.generate_assignment(c, inputs)
+            badl.update(acg.IntermediateWire(0), 7)   # unit_arithCircuitToQapNoFalsePositive, test/Test/QAP.hs:77-90
+            assert acg.verification_witness_zk_qap(ctx_bn, 0, 0, 0, ql, badl) is None
+            assert not acg.verify_assignment_qap(ctx_bn, ql, badl)
+            # an assignment with a wire the QAP does not know verifies as in the reference (combineWithDefaults)
+            extra = acg.generate_assignment(c, {**inputs, 9: 123})
+            assert acg.verify_assignment_qap(ctx_bn, ql, extra)
         # a bad witness
         bad = acg.generate_assignment(c, inputs)
         bad.update(acg.IntermediateWire(0), 7)
         assert acg.verification_witness_zk_qap(ctx_bn, 3, 5, 7, q, bad) is None
         assert not acg.verify_assignment_qap(ctx_bn, q, bad)
+
+
+@pytest.mark.parametrize("fid,n_rows,seed", [(0, 1, 1), (0, 2, 2), (0, 33, 3), (0, 64, 4), (1, 100, 5), (0, 700, 6)])
+def test_qap_verify_division_vs_oracle(acg, ctxs, fid, n_rows, seed):
+    """acg_qap_verify on a Lagrange-built QAP of the synthetic family (arbitrary roots, target prod (X - root)) and on
+    its FFT build (padded domain for n not a power of two): h equals the big-int oracle's schoolbook quotRem
+    (src/QAP.hs:325-327) with and without delta terms; a tampered witness gives None; the long division crosses
+    several 32-coefficient blocks at the larger sizes."""
+    F, ctx = FIELDS[fid], ctxs[fid]
+    rnd = random.Random(seed)
+    circuit, inputs = acg.synth_circuit(fid, n_rows, 1000 + seed)
+    a = acg.generate_assignment(circuit, inputs)
+    roots = rnd.sample(range(1, 1 << 60), n_rows)
+    g = acg.arith_circuit_to_gen_qap(circuit, [[r] for r in roots])
+    w = acg.from_limbs(acg.witness_vector(a, g.layout))
+    mats = [O.CSR(list(map(int, rp)), list(map(int, col)), acg.from_limbs(val)) for rp, col, val in g.mats]
+    abc = [O.csr_matvec(F, M, w) for M in mats]          # rows in ascending-root order
+    xs = sorted(r % F.r for r in roots)
+    for kind in ("lagrange", "fft"):
+        if kind == "lagrange":
+            q = acg.create_polynomials_qap(ctx, g)
+            target = [1]
+            for x in xs:
+                target = O.p_mul(F, target, [F.r - x, 1])
+            polys = [O.lagrange_interpolate(F, list(zip(xs, v))) for v in abc]
+        else:
+            q = acg.create_polynomials_fft_qap(ctx, g)
+            N = 1
+            while N < n_rows:
+                N <<= 1
+            om = F.root_of_unity(N.bit_length() - 1)
+            target = [1]
+            for i in range(n_rows):
+                target = O.p_mul(F, target, [F.r - pow(om, i, F.r), 1])
+            polys = [O.fft_interpolate(F, v + [0] * (N - n_rows)) for v in abc]
+        assert q.target == O.p_norm(F, target)
+        for d in ((0, 0, 0), (rnd.randrange(F.r), rnd.randrange(F.r), rnd.randrange(F.r))):
+            pa, pb, pc = (O.p_add(F, O.p_scale(F, dk, target), pk) for dk, pk in zip(d, polys))
+            quo, rem = O.p_quot_rem(F, O.p_sub(F, O.p_mul(F, pa, pb), pc), target)
+            assert not rem
+            assert acg.verification_witness_zk_qap(ctx, d[0], d[1], d[2], q, a) == O.p_norm(F, quo), (kind, d)
+        bad = acg.generate_assignment(circuit, inputs)
+        victim = acg.IntermediateWire((n_rows - 1) // 2) if n_rows > 1 else acg.OutputWire(0)
+        bad.update(victim, (bad.lookup(victim) + 1) % F.r)
+        assert acg.verification_witness_zk_qap(ctx, 0, 0, 0, q, bad) is None
+        q.free_device()
 
 
 # ------------------------------------------------------------------------------------------------ K6
@@ -519,9 +574,10 @@ def test_qap_witness_vs_c_oracle(acg, ctxs, fid, n, delta):
     assert ctx.qap_witness(m, dw, delta, want=())[1] is False
 
 
-def test_qap_identity_at_random_point_2_20(acg, ctx_bn):
-    """Full-size property: a(z) * b(z) - c(z) == h(z) * (z^N - 1) at a random z (Schwartz-Zippel), with
-    Horner evaluation in Python big ints over the returned coefficient vectors."""
+def test_qap_identity_at_random_point_2_16(acg, ctx_bn):
+    """Size-independent property: a(z) * b(z) - c(z) == h(z) * (z^N - 1) at a random z (Schwartz-Zippel), with
+    Horner evaluation in Python big ints over the returned coefficient vectors (N = 2^16; the 2^22 case is
+    test_config3_qap_witness_2_22, bit-exact against the C oracle)."""
     n = 1 << 16
     F = O.BN254
     g, w = acg.synth_r1cs(0, n, 5)
@@ -569,6 +625,189 @@ def test_lagrange_matches_reference_qap_build(acg, ctx_bn):
         assert O.p_eval(F, polys[0], xs[i]) == ys[i]
 
 
+def test_reference_gate_mix_split_rows_one_launch(acg, ctx_bn):
+    """A circuit with the gate mix of the reference's own generator (Mul : Equal : Split = 50 : 10 : 1, 256-bit Split,
+    test/Test/Circuit/Arithmetic.hs:77-126): every Split contributes one 256-entry row of general coefficients 2^i.
+    However many there are, a check is at most two launches (all long rows in one warp-per-row launch, then the tiles);
+    counts, first bad row and the emitted A.w, B.w, C.w equal the C oracle's."""
+    n = 1 << 15
+    g, w = acg.synth_mixed_r1cs(0, n, 99)
+    lens = np.diff(g.mats[0][0].astype(np.int64))
+    assert (lens > 8).sum() >= 50
+    ref = oracle_check(0, g, w, True)
+    assert ref["n_violations"] == 0
+    m, dw = ctx_bn.upload_r1cs(g), ctx_bn.upload_witness(w)
+    _select(acg, ctx_bn, "tiled", 0)
+    assert ctx_bn.r1cs_check(m, dw) == (0, -1)
+    assert ctx_bn.last_timing()["kernel_launches"] <= 2
+    aw, bw, cw = ctx_bn.r1cs_eval(m, dw)
+    assert (aw == ref["Aw"]).all() and (bw == ref["Bw"]).all() and (cw == ref["Cw"]).all()
+    # flip one output bit of every tenth Split and one Equal/Mul wire
+    wb = w.copy()
+    long_rows = np.nonzero(lens > 8)[0]
+    for r in long_rows[::10]:
+        col = int(g.mats[0][1][g.mats[0][0][r] + 17])    # the wire of bit 17 of that Split
+        wb[col, 0] ^= np.uint64(1)
+    wb[g.n_cols // 2, 0] += np.uint64(1)
+    refb = oracle_check(0, g, wb)
+    assert refb["n_violations"] > len(long_rows[::10])
+    dw.update(wb)
+    assert _both_kernels(acg, ctx_bn, lambda: ctx_bn.r1cs_check(m, dw)) == (refb["n_violations"], refb["first_bad_row"])
+    dw.free()
+    m.free()
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs at full size
+def _default_geometry(acg, ctx):
+    ctx.set_tiled_variant(0)
+    ctx.set_check_kernel(acg.CHECK_AUTO)
+
+
+def test_config3_qap_witness_2_22(acg, _ctx_bn):
+    """BASELINE configs[2]: S(2^22, 20260003, BN254) -- check + A.w, B.w, C.w + 3 inverse NTTs of 2^22 points + coset
+    quotient: h, a, b, c of acg_qap_witness bit-exact against the C oracle's radix-2 NTT / coset division, with delta
+    terms; a tampered witness is not divisible."""
+    ctx = _ctx_bn
+    _default_geometry(acg, ctx)
+    n = 1 << 22
+    g, w = acg.synth_r1cs(0, n, 20260003)
+    m, dw = ctx.upload_r1cs(g), ctx.upload_witness(w)
+    assert ctx.r1cs_check(m, dw) == (0, -1)
+    ref = oracle_check(0, g, w, True, n_threads=16)
+    aw, bw, cw = ctx.r1cs_eval(m, dw)
+    assert (aw == ref["Aw"]).all() and (bw == ref["Bw"]).all() and (cw == ref["Cw"]).all()
+    delta = (0x1234567, 3, F_R_MINUS_1)
+    bufs, ok = ctx.qap_witness(m, dw, delta)
+    a, b, c, h, rok = CO.qap_witness(0, ref["Aw"], ref["Bw"], ref["Cw"], delta, 16)
+    assert ok and rok
+    for k, want in (("h", h), ("a", a), ("b", b), ("c", c)):
+        assert (bufs[k] == want).all(), k
+    wb = w.copy()
+    wb[1025 + n // 3, 0] += np.uint64(1)
+    dw.update(wb)
+    _bufs, ok = ctx.qap_witness(m, dw, (0, 0, 0), want=())
+    assert not ok
+    dw.free()
+    m.free()
+
+
+@pytest.mark.parametrize("variant", [0, 2])
+def test_config5_bls12_381_2_20(acg, _ctx_bls, variant):
+    """BASELINE configs[4]: S(2^20, 20260005, BLS12-381 Fr) -- honest and tampered witness, both kernels, against the
+    C oracle's count and first bad row; emitted A.w, B.w, C.w bit-exact."""
+    ctx = _ctx_bls
+    ctx.set_tiled_variant(variant)
+    n = 1 << 20
+    g, w = acg.synth_r1cs(1, n, 20260005)
+    m, dw = ctx.upload_r1cs(g), ctx.upload_witness(w)
+    ref = oracle_check(1, g, w, True, n_threads=16)
+    assert ref["n_violations"] == 0
+    aw, bw, cw = ctx.r1cs_eval(m, dw)
+    assert (aw == ref["Aw"]).all() and (bw == ref["Bw"]).all() and (cw == ref["Cw"]).all()
+    wb = w.copy()
+    wb[1025 + n // 3, 0] += np.uint64(1)
+    for t in (7, 1025 + n - 2):
+        wb[t, 3] ^= np.uint64(1 << 9)
+    refb = oracle_check(1, g, wb, False, n_threads=16)
+    assert refb["n_violations"] > 0
+    for kernel, stages in KERNELS:
+        _select(acg, ctx, kernel, stages)
+        dw.update(w)
+        assert ctx.r1cs_check(m, dw) == (0, -1)
+        dw.update(wb)
+        assert ctx.r1cs_check(m, dw) == (refb["n_violations"], refb["first_bad_row"])
+    _reset(acg, ctx)
+    ctx.set_tiled_variant(0)
+    dw.free()
+    m.free()
+
+
+def test_config4_shards_of_2_24(acg, _ctx_bn):
+    """BASELINE configs[3]: S(2^24, 20260004, BN254) split in 8 contiguous row blocks, witness replicated -- shards 0 and
+    7 run on this GPU: per-shard violation count and first bad (global) row equal the C oracle's on the same shard,
+    for the honest witness and for one tampered in both shards' reach."""
+    from arithmetic_circuits_b200 import sharding
+    ctx = _ctx_bn
+    _default_geometry(acg, ctx)
+    n = 1 << 24
+    dw = None
+    for rank in (0, 7):
+        rb, re = sharding.row_shard(n, 8, rank)
+        g, w = acg.synth_r1cs(0, n, 20260004, rows=(rb, re))
+        assert g.n_rows == re - rb == n // 8 and g.n_cols == 1025 + n
+        # upload the shard as the row range [rb, re) of the global system (first_bad_row is global)
+        a, b, c = g.csr_structs()
+        mats = [(np.concatenate([np.zeros(rb, np.uint32), rp, np.full(n - re, rp[-1], np.uint32)]), col, val)
+                for rp, col, val in g.mats]
+        gg = acg.GenQAP(0, n, g.n_cols, g.layout, mats)
+        m = ctx.upload_r1cs(gg, rb, re)
+        if dw is None:
+            dw = ctx.upload_witness(w)
+            wb = w.copy()
+            wb[1025 + 12345, 0] += np.uint64(1)        # defined in shard 0, referenced far and wide afterwards
+            wb[1025 + n - 5, 1] ^= np.uint64(1 << 20)  # defined in shard 7
+        dw.update(w)
+        assert ctx.r1cs_check(m, dw) == (0, -1)
+        ref = oracle_check(0, g, wb, False, n_threads=16)
+        dw.update(wb)
+        nv, first = ctx.r1cs_check(m, dw)
+        assert nv == ref["n_violations"] > 0
+        assert first == rb + ref["first_bad_row"]
+        m.free()
+    dw.free()
+
+
+def test_pipelined_witness_updates(acg, _ctx_bn):
+    """acg_witness_update_async: two resident vectors, the upload of witness i + 1 (copy stream) overlaps the check of
+    witness i; every check still sees exactly its own witness, a non-canonical element is reported by the check that
+    reads the vector, and the blocking update leaves a vector untouched when it rejects."""
+    import torch
+    ctx = _ctx_bn
+    _default_geometry(acg, ctx)
+    n = 1 << 16
+    g, w = acg.synth_r1cs(0, n, 777)
+    m = ctx.upload_r1cs(g)
+    wits, wants = [], []
+    for i in range(6):
+        wi = w.copy()
+        if i % 3:
+            wi[1025 + 1000 * i, 0] ^= np.uint64(1 << i)
+        ref = oracle_check(0, g, wi)
+        wits.append(torch.from_numpy(wi.view(np.int64)).pin_memory())
+        wants.append((ref["n_violations"], ref["first_bad_row"]))
+    vecs = [ctx.upload_witness(w), ctx.upload_witness(w)]
+    vecs[0].update_async(wits[0].numpy().view(np.uint64))
+    got = []
+    for i in range(6):
+        if i + 1 < 6:
+            vecs[(i + 1) & 1].update_async(wits[i + 1].numpy().view(np.uint64))
+        got.append(ctx.r1cs_check(m, vecs[i & 1]))
+    assert got == wants
+    # a non-canonical element: reported by the check of that vector, not earlier and not for the other vector
+    bad = w.copy()
+    bad[5] = np.array([0xFFFFFFFFFFFFFFFF] * 4, np.uint64)
+    vecs[0].update_async(bad)
+    vecs[1].update_async(w)
+    assert ctx.r1cs_check(m, vecs[1]) == (0, -1)
+    with pytest.raises(acg.AcgError) as e:
+        ctx.r1cs_check(m, vecs[0])
+    assert e.value.code == -2
+    vecs[0].update_async(w)
+    vecs[0].status()
+    assert ctx.r1cs_check(m, vecs[0]) == (0, -1)
+    # blocking update: rejected -> unchanged
+    with pytest.raises(acg.AcgError) as e:
+        vecs[0].update(bad)
+    assert e.value.code == -2
+    assert (vecs[0].download() == w).all() and ctx.r1cs_check(m, vecs[0]) == (0, -1)
+    with pytest.raises(acg.AcgError):
+        vecs[0].update_range(bad[:16], 0)
+    assert (vecs[0].download() == w).all()
+    for v in vecs:
+        v.free()
+    m.free()
+
+
 # ------------------------------------------------------------------------------------------------ multi-GPU
 def test_peer_exchange_two_ranks():
     """Row shards on two GPUs, result pair all-reduced over peer memory by the check kernel's last CTA: every rank
@@ -586,7 +825,7 @@ def test_peer_exchange_two_ranks():
 
 
 def test_overlapping_consecutive_checks(acg, ctx_bn):
-    """Back-to-back async checks of the same system and witness are launched as programmatic dependents of each other
+    """With acg_ctx_set_overlap_checks(1), back-to-back async checks of the same system are launched as programmatic dependents of each other
     (they overlap on the GPU and share one scratch result pair): every one of them must still deliver the oracle's
     count and first bad row -- for a clean witness, for a tampered one (violation reports from overlapping launches),
     after the witness changes in between (chain broken), and with the overlap switched off."""
@@ -612,5 +851,16 @@ def test_overlapping_consecutive_checks(acg, ctx_bn):
             torch.cuda.synchronize()
             got = {(int(r[0].item()), int(r[1].item())) for r in results}
             assert got == {want}, (overlap, got, want)
-    ctx_bn.set_overlap_checks(True)
+        # two resident witnesses checked alternately, no host synchronisation: the chain holds across DIFFERENT witness
+        # buffers (nothing was enqueued through the context in between) and every launch reports its own witness
+        dwa, dwb = ctx_bn.upload_witness(w), ctx_bn.upload_witness(wb)
+        results = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(12)]
+        for i, r in enumerate(results):
+            ctx_bn.r1cs_check_async(m, dwb if i & 1 else dwa, r.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        got = [(int(r[0].item()), int(r[1].item())) for r in results]
+        assert got == [want_bad if i & 1 else (0, -1) for i in range(12)], (overlap, got)
+        dwa.free()
+        dwb.free()
+    ctx_bn.set_overlap_checks(False)   # the default: a plain launch per check
     _reset(acg, ctx_bn)

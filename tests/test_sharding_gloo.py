@@ -86,3 +86,49 @@ def test_row_shard_partitions():
     rp = np.concatenate([[0], np.cumsum([1] * 100 + [10000] + [1] * 100)]).astype(np.uint32)
     cuts = [sharding.row_shard_balanced([rp, rp, rp], 4, r) for r in range(4)]
     assert cuts[0][0] == 0 and cuts[-1][1] == 201 and all(cuts[i][1] == cuts[i + 1][0] for i in range(3))
+
+
+def _gather_worker(rank, world, port, n, q):
+    import torch
+    import torch.distributed as dist
+    from arithmetic_circuits_b200 import sharding
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # the exchange of sharding.upload_witness_allgather on host tensors: every rank holds only its slice (and the
+        # remainder) of a 32-byte-per-element vector, one in-place all-gather completes it
+        full = torch.arange(n * 32, dtype=torch.int64).remainder(251).to(torch.uint8)
+        mine = torch.zeros_like(full)
+        s, rem0 = sharding.gather_plan(n, world)
+        mine[rank * s * 32:(rank + 1) * s * 32] = full[rank * s * 32:(rank + 1) * s * 32]
+        mine[rem0 * 32:] = full[rem0 * 32:]
+        if s:
+            dist.all_gather_into_tensor(mine[:world * s * 32], mine[rank * s * 32:(rank + 1) * s * 32].clone())
+        q.put((rank, bool((mine == full).all())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1, 2, 1025 + 1500, 4097])
+def test_witness_slices_one_allgather(n):
+    """The slice plan of the row-sharded witness upload (equal slices + remainder) reassembles the vector with one
+    all-gather, world size 2, gloo."""
+    import torch.multiprocessing as mp
+    from arithmetic_circuits_b200 import sharding
+
+    for world in (1, 2, 3, 8):
+        s, rem0 = sharding.gather_plan(n, world)
+        assert s * world == rem0 <= n and n - rem0 < world
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got == [(0, True), (1, True)]
