@@ -22,7 +22,6 @@ static int binop(int op, const uint32_t* a, const uint32_t* b, uint32_t* o, uint
             case 6: z = fr_mul<P>(x, y); break;  // raw Montgomery product x*y/R
             case 7: z = fr_mul<P>(x, y); break;  // x <= p, y any 256-bit value (unreduced row sum)
             case 8: z = fr_add<P>(x, y); break;  // x, y <= p: result in [0, p]
-            case 9: z = fr_mul_karatsuba<P>(x, y); break;  // same contract as 7
             default: return -1;
         }
         std::memcpy(o + 8 * i, z.l, 32);

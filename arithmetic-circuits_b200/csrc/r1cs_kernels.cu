@@ -487,7 +487,8 @@ __device__ __forceinline__ fr_t canonical(fr_t x) {
 }
 }  // namespace tiled
 
-// phase cycle counters of the TIMING instantiation (a measurement aid: ACG_TILED_TIMING=1)
+// phase cycle counters of the TIMING instantiation (a measurement aid, compiled only with -DACG_TILED_TIMING_BUILD and
+// switched on with ACG_TILED_TIMING=1; the shipped library does not contain it)
 __device__ unsigned long long g_tiled_phase_cycles[2][8];
 // .. and per-CTA wall-clock marks (globaltimer, ns): kernel entry, first tile staged, last tile done, exit
 constexpr uint32_t kMaxTimedCtas = 2048;
@@ -812,6 +813,7 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
     }
     unsigned grid = (unsigned)sm_count * ctas;
     if (grid > ts.n_tiles) grid = ts.n_tiles;
+#ifdef ACG_TILED_TIMING_BUILD  // measurement build only (ACG_NVCC_EXTRA=-DACG_TILED_TIMING_BUILD python build.py --force)
     if (V == 0 && !EMIT) {  // ACG_TILED_TIMING=1: run the instrumented instantiation and print its counters
         static const bool timing = getenv("ACG_TILED_TIMING") != nullptr;
         if (timing) {
@@ -863,6 +865,7 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
             return cudaGetLastError();
         }
     }
+#endif
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kTileGeom[V].threads);

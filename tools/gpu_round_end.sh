@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw,power.limit,memory.total --format=csv > gpurun_out/gpu_info.txt 2>&1; nproc >> gpurun_out/gpu_info.txt; lscpu | grep "Model name" >> gpurun_out/gpu_info.txt
 echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 echo "=== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -6
-echo "=== K1 ceiling"; nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I arithmetic-circuits_b200/csrc tools/microbench/fr_mul_throughput.cu -o /tmp/fr_mul_throughput 2>/dev/null; timeout 120 /tmp/fr_mul_throughput > gpurun_out/fr_mul_throughput.txt 2>&1; tail -3 gpurun_out/fr_mul_throughput.txt | cut -c1-200
+echo "=== K1 ceiling"; nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I arithmetic-circuits_b200/csrc -I tools/microbench tools/microbench/fr_mul_throughput.cu -o /tmp/fr_mul_throughput 2>/dev/null; timeout 120 /tmp/fr_mul_throughput > gpurun_out/fr_mul_throughput.txt 2>&1; tail -3 gpurun_out/fr_mul_throughput.txt | cut -c1-200
 echo "=== bench reference arm"; timeout 900 python bench.py --impl reference --steps 20 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_reference.json | cut -c1-400
 echo "=== bench ours"; timeout 900 python bench.py 2>&1 | tail -1 | tee gpurun_out/bench_ours.json | cut -c1-1800
 echo "=== bench ours bls"; timeout 900 python bench.py --field bls12_381 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_ours_bls.json | cut -c1-300
