@@ -80,6 +80,8 @@ PROTOTYPES = {
     "acg_qap_witness": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int)]),
     "acg_lagrange": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp]),
     "acg_fr_binop": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_uint64]),
+    "acg_linear_constraints_check": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(AcgCsr),
+                                               C.POINTER(AcgCsr), vp, vp, vp, u64p, u64p]),
     "acg_circuit_parse": (C.c_int, [C.c_int, vp, C.c_uint64, C.POINTER(vp)]),
     "acg_circuit_free": (None, [vp]),
     "acg_circuit_num_gates": (C.c_uint64, [vp]),

@@ -17,7 +17,7 @@ OUT = os.path.join(HERE, "libacg.so")
 OBJ_DIR = os.path.join(HERE, "_build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CU_SOURCES = ["r1cs_kernels.cu", "ntt_kernels.cu", "lagrange_kernels.cu", "witness_kernels.cu", "poly_kernels.cu", "abi.cu"]
+CU_SOURCES = ["r1cs_kernels.cu", "ntt_kernels.cu", "lagrange_kernels.cu", "witness_kernels.cu", "poly_kernels.cu", "linear_kernels.cu", "abi.cu"]
 CPP_SOURCES = ["host/circuit.cpp", "host/synth.cpp"]
 HEADERS = ["fr.cuh", "fr_constants.inc", "dev.cuh", "kernels.h", "host/fr_host.hpp", "host/circuit.hpp",
            "../../include/acg.h"]

@@ -2026,6 +2026,75 @@ int acg_fft_target(acg_ctx* ctx, uint32_t n_roots, uint64_t* out) {
 }
 
 // --------------------------------------------------------------------------------------------------
+// linear constraints (Bulletproofs backend): checkLinearConstraint, src/Circuit/Bulletproofs.hs:329-338
+// --------------------------------------------------------------------------------------------------
+int acg_linear_constraints_check(acg_ctx* ctx, int modulus_id, uint32_t n_constraints, uint32_t n_lhs_vars,
+                                 uint32_t n_rhs_vars, const acg_csr* lhs, const acg_csr* rhs, const uint64_t* constants,
+                                 const uint64_t* x, const uint64_t* v, uint64_t* n_violations, uint64_t* first_bad) {
+    ACG_TRY
+    int rc = activate(ctx);
+    if (rc) return rc;
+    if (modulus_id < 0 || modulus_id > ACG_FIELD_SECP256K1_FN || !lhs || !rhs || (n_constraints && !constants) ||
+        (n_lhs_vars && !x) || (n_rhs_vars && !v))
+        return fail(ctx, ACG_ERR_BAD_ARG, "acg_linear_constraints_check: bad argument");
+    const acg_csr* src[2] = {lhs, rhs};
+    const uint32_t n_vars[2] = {n_lhs_vars, n_rhs_vars};
+    for (int k = 0; k < 2; ++k) {
+        const acg_csr* M = src[k];
+        if (!M->rowptr || (M->nnz && (!M->col || !M->val)) || M->nnz > 0xFFFFFFF0ull || M->rowptr[0] != 0 ||
+            M->rowptr[n_constraints] != M->nnz)
+            return fail(ctx, ACG_ERR_BAD_ARG, "acg_linear_constraints_check: malformed CSR");
+        for (uint32_t r = 0; r < n_constraints; ++r)
+            if (M->rowptr[r] > M->rowptr[r + 1]) return fail(ctx, ACG_ERR_BAD_ARG, "acg_linear_constraints_check: rowptr not monotone");
+        for (uint64_t e = 0; e < M->nnz; ++e)
+            if (M->col[e] >= n_vars[k]) return fail(ctx, ACG_ERR_BAD_ARG, "acg_linear_constraints_check: column index out of range");
+    }
+    cudaStream_t s = ctx->stream;
+    DevBuf d_rp[2], d_col[2], d_val[2], d_x[2], d_c, d_res;
+    const uint64_t* host_x[2] = {x, v};
+    auto h2d = [&](DevBuf& d, const void* p, size_t bytes) -> cudaError_t {
+        cudaError_t e = d.alloc(bytes);
+        if (e != cudaSuccess || bytes == 0) return e;
+        return cudaMemcpyAsync(d.p, p, bytes, cudaMemcpyHostToDevice, s);
+    };
+    CU(ctx, cudaEventRecord(ctx->ev[0], s));
+    for (int k = 0; k < 2; ++k) {
+        CU(ctx, h2d(d_rp[k], src[k]->rowptr, ((size_t)n_constraints + 1) * sizeof(uint32_t)));
+        CU(ctx, h2d(d_col[k], src[k]->col, (size_t)src[k]->nnz * sizeof(uint32_t)));
+        CU(ctx, h2d(d_val[k], src[k]->val, (size_t)src[k]->nnz * 32));
+        CU(ctx, h2d(d_x[k], host_x[k], (size_t)n_vars[k] * 32));
+    }
+    CU(ctx, h2d(d_c, constants, (size_t)n_constraints * 32));
+    const unsigned long long init[2] = {0ull, ~0ull};
+    CU(ctx, h2d(d_res, init, sizeof init));
+    CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
+    CU(ctx, cudaEventRecord(ctx->ev[1], s));
+    uint32_t launches = 0;
+    for (int k = 0; k < 2; ++k) {
+        CU(ctx, launch_lin_to_mont(modulus_id, d_x[k].as<uint64_t>(), n_vars[k], ctx->d_flag, s));
+        launches += n_vars[k] ? 1 : 0;
+    }
+    CU(ctx, launch_linear_constraints(modulus_id, d_rp[0].as<uint32_t>(), d_col[0].as<uint32_t>(), d_val[0].as<uint64_t>(),
+                                      d_rp[1].as<uint32_t>(), d_col[1].as<uint32_t>(), d_val[1].as<uint64_t>(),
+                                      d_c.as<uint64_t>(), d_x[0].as<uint64_t>(), d_x[1].as<uint64_t>(), n_constraints,
+                                      d_res.as<unsigned long long>(), ctx->d_flag, s));
+    launches += n_constraints ? 1 : 0;
+    CU(ctx, cudaEventRecord(ctx->ev[2], s));
+    CU(ctx, cudaMemcpyAsync(ctx->h_result, d_res.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaEventRecord(ctx->ev[3], s));
+    CU(ctx, cudaStreamSynchronize(s));
+    ctx->launches += launches;
+    ctx->timing = acg_timing{elapsed(ctx->ev[0], ctx->ev[1]), elapsed(ctx->ev[1], ctx->ev[2]), elapsed(ctx->ev[2], ctx->ev[3]),
+                             launches, 0};
+    if (*ctx->h_flag) return fail(ctx, ACG_ERR_NON_CANONICAL, "acg_linear_constraints_check: element >= modulus");
+    if (n_violations) *n_violations = ctx->h_result[0];
+    if (first_bad) *first_bad = ctx->h_result[1];
+    return ACG_OK;
+    ACG_CATCH(ctx)
+}
+
+// --------------------------------------------------------------------------------------------------
 // multi-GPU: result all-reduce over peer memory
 // --------------------------------------------------------------------------------------------------
 int acg_peer_create(acg_ctx* ctx, uint32_t world, uint32_t rank, acg_peer** out, uint8_t* handle_out) {

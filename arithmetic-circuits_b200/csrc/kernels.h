@@ -269,6 +269,17 @@ cudaError_t launch_any_nonzero(const fr_t* v, uint64_t n, int* d_flag, cudaStrea
 cudaError_t launch_poly_divmod(int field, fr_t* p, uint32_t len_p, const fr_t* T, uint32_t n, fr_t lc_inv, bool monic,
                                fr_t* h, cudaStream_t s, uint32_t* launches);
 
+// Linear constraints over any 256-bit prime modulus (linear_kernels.cu): modulus 0 BN254 Fr, 1 BLS12-381 Fr,
+// 2 the secp256k1 group order.  x[i] <- x[i] * 2^256 mod n in place (flag: an element >= n); then constraint i holds
+// <=> lhs_i . x == rhs_i . v + cst_i (weights and constants canonical limbs, x_mont / v_mont from launch_lin_to_mont).
+// d_result = {violated, first violated} accumulates: {0, ~0} on entry.
+cudaError_t launch_lin_to_mont(int modulus, uint64_t* x, uint64_t n_el, int* d_bad_flag, cudaStream_t s);
+cudaError_t launch_linear_constraints(int modulus, const uint32_t* l_rowptr, const uint32_t* l_col, const uint64_t* l_val,
+                                      const uint32_t* r_rowptr, const uint32_t* r_col, const uint64_t* r_val,
+                                      const uint64_t* cst, const uint64_t* x_mont, const uint64_t* v_mont,
+                                      uint32_t n_constraints, unsigned long long* d_result, int* d_bad_flag,
+                                      cudaStream_t s);
+
 // Lagrange (K5): n <= 4096 distinct xs (Montgomery), n_polys value vectors -> coefficient vectors;
 // target: n+1 coefficients of prod (X - x_i) (may be null).  d_status: set to 1 if two xs coincide.
 cudaError_t launch_lagrange(int field, const fr_t* xs, const fr_t* ys, uint32_t n, uint32_t n_polys, fr_t* coeffs,

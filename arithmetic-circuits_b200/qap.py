@@ -791,6 +791,69 @@ def create_polynomials(ctx: Context, xs: Sequence[int], ys: Sequence[Sequence[in
 
 
 # ---------------------------------------------------------------------------------------------------
+# Bulletproofs backend: linear constraints (src/Circuit/Bulletproofs.hs:116-129, 329-338)
+# ---------------------------------------------------------------------------------------------------
+SECP256K1_FN = 2   # modulus id of the secp256k1 scalar field (acg_linear_constraints_check only)
+_MODULI = {SECP256K1_FN: 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141}
+
+
+def modulus_of(modulus_id: int) -> int:
+    return _MODULI[modulus_id] if modulus_id in _MODULI else field_constants(modulus_id)["modulus"]
+
+
+def check_linear_constraints(ctx: "Context", modulus_id: int, constraints: Sequence[Dict], assignment: Dict) -> Tuple[int, int]:
+    """checkLinearConstraint (src/Circuit/Bulletproofs.hs:329-338) for a batch of LinearConstraint values against one
+    Assignment, on the device: constraint i holds <=> wL_i.aL + wR_i.aR + wO_i.aO == wV_i.v + c_i over the field
+    `modulus_id` (SECP256K1_FN for the reference's Bulletproofs circuits; BN254_FR / BLS12_381_FR also work).
+    constraints: dicts {"wL", "wR", "wO", "wV": {index: weight}, "c": constant} (LinearConstraint, :116-129);
+    assignment: {"aL", "aR", "aO", "v": {index: value}} -- a wire it lacks counts as 0 (dotProduct,
+    src/Circuit/Affine.hs:121-125).  Returns (number of violated constraints, first violated index or -1)."""
+    r = modulus_of(modulus_id)
+    sides = ("L", "R", "O")
+    dims = {k: 1 + max([-1] + [ix for c in constraints for ix in c["w" + k]]) for k in sides}   # columns the weights use
+    off = {"L": 0, "R": dims["L"], "O": dims["L"] + dims["R"]}
+    n_lhs = dims["L"] + dims["R"] + dims["O"]
+    n_rhs = 1 + max([-1] + [ix for c in constraints for ix in c["wV"]])
+    x = [0] * n_lhs
+    for k in sides:
+        for ix, val in assignment.get("a" + k, {}).items():
+            if ix < dims[k]:
+                x[off[k] + ix] = val % r
+    v = [0] * n_rhs
+    for ix, val in assignment.get("v", {}).items():
+        if ix < n_rhs:
+            v[ix] = val % r
+
+    def csr(rows):
+        rowptr, cols, vals = [0], [], []
+        for row in rows:
+            for col, wgt in sorted(row):
+                if wgt % r:
+                    cols.append(col)
+                    vals.append(wgt % r)
+            rowptr.append(len(cols))
+        return (np.array(rowptr, np.uint32), np.array(cols, np.uint32),
+                to_limbs(vals) if vals else np.zeros((0, 4), np.uint64))
+    lhs = csr([[(off[k] + ix, wgt) for k in sides for ix, wgt in c["w" + k].items()] for c in constraints])
+    rhs = csr([list(c["wV"].items()) for c in constraints])
+    cst = to_limbs([c["c"] % r for c in constraints]) if constraints else np.zeros((0, 4), np.uint64)
+    xs = to_limbs(x) if x else np.zeros((0, 4), np.uint64)
+    vs = to_limbs(v) if v else np.zeros((0, 4), np.uint64)
+    structs = [AcgCsr(m[0].ctypes.data_as(_lib.u32p), m[1].ctypes.data_as(_lib.u32p), m[2].ctypes.data_as(_lib.u64p),
+                      len(m[1])) for m in (lhs, rhs)]
+    nv, fb = C.c_uint64(), C.c_uint64()
+    _check(_lib.lib().acg_linear_constraints_check(ctx._h, modulus_id, len(constraints), n_lhs, n_rhs, C.byref(structs[0]),
+                                                   C.byref(structs[1]), _ptr(cst), _ptr(xs), _ptr(vs), C.byref(nv),
+                                                   C.byref(fb)), ctx)
+    return nv.value, (-1 if fb.value == UINT64_MAX else fb.value)
+
+
+def check_linear_constraint(ctx: "Context", modulus_id: int, constraint: Dict, assignment: Dict) -> bool:
+    """checkLinearConstraint (src/Circuit/Bulletproofs.hs:329-338) for one constraint."""
+    return check_linear_constraints(ctx, modulus_id, [constraint], assignment)[0] == 0
+
+
+# ---------------------------------------------------------------------------------------------------
 # per-wire QAP value (SURVEY 8f N4): QAP f (src/QAP.hs:74-79) as createPolynomials[FFT] returns it
 # ---------------------------------------------------------------------------------------------------
 class QAP:

@@ -35,7 +35,9 @@ extern "C" {
 
 /* field_id: the reference's type parameter `f` / `k`, monomorphised (FFI cannot be class-polymorphic) */
 enum { ACG_FIELD_BN254_FR = 0,       /* Data.Pairing.BN254.Fr   (bench/Circuit.hs:10, test/Test/QAP.hs:12) */
-       ACG_FIELD_BLS12_381_FR = 1 }; /* BASELINE.json configs[4] */
+       ACG_FIELD_BLS12_381_FR = 1,   /* BASELINE.json configs[4] */
+       ACG_FIELD_SECP256K1_FN = 2 }; /* scalar field of secp256k1 (src/Circuit/Bulletproofs.hs): a modulus id of
+                                      * acg_linear_constraints_check ONLY -- contexts exist for the first two */
 
 enum {
     ACG_OK = 0,
@@ -256,6 +258,18 @@ int acg_qap_verify(acg_ctx* ctx, const acg_qap* q, const uint64_t* w, const uint
  * out: n_roots + 1 canonical coefficients.  A partial domain is built on the device (K5 master polynomial) and is
  * limited to 4096 roots. */
 int acg_fft_target(acg_ctx* ctx, uint32_t n_roots, uint64_t* out);
+
+/* ---- linear constraints: replaces checkLinearConstraint of the Bulletproofs backend ------------------------------
+ * (src/Circuit/Bulletproofs.hs:329-338):  wL.aL + wR.aR + wO.aO == wV.v + c  over the scalar field of secp256k1, each
+ * dot product as src/Circuit/Affine.hs:121-125 (missing = 0).  n_constraints constraints at once: `lhs` is the CSR
+ * matrix of the weights over the concatenated assignment x = [aL | aR | aO] (n_lhs_vars elements), `rhs` that of wV over
+ * v (n_rhs_vars), `constants` the c of every constraint; all canonical limbs.  Constraint i holds <=> lhs_i . x ==
+ * rhs_i . v + c_i.  *n_violations / *first_bad as for acg_r1cs_check.  modulus_id: any of the three ids above (the
+ * context's own field does not matter: secp256k1's order is >= 2^255, which the main path's Montgomery arithmetic does not
+ * cover -- this entry point uses its own textbook 4 x 64-bit-limb arithmetic, linear_kernels.cu).  Blocking. */
+int acg_linear_constraints_check(acg_ctx* ctx, int modulus_id, uint32_t n_constraints, uint32_t n_lhs_vars,
+                                 uint32_t n_rhs_vars, const acg_csr* lhs, const acg_csr* rhs, const uint64_t* constants,
+                                 const uint64_t* x, const uint64_t* v, uint64_t* n_violations, uint64_t* first_bad);
 
 /* ---- field ops on the device (K1 self-test surface) ------------------------------------------------
  * op: 0 add, 1 sub, 2 mul, 3 inverse of a (inv 0 = 0, as evalGate treats it, Arithmetic.hs:130).

@@ -999,6 +999,23 @@ def synth_r1cs(F: Field, n: int, seed: int, dense: bool = False):
 
 
 # ----------------------------------------------------------------------------------------------
+# Bulletproofs backend: linear constraints (src/Circuit/Bulletproofs.hs:116-129, 329-338)
+# ----------------------------------------------------------------------------------------------
+SECP256K1_N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141   # order of the secp256k1 group
+
+
+def check_linear_constraint(modulus: int, lc: Dict[str, Dict[int, int]], asg: Dict[str, Dict[int, int]]) -> bool:
+    """checkLinearConstraint, src/Circuit/Bulletproofs.hs:329-338:
+        wL `dotProduct` aL + wR `dotProduct` aR + wO `dotProduct` aO == wV `dotProduct` v + c
+    with dotProduct as src/Circuit/Affine.hs:121-125 (a wire the assignment lacks counts as 0).
+    lc: {"wL", "wR", "wO", "wV": {index: weight}, "c": constant};  asg: {"aL", "aR", "aO", "v": {index: value}}."""
+    dot = lambda wgt, val: sum(c * val.get(ix, 0) for ix, c in wgt.items())
+    lhs = dot(lc["wL"], asg["aL"]) + dot(lc["wR"], asg["aR"]) + dot(lc["wO"], asg["aO"])
+    rhs = dot(lc["wV"], asg["v"]) + lc["c"]
+    return (lhs - rhs) % modulus == 0
+
+
+# ----------------------------------------------------------------------------------------------
 # limb helpers shared by tests
 # ----------------------------------------------------------------------------------------------
 

@@ -657,6 +657,54 @@ def test_reference_gate_mix_split_rows_one_launch(acg, ctx_bn):
     m.free()
 
 
+@pytest.mark.parametrize("modulus_id", [2, 0, 1])
+def test_linear_constraints_bulletproofs(acg, _ctx_bn, modulus_id):
+    """checkLinearConstraint (src/Circuit/Bulletproofs.hs:329-338) over the scalar field of secp256k1 (a modulus >= 2^255,
+    its own arithmetic on the device) and over the two fields of the main path: a batch of random sparse constraints
+    made to hold by solving for the constant, some then broken; counts and first violated index against the big-int
+    oracle; edge values (0, n - 1, weights hitting missing wires); a non-canonical weight is rejected."""
+    ctx = _ctx_bn
+    rnd = random.Random(100 + modulus_id)
+    r = acg.modulus_of(modulus_id)
+    assert r == (O.SECP256K1_N if modulus_id == 2 else FIELDS[modulus_id].r)
+    n_gates, n_in = 300, 40
+    edge = [0, 1, r - 1, r - 2, (1 << 255) % r, (r >> 1) + 1]
+    val = lambda: rnd.choice(edge) if rnd.random() < 0.15 else rnd.randrange(r)
+    asg = {"aL": {i: val() for i in range(n_gates) if rnd.random() < 0.95},      # some wires missing: they count as 0
+           "aR": {i: val() for i in range(n_gates)}, "aO": {i: val() for i in range(n_gates)},
+           "v": {i: val() for i in range(n_in)}}
+    cons = []
+    for i in range(1000):
+        lc = {k: {rnd.randrange(n_gates): val() for _ in range(rnd.randrange(0, 6))} for k in ("wL", "wR", "wO")}
+        lc["wV"] = {rnd.randrange(n_in): val() for _ in range(rnd.randrange(0, 3))}
+        dot = lambda wgt, a: sum(c * a.get(ix, 0) for ix, c in wgt.items())
+        lc["c"] = (dot(lc["wL"], asg["aL"]) + dot(lc["wR"], asg["aR"]) + dot(lc["wO"], asg["aO"]) - dot(lc["wV"], asg["v"])) % r
+        if i % 97 == 5:
+            lc["c"] = (lc["c"] + 1 + rnd.randrange(r - 1)) % r       # broken
+        cons.append(lc)
+    want = [O.check_linear_constraint(r, lc, asg) for lc in cons]
+    bad = [i for i, ok in enumerate(want) if not ok]
+    assert len(bad) == len([i for i in range(1000) if i % 97 == 5])
+    assert acg.check_linear_constraints(ctx, modulus_id, cons, asg) == (len(bad), bad[0])
+    good = [lc for lc, ok in zip(cons, want) if ok]
+    assert acg.check_linear_constraints(ctx, modulus_id, good, asg) == (0, -1)
+    assert acg.check_linear_constraint(ctx, modulus_id, good[0], asg) is True
+    assert acg.check_linear_constraint(ctx, modulus_id, cons[bad[0]], asg) is False
+    assert acg.check_linear_constraints(ctx, modulus_id, [], asg) == (0, -1)
+    # the ABI rejects a weight >= n instead of reducing it
+    import ctypes as C
+    L = acg._lib.lib()
+    rp = np.array([0, 1], np.uint32); col = np.array([0], np.uint32); wv = acg.to_limbs([r])
+    zero_rp = np.array([0, 0], np.uint32)
+    A = acg.qap.AcgCsr(rp.ctypes.data_as(acg._lib.u32p), col.ctypes.data_as(acg._lib.u32p), wv.ctypes.data_as(acg._lib.u64p), 1)
+    B = acg.qap.AcgCsr(zero_rp.ctypes.data_as(acg._lib.u32p), col.ctypes.data_as(acg._lib.u32p), wv.ctypes.data_as(acg._lib.u64p), 0)
+    one = acg.to_limbs([1])
+    nv, fb = C.c_uint64(), C.c_uint64()
+    rc = L.acg_linear_constraints_check(ctx._h, modulus_id, 1, 1, 0, C.byref(A), C.byref(B), acg.qap._ptr(one), acg.qap._ptr(one),
+                                        None, C.byref(nv), C.byref(fb))
+    assert rc == -2
+
+
 # ------------------------------------------------------------------------------------------------ BASELINE configs at full size
 def _default_geometry(acg, ctx):
     ctx.set_tiled_variant(0)
