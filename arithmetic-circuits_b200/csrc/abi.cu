@@ -34,6 +34,10 @@ struct acg_ctx {
     size_t staging_cap = 0;                  //   (elements)
     // work buffers of acg_qap_witness, kept between calls (seven vectors of N elements: a fresh cudaMalloc / cudaFree
     // pair per buffer and call cost more than the kernels at N = 2^22)
+    // where the block scheduler puts block b of the tiled kernel's full grid (SM id per block), probed once per tile
+    // geometry (kernels.h CtaRun); empty after a probe that did not see every SM filled evenly
+    std::vector<uint32_t> placement[kNumTileVariants];
+    bool placement_probed[kNumTileVariants] = {};
     fr_t* work[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t work_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -83,6 +87,8 @@ struct acg_r1cs {
     uint32_t n_tiles = 0;
     int variant = 0;
     std::vector<std::pair<uint32_t, uint32_t>> long_ranges;  // local row ranges too wide for a tile
+    CtaRun* d_runs = nullptr;         // weighted runs of the tiled kernel's CTAs (kernels.h CtaRun), or null
+    uint32_t n_runs = 0;
     uint32_t* d_long_rows = nullptr;  // .. flattened: the rows the warp-per-row kernel handles in one launch
     uint32_t n_long_rows = 0;
 };
@@ -303,6 +309,61 @@ int work_buffer(acg_ctx* ctx, int slot, size_t n, fr_t** out) {
     return ACG_OK;
 }
 
+// Relative tile rates of the 1st .. n-th CTA to arrive on an SM (kernels.h CtaRun), measured with the per-CTA timeline
+// of the instrumented build on B200 for the 128-row geometries (profiles/r02_cta_timeline_*.txt).
+// ACG_K2_WAVE_SHARES="a,b,c,.." overrides them (one relative weight per resident CTA; "0": equal runs); geometries
+// without a measurement get equal runs.  Returns the number of weights, 0 for equal runs.
+unsigned tile_rate_weights(int variant, unsigned ctas, double* wgt) {
+    unsigned n = 0;
+    if (const char* env = getenv("ACG_K2_WAVE_SHARES")) {
+        const char* p = env;
+        while (*p && n < 8) {
+            char* end = nullptr;
+            const double v = strtod(p, &end);
+            if (end == p) break;
+            wgt[n++] = v;
+            p = (*end == ',') ? end + 1 : end;
+        }
+        if (n != ctas) return 0;
+    } else if ((variant == 0 || variant == 4 || variant == 6) && ctas == 5) {
+        static const double dflt[5] = {1.0 / 3.99, 1.0 / 4.12, 1.0 / 4.45, 1.0 / 5.10, 1.0 / 5.95};
+        for (n = 0; n < 5; ++n) wgt[n] = dflt[n];
+    } else {
+        return 0;
+    }
+    for (unsigned i = 0; i < n; ++i)
+        if (!(wgt[i] > 0.0)) return 0;
+    return n;
+}
+
+// Block placement of the tiled kernel's full grid for this geometry (probed once): smid per block, or empty
+int get_placement(acg_ctx* ctx, int variant, const std::vector<uint32_t>** out) {
+    *out = &ctx->placement[variant];
+    if (ctx->placement_probed[variant]) return ACG_OK;
+    ctx->placement_probed[variant] = true;
+    const uint32_t ctas = tiled_ctas_per_sm(variant);
+    const uint32_t grid = (uint32_t)ctx->sm_count * ctas;
+    DevBuf d_smid, d_arrived;
+    CU(ctx, d_smid.alloc((size_t)grid * sizeof(uint32_t)));
+    CU(ctx, d_arrived.alloc(sizeof(unsigned int)));
+    CU(ctx, cudaMemsetAsync(d_arrived.p, 0, sizeof(unsigned int), ctx->stream));
+    CU(ctx, cudaMemsetAsync(d_smid.p, 0xFF, (size_t)grid * sizeof(uint32_t), ctx->stream));
+    uint32_t launched = 0;
+    CU(ctx, launch_probe_placement(variant, ctx->sm_count, d_smid.as<uint32_t>(), d_arrived.as<unsigned int>(), &launched,
+                                   ctx->stream));
+    ++ctx->launches;
+    std::vector<uint32_t> smid(grid);
+    CU(ctx, cudaMemcpyAsync(smid.data(), d_smid.p, (size_t)grid * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    // usable only if every SM received exactly `ctas` blocks (nothing else was resident, the grid filled the chip)
+    std::map<uint32_t, uint32_t> per_sm;
+    for (uint32_t v : smid) ++per_sm[v];
+    bool ok = launched == grid && per_sm.size() == (size_t)ctx->sm_count;
+    for (const auto& kv : per_sm) ok = ok && kv.second == ctas;
+    if (ok) ctx->placement[variant] = std::move(smid);
+    return ACG_OK;
+}
+
 struct HostTile {
     uint32_t row0, nrows, e0[3], ne[3], width[3];
 };
@@ -422,8 +483,16 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* wv, unsigned l
         }
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[2 * ctx->prof_used], s));
         if (m->n_tiles) {
-            DevTileStream ts{m->d_stream, m->d_meta, m->d_far_cols, m->n_tiles, (uint32_t)m->variant,
-                             (uint32_t)(m->blob_bytes / 16), m->n_cols};
+            DevTileStream ts{};
+            ts.blobs = m->d_stream;
+            ts.meta = m->d_meta;
+            ts.far_cols = m->d_far_cols;
+            ts.n_tiles = m->n_tiles;
+            ts.variant = (uint32_t)m->variant;
+            ts.blobs_len16 = (uint32_t)(m->blob_bytes / 16);
+            ts.n_cols = m->n_cols;
+            ts.runs = m->d_runs;
+            ts.n_runs = m->n_runs;
             // back-to-back checks of the same system may overlap (see CheckEpilogue): every entry point bumps ctx->ops,
             // so "the previous operation was that check" is ops == last_check_op + 1 -- nothing, in particular no
             // witness update, was enqueued through this context in between (the witnesses of the two checks may be
@@ -681,6 +750,7 @@ void acg_r1cs_free(acg_r1cs* m) {
     cudaFree(m->d_meta);
     cudaFree(m->d_far_cols);
     cudaFree(m->d_long_rows);
+    cudaFree(m->d_runs);
     delete m;
 }
 
@@ -943,32 +1013,64 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
         }
         h.n_general = n_prod;
         h.n_const = n_const;
+        // rows sorted by shape (lengths of their A, B, C rows: rows of one shape end up in the same warps), and the ELL
+        // widths per warp of that order (kernels.h TileWarp)
+        std::vector<uint32_t> order(t.nrows);
+        for (uint32_t r = 0; r < t.nrows; ++r) order[r] = r;
+        auto row_len = [&](int k, uint32_t r) { return local_rp[k][t.row0 + r + 1] - local_rp[k][t.row0 + r]; };
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+            const uint32_t kx = (row_len(1, x) << 16) | (row_len(0, x) << 8) | row_len(2, x);
+            const uint32_t ky = (row_len(1, y) << 16) | (row_len(0, y) << 8) | row_len(2, y);
+            return kx < ky;
+        });
+        TileWarp warps[kMaxTileWarps] = {};
+        const uint32_t n_warps = (t.nrows + 31u) / 32u;
+        uint32_t n_words = 0;
+        for (uint32_t q = 0; q < n_warps; ++q) {
+            TileWarp& tw = warps[q];
+            tw.words0 = (uint16_t)n_words;
+            tw.nrows = (uint8_t)std::min(32u, t.nrows - 32u * q);
+            for (uint32_t l = 0; l < tw.nrows; ++l)
+                for (int k = 0; k < 3; ++k) tw.width[k] = std::max<uint8_t>(tw.width[k], (uint8_t)row_len(k, order[32u * q + l]));
+            n_words += (uint32_t)(tw.width[0] + tw.width[1] + tw.width[2]) * tw.nrows;
+        }
         // layout (offsets from the blob start; the blob lands at shared-memory offset 0)
         auto up = [](uint32_t x, uint32_t a) { return (x + a - 1) / a * a; };
-        h.off_words = (uint32_t)sizeof(TileHeader);
-        h.off_next_far = up(h.off_words + (t.width[0] + t.width[1] + t.width[2]) * t.nrows * 4u, 16);
+        h.off_words = up(kTilePermOffset + t.nrows, 16);
+        h.off_next_far = up(h.off_words + n_words * 4u, 16);
         h.off_gop = up(h.off_next_far + h.next_n_far * 4u, 16);
         h.off_gval = up(h.off_gop + n_prod * 2u, 32);
-        // entry words, slot-major
-        for (int k = 0; k < 3; ++k)
-            for (uint32_t j = 0; j < t.width[k]; ++j)
-                for (uint32_t r = 0; r < t.nrows; ++r) {
-                    const uint32_t s0 = local_rp[k][t.row0 + r], s1 = local_rp[k][t.row0 + r + 1];
-                    if (s0 + j >= s1) {
-                        put32(term_chunk(kZero, false));
-                        continue;
+        // warp records, row offsets, then the entry words: per warp, slot-major over the warp's rows
+        stream.resize(base + kTileWarpsOffset, 0);
+        for (uint32_t q = 0; q < kMaxTileWarps; ++q) {
+            put16(warps[q].words0);
+            stream.push_back(warps[q].nrows);
+            for (int k = 0; k < 3; ++k) stream.push_back(warps[q].width[k]);
+            put16(0);
+        }
+        for (uint32_t r = 0; r < t.nrows; ++r) stream.push_back((uint8_t)order[r]);
+        stream.resize(base + h.off_words, 0);
+        for (uint32_t q = 0; q < n_warps; ++q)
+            for (int k = 0; k < 3; ++k)
+                for (uint32_t j = 0; j < warps[q].width[k]; ++j)
+                    for (uint32_t l = 0; l < warps[q].nrows; ++l) {
+                        const uint32_t r = order[32u * q + l];
+                        const uint32_t s0 = local_rp[k][t.row0 + r], s1 = local_rp[k][t.row0 + r + 1];
+                        if (s0 + j >= s1) {
+                            put32(term_chunk(kZero, false));
+                            continue;
+                        }
+                        const uint32_t word = tagged_col[k][s0 + j];
+                        const uint32_t tag = word >> 30;
+                        if (tag == kTagGeneral) {
+                            const int32_t g = gid[k][s0 + j - t.e0[k]];
+                            put32(g >= 0 ? (geom.prod_in_place ? blob_chunk(h.off_gval, (uint32_t)g)
+                                                               : term_chunk(kProd0 + (uint32_t)g, false))
+                                         : blob_chunk(h.off_gval, n_prod + (uint32_t)(~g)));
+                        } else {
+                            put32((tag == kTagMinusOne ? kTermSign : 0u) | chunk_of(word & kColMask));
+                        }
                     }
-                    const uint32_t word = tagged_col[k][s0 + j];
-                    const uint32_t tag = word >> 30;
-                    if (tag == kTagGeneral) {
-                        const int32_t g = gid[k][s0 + j - t.e0[k]];
-                        put32(g >= 0 ? (geom.prod_in_place ? blob_chunk(h.off_gval, (uint32_t)g)
-                                                           : term_chunk(kProd0 + (uint32_t)g, false))
-                                     : blob_chunk(h.off_gval, n_prod + (uint32_t)(~g)));
-                    } else {
-                        put32((tag == kTagMinusOne ? kTermSign : 0u) | chunk_of(word & kColMask));
-                    }
-                }
         stream.resize(base + h.off_next_far, 0);
         for (uint32_t f = 0; f < h.next_n_far; ++f) put32(far_all[final_tiles[ti + 1].far_off + f]);
         stream.resize(base + h.off_gop, 0);
@@ -1038,6 +1140,75 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
         CU(ctx, launch_to_mont_scattered(ctx->field, m->d_stream, d_goffs.as<uint32_t>(), gval_offs.size(), ctx->d_flag,
                                          ctx->stream));
         ++launches;
+    }
+    // weighted runs of the tiled kernel's CTAs (kernels.h CtaRun) when the system fills the chip
+    {
+        const uint32_t ctas = tiled_ctas_per_sm(m->variant);
+        const uint32_t grid = (uint32_t)ctx->sm_count * ctas;
+        double wgt[8];
+        const unsigned n_w = n_tiles_out >= grid ? tile_rate_weights(m->variant, ctas, wgt) : 0u;
+        const std::vector<uint32_t>* place = nullptr;
+        if (n_w) {
+            int prc = get_placement(ctx, m->variant, &place);
+            if (prc) return prc;
+        }
+        if (n_w && place && place->size() == grid) {
+            const uint32_t n_sm = (uint32_t)ctx->sm_count;
+            // rank of every block among the blocks of its SM (arrival order = block order), SMs numbered by first use
+            std::map<uint32_t, uint32_t> sm_pos, sm_seen;
+            std::vector<uint32_t> rank(grid), pos(grid);
+            for (uint32_t b = 0; b < grid; ++b) {
+                const uint32_t sm = (*place)[b];
+                if (!sm_pos.count(sm)) {
+                    const uint32_t p = (uint32_t)sm_pos.size();
+                    sm_pos[sm] = p;
+                }
+                pos[b] = sm_pos[sm];
+                rank[b] = sm_seen[sm]++;
+            }
+            // every SM gets the same number of tiles (+-1); inside an SM they are dealt to its CTAs one at a time, always
+            // to the CTA that would finish its share first (list scheduling with the per-rank tile times 1 / weight);
+            // the tiles of rank k over all SMs form one contiguous region of the stream, so that every SM works on every
+            // part of the system (later rows gather from a wider part of the witness and cost more)
+            std::vector<std::vector<uint32_t>> cnt(n_sm, std::vector<uint32_t>(n_w, 0));
+            for (uint32_t p = 0; p < n_sm; ++p) {
+                const uint32_t total = n_tiles_out / n_sm + (p < n_tiles_out % n_sm ? 1u : 0u);
+                for (uint32_t i = 0; i < total; ++i) {
+                    unsigned best = 0;
+                    double best_t = 1e300;
+                    for (unsigned k = 0; k < n_w; ++k) {
+                        const double t = (double)(cnt[p][k] + 1u) / wgt[k];
+                        if (t < best_t) {
+                            best_t = t;
+                            best = k;
+                        }
+                    }
+                    ++cnt[p][best];
+                }
+            }
+            std::vector<uint32_t> region0(n_w + 1, 0);  // first tile of rank k's region
+            for (unsigned k = 0; k < n_w; ++k) {
+                uint32_t sum_k = 0;
+                for (uint32_t p = 0; p < n_sm; ++p) sum_k += cnt[p][k];
+                region0[k + 1] = region0[k] + sum_k;
+            }
+            std::vector<std::vector<uint32_t>> before(n_w, std::vector<uint32_t>(n_sm + 1, 0));
+            for (unsigned k = 0; k < n_w; ++k)
+                for (uint32_t p = 0; p < n_sm; ++p) before[k][p + 1] = before[k][p] + cnt[p][k];
+            std::vector<CtaRun> runs(grid);
+            for (uint32_t b = 0; b < grid; ++b) {
+                const uint32_t k = rank[b], p = pos[b];
+                CtaRun& run = runs[b];
+                run = CtaRun{};
+                run.t_begin = region0[k] + before[k][p];
+                run.t_end = run.t_begin + cnt[p][k];
+                if (run.t_begin < run.t_end) run.first = metas[run.t_begin];
+            }
+            CU(ctx, cudaMalloc(&m->d_runs, runs.size() * sizeof(CtaRun)));
+            CU(ctx, cudaMemcpyAsync(m->d_runs, runs.data(), runs.size() * sizeof(CtaRun), cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));  // (`runs` is about to go out of scope)
+            m->n_runs = grid;
+        }
     }
     m->dev.tagged = 1;
     CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

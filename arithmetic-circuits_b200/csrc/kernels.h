@@ -74,6 +74,22 @@ struct alignas(16) TileHeader {
     uint32_t n_const;       // general entries on column 0 (values follow the n_general product coefficients)
 };
 static_assert(sizeof(TileHeader) == 64, "TileHeader must be 64 bytes");
+// Rows are SORTED BY SHAPE inside a tile (by the lengths of their A, B and C rows), thread t handles the t-th row of
+// that order, and the entry words are laid out per WARP: warp q owns the words of its <= 32 rows, slot-major, with
+// the ELL widths of ITS rows -- in the synthetic family 56 % of the rows have two-entry A and B rows, and their warps
+// no longer execute the third (padding) slot that a tile-wide width would force on them.  The header is followed by
+// kMaxTileWarps of these records and by one byte per thread: the row's offset from row0 (for emitted vectors and
+// violation reports, which are by original row).
+struct TileWarp {
+    uint16_t words0;   // first word of the warp's block, in words from off_words
+    uint8_t nrows;     // rows of this warp (<= 32)
+    uint8_t width[3];  // ELL widths of A, B, C over the warp's rows
+    uint8_t pad[2];
+};
+static_assert(sizeof(TileWarp) == 8, "TileWarp must be 8 bytes");
+constexpr uint32_t kMaxTileWarps = 8;
+constexpr uint32_t kTileWarpsOffset = 64;                                  // byte offset of the TileWarp records
+constexpr uint32_t kTilePermOffset = kTileWarpsOffset + kMaxTileWarps * 8; // .. and of the row-offset bytes
 constexpr uint32_t kTermSign = 0x80000000u;
 
 // Tiled kernel geometry (see DESIGN.md "K2"); the variant is bound when the system is uploaded.
@@ -109,8 +125,8 @@ ACG_HD constexpr uint32_t swz16(uint32_t chunk) {
     return chunk ^ ((chunk >> 3) & 1u);
 }
 constexpr uint32_t tile_blob_capacity(const TileGeometry& g) {
-    return 64u + g.threads * g.max_slots * 4u + g.max_far * 4u + ((g.max_gen * 2u + 15u) / 16u) * 16u + 16u +
-           (g.max_gen + g.max_const) * 32u;
+    return 64u + kMaxTileWarps * 8u + (g.threads + 15u) / 16u * 16u + g.threads * g.max_slots * 4u + g.max_far * 4u +
+           ((g.max_gen * 2u + 15u) / 16u) * 16u + 16u + (g.max_gen + g.max_const) * 32u;
 }
 // shared-memory offset of the term array (the blob sits at offset 0); entry words and operand words address
 // 16-byte chunks from the start of shared memory, so that a word can also point INTO the blob (see below)
@@ -151,6 +167,7 @@ constexpr uint32_t tile_ctas_per_sm(const TileGeometry& g) {
     const uint32_t m = by_smem < by_regs ? by_smem : by_regs;
     return m > 32u ? 32u : m;
 }
+struct CtaRun;
 struct DevTileStream {
     const uint8_t* blobs;       // concatenated tile blobs
     const TileMeta* meta;       // n_tiles records
@@ -159,7 +176,26 @@ struct DevTileStream {
     uint32_t variant;
     uint32_t blobs_len16;       // length of `blobs` in 16-byte units
     uint32_t n_cols;            // witness length
+    // Static split of the tiles over the CTAs when the grid fills the chip (n_runs == gridDim.x): CTA b walks the tiles
+    // [runs[b].t_begin, runs[b].t_end).  The runs are UNEQUAL (see CtaRun); runs == nullptr: equal runs.
+    const CtaRun* runs;
+    uint32_t n_runs;
 };
+// The warp scheduler does not share an SM evenly between its resident CTAs: the first-launched CTA of an SM retires
+// tiles ~30 % faster than the fifth (profiles/r02_cta_timeline_*), and the block scheduler's placement of blocks on SMs
+// is a fixed but irregular pattern (blocks 0..5 go to SMs 142..147, some SMs receive their k-th block a hundred blocks
+// earlier than others).  Equal runs therefore leave the SMs half empty for the last sixth of the kernel.  At upload the
+// library PROBES the placement (k_probe_placement: same launch geometry, every block records its SM), ranks the blocks
+// of each SM by arrival, and cuts the tiles into per-rank regions whose sizes follow the measured tile rates, each
+// region split evenly over the SMs with the remainders placed cyclically -- every SM ends up with the same number of
+// tiles (+-1) and every CTA with a run proportional to the rate it will get.  The record also carries the TileMeta of
+// the run's first tile, so the prologue needs one dependent load, not two.
+struct alignas(64) CtaRun {
+    uint32_t t_begin, t_end;
+    uint32_t pad[6];
+    TileMeta first;
+};
+static_assert(sizeof(CtaRun) == 64, "CtaRun must be 64 bytes");
 
 // All-reduce of the check result over peer memory (multi-GPU row shards): base[r] = rank r's exchange buffer as
 // mapped into this process, 2 (sequence parity) x kMaxPeers slots of 4 x u64 {count, first bad row, sequence, pad}.
@@ -206,6 +242,13 @@ cudaError_t launch_r1cs_rowwise(int field, const DevR1cs& m, const fr_t* w, uint
 cudaError_t launch_r1cs_longrows(int field, const DevR1cs& m, const fr_t* w, const uint32_t* d_rows, uint32_t n_rows,
                                  uint64_t row_base, const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw,
                                  cudaStream_t s);
+// Placement probe (see CtaRun): launches the tiled kernel's grid for geometry `variant` on an empty body; block b writes
+// the id of the SM it landed on to d_smid[b] and leaves only when all blocks have arrived (d_arrived: zeroed counter).
+// *grid_out = blocks launched (SM count x resident CTAs per SM).
+cudaError_t launch_probe_placement(int variant, int sm_count, uint32_t* d_smid, unsigned int* d_arrived,
+                                   uint32_t* grid_out, cudaStream_t s);
+// resident CTAs per SM of the tiled kernel for geometry `variant`
+uint32_t tiled_ctas_per_sm(int variant);
 // TMA-staged tile kernel over the tile stream.
 cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w, uint64_t row_base,
                               const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count, cudaStream_t s);

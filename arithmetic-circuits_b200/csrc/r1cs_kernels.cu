@@ -535,13 +535,23 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     uint8_t* blob = smem;
     uint4* smem4 = reinterpret_cast<uint4*>(smem);  // entry / operand words address 16-byte chunks from here
     // this CTA's run of tiles
-    const uint32_t t_begin = (uint32_t)((uint64_t)blockIdx.x * ts.n_tiles / gridDim.x);
-    const uint32_t t_end = (uint32_t)((uint64_t)(blockIdx.x + 1u) * ts.n_tiles / gridDim.x);
+    uint32_t t_begin, t_end;
+    TileMeta tm;
+    const bool planned = ts.runs != nullptr && gridDim.x == ts.n_runs;  // weighted runs (kernels.h CtaRun)
+    if (planned) {
+        const CtaRun run = ts.runs[blockIdx.x];
+        t_begin = run.t_begin;
+        t_end = run.t_end;
+        tm = run.first;
+    } else {
+        t_begin = (uint32_t)((uint64_t)blockIdx.x * ts.n_tiles / gridDim.x);
+        t_end = (uint32_t)((uint64_t)(blockIdx.x + 1u) * ts.n_tiles / gridDim.x);
+    }
     if (t_begin >= t_end) {  // (the launcher never makes the grid larger than the tile count)
         finish_check(ep);
         return;
     }
-    const TileMeta tm = ts.meta[t_begin];  // the first tile of the run is described from outside
+    if (!planned) tm = ts.meta[t_begin];  // the first tile of the run is described from outside
     // column 0 is the constant wire: w[0] == 1 for every witness the reference builds, and then a general
     // coefficient on column 0 is its own product (kernels.h); anything else takes the multiply-in-place path
     // (loaded here, behind the tile record, and first looked at in P2: off the start-up critical path)
@@ -613,21 +623,28 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
 
         // ---- P3: thread per row, warp-uniform, shared memory only: the sums A.w, B.w, C.w advance together
         //          slot by slot (three independent carry chains); a -1 coefficient negates under a predicate
+        // (rows are sorted by shape and the words laid out per warp, kernels.h TileWarp: this warp's widths, not the tile's)
         bool bad = false;
-        if (tid < h.nrows) {
-            const uint32_t wA = h.width[0], wB = h.width[1], wC = h.width[2];
+        const TileWarp tw = reinterpret_cast<const TileWarp*>(blob + kTileWarpsOffset)[tid >> 5];
+        if (lane < tw.nrows) {
+            const uint32_t wA = tw.width[0], wB = tw.width[1], wC = tw.width[2];
+            const uint32_t* wp = words + tw.words0 + lane;
             fr_t a, b, c;
-            if (wA == 3u && wB == 3u && wC == 1u) {  // the common shape: straight-line code, no predicates
-                row_sums_fixed<P, 3, 3, 1>(smem4, words + tid, h.nrows, a, b, c);
-            } else if (wA == 2u && wB == 2u && wC == 1u) {
-                row_sums_fixed<P, 2, 2, 1>(smem4, words + tid, h.nrows, a, b, c);
+            if (wA == 2u && wB == 2u && wC == 1u) {  // the common shapes: straight-line code, no predicates
+                row_sums_fixed<P, 2, 2, 1>(smem4, wp, tw.nrows, a, b, c);
+            } else if (wA == 3u && wB == 2u && wC == 1u) {
+                row_sums_fixed<P, 3, 2, 1>(smem4, wp, tw.nrows, a, b, c);
+            } else if (wA == 2u && wB == 3u && wC == 1u) {
+                row_sums_fixed<P, 2, 3, 1>(smem4, wp, tw.nrows, a, b, c);
+            } else if (wA == 3u && wB == 3u && wC == 1u) {
+                row_sums_fixed<P, 3, 3, 1>(smem4, wp, tw.nrows, a, b, c);
             } else {
-                row_sums_any<P>(smem4, words + tid, h.nrows, wA, wB, wC, a, b, c);
+                row_sums_any<P>(smem4, wp, tw.nrows, wA, wB, wC, a, b, c);
             }
             if (EMIT) {
                 a = canonical<P>(a);
                 b = fr_add<P>(b, fr_zero<P>());
-                const uint32_t row = h.row0 + tid;
+                const uint32_t row = h.row0 + blob[kTilePermOffset + tid];
                 if (Aw) Aw[row] = a;
                 if (Bw) Bw[row] = b;
                 if (Cw) Cw[row] = c;
@@ -635,9 +652,13 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
             bad = !fr_eq(fr_mul<P>(b, a), c);  // b (<= p) is the vector operand, a the limb-wise scalar
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, bad);
-        if (bal != 0u && lane == 0u) {
-            if (ep.overlap) griddep_wait();  // the scratch pair belongs to the previous check until it completes
-            report_bad_rows(ep.accum, bal, row_base + h.row0 + (tid & ~31u));
+        if (bal != 0u) {  // rare: violated rows -- count them and find the smallest ORIGINAL row among them
+            const uint32_t first = __reduce_min_sync(0xffffffffu, bad ? (uint32_t)blob[kTilePermOffset + tid] : 0xFFFFFFFFu);
+            if (lane == 0u) {
+                if (ep.overlap) griddep_wait();  // the scratch pair belongs to the previous check until it completes
+                atomicAdd(&ep.accum[0], (unsigned long long)__popc(bal));
+                atomicMin(&ep.accum[1], (unsigned long long)(row_base + h.row0 + first));
+            }
         }
         mark(4);
         if (tile + 1u == t_end) break;
@@ -794,6 +815,53 @@ cudaError_t launch_r1cs_longrows(int field, const DevR1cs& m, const fr_t* w, con
     return cudaGetLastError();
 }
 
+// Placement probe (kernels.h CtaRun): the tiled kernel's launch geometry on an empty body
+template <int V>
+__global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerSm)
+    k_probe_placement(uint32_t* __restrict__ smid_out, unsigned int* __restrict__ arrived) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    if (threadIdx.x == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        smid_out[blockIdx.x] = smid;
+        smem[0] = (uint8_t)smid;  // (keeps the dynamic shared memory allocation alive)
+        __threadfence();
+        atomicAdd(arrived, 1u);
+        // stay resident until every block has been placed (they all fit at once: grid = SMs x resident CTAs per SM);
+        // give up after ~50 ms rather than hang if something else occupies the device
+        const long long t0 = clock64();
+        while (atomicAdd(arrived, 0u) < gridDim.x && clock64() - t0 < 100000000ll) __nanosleep(200);
+    }
+    __syncthreads();
+}
+template <int V>
+static cudaError_t launch_probe_impl(int sm_count, uint32_t* d_smid, unsigned int* d_arrived, uint32_t* grid_out,
+                                     cudaStream_t s) {
+    using C = tiled::Cfg<V>;
+    cudaError_t e = cudaFuncSetAttribute(k_probe_placement<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kBytes);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)sm_count * C::kCtasPerSm;
+    *grid_out = grid;
+    k_probe_placement<V><<<grid, kTileGeom[V].threads, C::kBytes, s>>>(d_smid, d_arrived);
+    return cudaGetLastError();
+}
+cudaError_t launch_probe_placement(int variant, int sm_count, uint32_t* d_smid, unsigned int* d_arrived,
+                                   uint32_t* grid_out, cudaStream_t s) {
+    switch (variant) {
+        case 1: return launch_probe_impl<1>(sm_count, d_smid, d_arrived, grid_out, s);
+        case 2: return launch_probe_impl<2>(sm_count, d_smid, d_arrived, grid_out, s);
+        case 3: return launch_probe_impl<3>(sm_count, d_smid, d_arrived, grid_out, s);
+        case 4: return launch_probe_impl<4>(sm_count, d_smid, d_arrived, grid_out, s);
+        case 5: return launch_probe_impl<5>(sm_count, d_smid, d_arrived, grid_out, s);
+        case 6: return launch_probe_impl<6>(sm_count, d_smid, d_arrived, grid_out, s);
+        case 7: return launch_probe_impl<7>(sm_count, d_smid, d_arrived, grid_out, s);
+        default: return launch_probe_impl<0>(sm_count, d_smid, d_arrived, grid_out, s);
+    }
+}
+uint32_t tiled_ctas_per_sm(int variant) {
+    return variant >= 0 && variant < kNumTileVariants ? tile_ctas_per_sm(kTileGeom[variant]) : 0u;
+}
+
 template <class P, bool EMIT, int V>
 static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uint64_t row_base,
                                      const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count,
@@ -813,6 +881,7 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
     }
     unsigned grid = (unsigned)sm_count * ctas;
     if (grid > ts.n_tiles) grid = ts.n_tiles;
+    const DevTileStream& tsw = ts;
 #ifdef ACG_TILED_TIMING_BUILD  // measurement build only (ACG_NVCC_EXTRA=-DACG_TILED_TIMING_BUILD python build.py --force)
     if (V == 0 && !EMIT) {  // ACG_TILED_TIMING=1: run the instrumented instantiation and print its counters
         static const bool timing = getenv("ACG_TILED_TIMING") != nullptr;
@@ -821,7 +890,7 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
                                  (int)C::kBytes);
             unsigned long long z[2][8] = {};
             cudaMemcpyToSymbolAsync(g_tiled_phase_cycles, z, sizeof z, 0, cudaMemcpyHostToDevice, s);
-            k_r1cs_tiled<P, false, 0, true><<<grid, kTileGeom[0].threads, C::kBytes, s>>>(ts, w, row_base, ep, Aw, Bw,
+            k_r1cs_tiled<P, false, 0, true><<<grid, kTileGeom[0].threads, C::kBytes, s>>>(tsw, w, row_base, ep, Aw, Bw,
                                                                                           Cw);
             cudaMemcpyFromSymbolAsync(z, g_tiled_phase_cycles, sizeof z, 0, cudaMemcpyDeviceToHost, s);
             static unsigned long long marks[kMaxTimedCtas][6];
@@ -876,7 +945,7 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = ep.overlap ? 1u : 0u;
-    return cudaLaunchKernelEx(&cfg, k_r1cs_tiled<P, EMIT, V>, ts, w, row_base, ep, Aw, Bw, Cw);
+    return cudaLaunchKernelEx(&cfg, k_r1cs_tiled<P, EMIT, V>, tsw, w, row_base, ep, Aw, Bw, Cw);
 }
 
 cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w, uint64_t row_base,
