@@ -367,7 +367,7 @@ int get_placement(acg_ctx* ctx, int variant, const std::vector<uint32_t>** out) 
 struct HostTile {
     uint32_t row0, nrows, e0[3], ne[3], width[3];
 };
-// Greedy tiling in groups of 4 rows: a tile holds at most geom.threads rows and geom.max_gen
+// Greedy tiling in groups of up to 4 rows: a tile holds at most geom.threads rows and geom.max_gen
 // general-coefficient entries, and the sum of its three ELL widths (max row length per matrix) stays within
 // geom.max_slots.  Rows longer than kMaxEllWidth in any matrix (Split gates, src/QAP.hs:443-473) are left to
 // the row-wise kernel.  gcum[k][r] = number of general entries of matrix k in local rows < r.
@@ -394,39 +394,45 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
         const uint32_t row_cap = geom.threads;
         uint32_t width[3] = {0, 0, 0};
         bool hit_long = false;
+        uint32_t step = 4u;
         while (end < n_local && end - r < row_cap) {
-            const uint32_t g_end = std::min(end + 4u, n_local);
+            uint32_t g_end = std::min(std::min(end + step, n_local), r + row_cap);
+            // a row too long for a tile ends the group before it (and the tile, if it is the group's first row): only
+            // that row goes to the warp-per-row kernel, its neighbours stay in tiles
+            for (uint32_t q = end; q < g_end; ++q)
+                if (rp[0][q + 1] - rp[0][q] > kMaxEllWidth || rp[1][q + 1] - rp[1][q] > kMaxEllWidth ||
+                    rp[2][q + 1] - rp[2][q] > kMaxEllWidth) {
+                    g_end = q;
+                    hit_long = true;
+                    break;
+                }
+            if (g_end == end) break;
             uint32_t nw[3] = {width[0], width[1], width[2]};
             uint64_t gen = 0, cst = 0;
-            bool too_long = false;
             for (int k = 0; k < 3; ++k) {
-                for (uint32_t q = end; q < g_end; ++q) {
-                    const uint32_t len = rp[k][q + 1] - rp[k][q];
-                    if (len > kMaxEllWidth) too_long = true;
-                    nw[k] = std::max(nw[k], len);
-                }
+                for (uint32_t q = end; q < g_end; ++q) nw[k] = std::max(nw[k], rp[k][q + 1] - rp[k][q]);
                 gen += gcum[k][g_end];
                 cst += ccum[k][g_end];
-            }
-            if (too_long) {
-                hit_long = true;
-                break;
             }
             // products needed: general entries off column 0.  One full round of the product phase (one entry
             // per thread) beats one round and a bit: past half a tile of rows, stop at `threads` products.
             const uint64_t prods = (gen - g_base) - (cst - c_base);
             if (nw[0] + nw[1] + nw[2] > geom.max_slots || prods > (uint64_t)geom.max_gen ||
-                cst - c_base > (uint64_t)geom.max_const)
+                cst - c_base > (uint64_t)geom.max_const) {
+                if (end == r && g_end - end > 1u) {  // not even the first group fits: try its first row alone
+                    step = 1u;
+                    continue;
+                }
                 break;
+            }
             if (prods > (uint64_t)geom.threads && end - r >= row_cap / 2u) break;
             for (int k = 0; k < 3; ++k) width[k] = nw[k];
             end = g_end;
         }
-        if (end == r) {  // the next 4-row group cannot be tiled: the row-wise kernel handles it
+        if (end == r) {  // row r cannot open a tile (too long, or alone over a cap): the warp-per-row kernel handles it
             (void)hit_long;
-            const uint32_t g_end = std::min(r + 4u, n_local);
-            add_long(r, g_end);
-            r = g_end;
+            add_long(r, r + 1u);
+            r += 1u;
             continue;
         }
         t.nrows = end - r;

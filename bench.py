@@ -72,7 +72,7 @@ def parse_args():
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: all-reduce of the result pair over peer memory (default) or by NCCL")
     ap.add_argument("--variant", type=int, default=0, choices=list(range(8)), help="tiled kernel geometry (kernels.h kTileGeom): 0-3 rows per tile 128/256/64/32, 4/5 = 128/64 with the natural term layout, 6 = products in place, 7 = 6 + one far buffer (6 CTAs per SM)")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = max(steps, 20) capped at 50")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = max(steps, 50) capped at 200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-qap", action="store_true", help="skip the secondary configs[2] measurement (N = 1)")
     ap.add_argument("--no-one-shot", action="store_true", help="skip e2e.one_shot")
@@ -446,7 +446,7 @@ def run_ours(args, rank, world, local_rank):
         iso_ms = max(per_rank_ms)   # the slowest shard bounds the step
 
     # ---- end to end, one shot: everything from pinned host buffers every step (PCIe-bound)
-    e2e_steps = min(max(args.e2e_steps or max(args.steps, 20), 1), 50)
+    e2e_steps = min(max(args.e2e_steps or max(args.steps, 50), 1), 200)
     pinned = []
     one_shot = None
     wt = torch.from_numpy(w.view(np.int64)).pin_memory()
