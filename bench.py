@@ -309,7 +309,17 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
+        # one process per GPU: run (and allocate the pinned witness buffers) on the CPUs next to this rank's GPU, so that
+        # the N host-to-device copies of a step do not all pull from one NUMA node
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            numa = "cpu affinity set to the GPU's NUMA node (%d cpus)" % len(os.sched_getaffinity(0))
+        except Exception as e:
+            numa = "not set (%s)" % (e,)
         dist.init_process_group("nccl", device_id=dev)
     field_id = FIELD_IDS[args.field]
     scaling = plan(args, world)[2]
@@ -528,6 +538,21 @@ def run_ours(args, rank, world, local_rank):
     l_w = ctx.kernel_launch_count() - l_w0
     for d in dws:
         d.status()   # (raises if an asynchronous update had met a non-canonical element)
+    # the floor of that step: the host-to-device copies alone (every rank its slice, all ranks at once), no all-gather,
+    # no check -- what the PCIe links / host memory of the box deliver when N GPUs pull at the same time
+    h2d_only_ms = None
+    if sliced:
+        s_len, rem0 = sharding.gather_plan(len(dws[0]), world)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(10):
+            dws[i & 1].update_async(hosts[i & 1][rank * s_len:(rank + 1) * s_len], rank * s_len)
+        for d in dws:
+            d.status()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d_only_ms = 1e3 * float(tt.item()) / 10
     sampler.stop()
     t = torch.tensor([e2e_w_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -569,7 +594,7 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": "rows split over %d rank(s), 1 all-reduce of the result pair per step (%s)" % (
                            world, {"p2p": "fused: the check kernel's last CTA stores the pair into every peer's memory over NVLink (CUDA IPC) and reduces", "nccl": "NCCL",
                                    "none": "single GPU: none"}[collective]),
-                       "setup_s": {"generate": round(t_gen, 2), "upload": round(t_up, 2)}},
+                       "setup_s": {"generate": round(t_gen, 2), "upload": round(t_up, 2)}, "host_numa": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "kernel": "k_r1cs_tiled" if args.kernel == "tiled" else "k_r1cs_rowwise",
@@ -590,6 +615,7 @@ def run_ours(args, rank, world, local_rank):
                                        "all-gather over NVLink completes it; two device vectors, copy i+1 overlaps all-gather + check i" % world)
                                       if sliced else "whole witness, copy stream; two device vectors, copy i+1 overlaps check i",
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_w_s / e2e_steps,
+                    "h2d_only_ms_per_step": h2d_only_ms,
                     "call": "acg_witness_update_async (new witness from pinned host memory) + acg_r1cs_check against the system "
                             "resident on the device -- the reference, too, keeps its QAP value in memory between calls",
                     "one_shot": one_shot},

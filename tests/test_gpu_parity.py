@@ -705,6 +705,21 @@ def test_linear_constraints_bulletproofs(acg, _ctx_bn, modulus_id):
     assert rc == -2
 
 
+def test_reference_fixture_replay_gpu(acg, _ctx_bn):
+    """tools/replay_fixtures.py with the GPU path switched on, on the committed file in DumpFixtures.hs's format: QAP
+    values (Lagrange and FFT builds), verifyAssignment, h and h with deltas from the device equal the file's."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("replay_fixtures", os.path.join(root, "tools", "replay_fixtures.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(root, "tests", "golden", "reference_format_fixtures.json")) as f:
+        fixtures = json.load(f)
+    n, failures = mod.replay(fixtures, use_gpu=True)
+    assert n >= 50 and not failures, failures
+
+
 # ------------------------------------------------------------------------------------------------ BASELINE configs at full size
 def _default_geometry(acg, ctx):
     ctx.set_tiled_variant(0)

@@ -106,3 +106,25 @@ def test_json_round_trip_random_circuits(acg):
         assert (a.words == b.words).all()
 
     check()
+
+
+def test_reference_fixture_replay_cpu():
+    """tools/replay_fixtures.py on a file in the exact format tools/DumpFixtures.hs writes (here produced by the oracle:
+    tests/golden/reference_format_fixtures.json): the reader understands the aeson encodings of circuit, inputs, roots,
+    assignment, QAP value and h, and oracle and host mirror agree with every value in it.  With a file dumped by the real
+    reference this is the test that pins value-level parity."""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("replay_fixtures", os.path.join(root, "tools", "replay_fixtures.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(root, "tests", "golden", "reference_format_fixtures.json")) as f:
+        fixtures = json.load(f)
+    n, failures = mod.replay(fixtures, use_gpu=False)
+    assert n >= 30 and not failures, failures
+    # a corrupted value is caught
+    fixtures[0]["h"][0] += 1
+    n, failures = mod.replay(fixtures, use_gpu=False)
+    assert len(failures) == 1 and "oracle h" in failures[0]
