@@ -425,7 +425,7 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
                 }
                 break;
             }
-            if (prods > (uint64_t)geom.threads && end - r >= row_cap / 2u) break;
+            if (geom.max_gen <= 2u * geom.threads && prods > (uint64_t)geom.threads && end - r >= row_cap / 2u) break;
             for (int k = 0; k < 3; ++k) width[k] = nw[k];
             end = g_end;
         }
@@ -878,6 +878,11 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     const uint32_t* cc[3] = {ccum[0].data(), ccum[1].data(), ccum[2].data()};
     // ---- tile stream (see kernels.h): one self-contained blob per tile, entries in ELL order
     m->variant = ctx->tiled_variant;
+    if (m->variant == 0 && n_local) {  // default geometry: systems dense in general coefficients get the roomier one
+        uint64_t prods = 0;
+        for (int k = 0; k < 3; ++k) prods += (uint64_t)gcum[k][n_local] - ccum[k][n_local];
+        if (prods * 10u > (uint64_t)n_local * 16u) m->variant = kDenseTileVariant;  // > 1.6 products per row
+    }
     const TileGeometry geom = kTileGeom[m->variant];
     std::vector<HostTile> tiles;
     build_tiles(geom, rp, gc, cc, n_local, tiles, m->long_ranges);

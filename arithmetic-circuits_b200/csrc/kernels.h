@@ -107,12 +107,18 @@ struct TileGeometry {
     uint32_t reg_budget; // registers per thread the kernel is compiled for (bounds the resident CTAs per SM)
 };
 constexpr uint32_t kMaxEllWidth = 8;
-constexpr int kNumTileVariants = 8;
+constexpr int kNumTileVariants = 9;
+// 0: the default (128-row tiles); 1-3: 256 / 64 / 32 rows; 4, 5: 128 / 64 rows with the natural term layout (no swizzle);
+// 6: products written over their coefficients; 7: 6 + one far buffer (6 CTAs per SM); 8: the geometry for systems dense
+// in general coefficients -- room for 4 products per row (512 per tile, in place), chosen automatically at upload when
+// the default would have to cut its tiles down to a third of their rows to stay within 160 products.
+constexpr int kDenseTileVariant = 8;
 constexpr TileGeometry kTileGeom[kNumTileVariants] = {
     {128, 10, 160, 192, 288, 96, 1, 2, 0, 96}, {256, 10, 320, 320, 576, 192, 1, 2, 0, 96},
     {64, 10, 96, 128, 160, 64, 1, 2, 0, 96},   {32, 10, 64, 96, 96, 32, 1, 2, 0, 96},
     {128, 10, 160, 192, 288, 96, 0, 2, 0, 96}, {64, 10, 96, 128, 160, 64, 0, 2, 0, 96},
-    {128, 10, 160, 192, 288, 96, 1, 2, 1, 96}, {128, 10, 160, 192, 288, 96, 1, 1, 1, 85}};
+    {128, 10, 160, 192, 288, 96, 1, 2, 1, 96}, {128, 10, 160, 192, 288, 96, 1, 1, 1, 85},
+    {128, 10, 512, 192, 288, 160, 1, 2, 1, 96}};
 // Shared memory is addressed in 16-byte CHUNKS from the start of the CTA's dynamic shared memory.  A term (32 bytes)
 // occupies the two chunks of one 32-byte unit; an entry word names the chunk that holds its LOW half and the high
 // half is the other chunk of the unit (word ^ 1).  Eight lanes of a 128-bit shared-memory access are served per

@@ -855,6 +855,7 @@ cudaError_t launch_probe_placement(int variant, int sm_count, uint32_t* d_smid, 
         case 5: return launch_probe_impl<5>(sm_count, d_smid, d_arrived, grid_out, s);
         case 6: return launch_probe_impl<6>(sm_count, d_smid, d_arrived, grid_out, s);
         case 7: return launch_probe_impl<7>(sm_count, d_smid, d_arrived, grid_out, s);
+        case 8: return launch_probe_impl<8>(sm_count, d_smid, d_arrived, grid_out, s);
         default: return launch_probe_impl<0>(sm_count, d_smid, d_arrived, grid_out, s);
     }
 }
@@ -967,6 +968,7 @@ cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w,
         case 5: ACG_TILED_V(5); break;
         case 6: ACG_TILED_V(6); break;
         case 7: ACG_TILED_V(7); break;
+        case 8: ACG_TILED_V(8); break;
         default: ACG_TILED_V(0); break;
     }
 #undef ACG_TILED_V

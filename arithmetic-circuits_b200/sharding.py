@@ -7,7 +7,7 @@ peer access -- it is also what the CPU tests run over gloo.  No other data-path 
 QAP build stays single-GPU."""
 from __future__ import annotations
 
-from typing import Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -37,6 +37,28 @@ def row_shard_balanced(rowptrs: Sequence[np.ndarray], world_size: int, rank: int
     for k in range(1, world_size + 1):
         cuts[k] = max(cuts[k], cuts[k - 1])
     return cuts[rank], cuts[rank + 1]
+
+
+def rebalance_cuts(cuts: Sequence[int], times: Sequence[float]) -> List[int]:
+    """Cost-balanced contiguous row blocks from one measurement: `cuts` (world + 1 boundaries) are the current blocks
+    and `times` what each block's check took.  The cost per row is taken as constant inside a measured block -- later
+    rows of a circuit built gate by gate gather from a wider part of the witness and cost more -- and the new boundaries
+    cut the cumulative cost into equal parts.  Rows stay contiguous and in order; every block keeps at least one row."""
+    world = len(times)
+    assert len(cuts) == world + 1 and all(t > 0 for t in times)
+    total = float(sum(times))
+    new = [cuts[0]]
+    k, acc = 0, 0.0     # block being consumed, cost before it
+    for j in range(1, world):
+        target = total * j / world
+        while k < world - 1 and acc + times[k] < target:
+            acc += times[k]
+            k += 1
+        frac = (target - acc) / times[k]
+        b = cuts[k] + int(round(frac * (cuts[k + 1] - cuts[k])))
+        new.append(min(max(b, new[-1] + 1), cuts[-1] - (world - j)))
+    new.append(cuts[-1])
+    return new
 
 
 def connect_peers(ctx, group=None):

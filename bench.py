@@ -71,11 +71,13 @@ def parse_args():
                     help="first timed region: do not overlap consecutive checks (plain launches)")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: all-reduce of the result pair over peer memory (default) or by NCCL")
-    ap.add_argument("--variant", type=int, default=0, choices=list(range(8)), help="tiled kernel geometry (kernels.h kTileGeom): 0-3 rows per tile 128/256/64/32, 4/5 = 128/64 with the natural term layout, 6 = products in place, 7 = 6 + one far buffer (6 CTAs per SM)")
+    ap.add_argument("--variant", type=int, default=0, choices=list(range(9)), help="tiled kernel geometry (kernels.h kTileGeom): 0-3 rows per tile 128/256/64/32, 4/5 = 128/64 with the natural term layout, 6 = products in place, 7 = 6 + one far buffer (6 CTAs per SM), 8 = room for 4 products per row (chosen automatically for dense systems)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = max(steps, 50) capped at 200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-qap", action="store_true", help="skip the secondary configs[2] measurement (N = 1)")
     ap.add_argument("--no-one-shot", action="store_true", help="skip e2e.one_shot")
+    ap.add_argument("--no-balance", action="store_true",
+                    help="N > 1: keep equal row blocks (default: one timing pass, then cost-balanced contiguous blocks)")
     return ap.parse_args()
 
 
@@ -190,8 +192,9 @@ def cpu_check_throughput(g, w, field_id, n_threads, min_seconds, max_reps):
     return g.n_rows / min(times), times
 
 
-def make_workload(acg, args, world, rank):
-    """-> (GenQAP of this rank's rows, full honest witness, (row_begin, row_end), total rows, generate seconds)"""
+def make_workload(acg, args, world, rank, rows=None):
+    """-> (GenQAP of this rank's rows, full honest witness, (row_begin, row_end), total rows, generate seconds).
+    rows: this rank's block when it is not the equal split."""
     from arithmetic_circuits_b200 import sharding
     field_id = FIELD_IDS[args.field]
     total, seed, _ = plan(args, world)
@@ -201,7 +204,7 @@ def make_workload(acg, args, world, rank):
             raise SystemExit("bench.py: --workload mix is a single-GPU workload")
         g, w = acg.synth_mixed_r1cs(field_id, total, seed)
         return g, w, (0, g.n_rows), g.n_rows, time.perf_counter() - t0
-    rb, re = sharding.row_shard(total, world, rank)
+    rb, re = rows if rows is not None else sharding.row_shard(total, world, rank)
     g, w = acg.synth_r1cs(field_id, total, seed, args.dense, rows=(rb, re))
     return g, w, (rb, re), total, time.perf_counter() - t0
 
@@ -332,6 +335,39 @@ def run_ours(args, rank, world, local_rank):
     m = ctx.upload_r1cs(g)
     m.set_row_offset(rb)   # this rank's rows are [rb, re) of the global system
     t_up = time.perf_counter() - t_up
+    # N > 1: the row blocks are contiguous but need not be equal -- later rows of a circuit built gate by gate gather
+    # from a wider part of the (replicated) witness and cost more.  One timing pass over the equal blocks, then the
+    # boundaries are moved so that every rank gets the same COST (sharding.rebalance_cuts) and the blocks are rebuilt.
+    balance = None
+    if world > 1 and not args.no_balance and args.workload == "s":
+        dw0 = ctx.upload_witness(w)
+        r0 = torch.zeros(2, dtype=torch.int64, device=dev)
+        st0 = torch.cuda.current_stream()
+        for _ in range(3):
+            ctx.r1cs_check_async(m, dw0, r0.data_ptr(), st0.cuda_stream)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ea.record(st0)
+        for _ in range(10):
+            ctx.r1cs_check_async(m, dw0, r0.data_ptr(), st0.cuda_stream)
+        eb.record(st0)
+        torch.cuda.synchronize()
+        mine = torch.tensor([ea.elapsed_time(eb) / 10, float(rb), float(re)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        times = [float(x[0].item()) for x in allr]
+        cuts = [int(x[1].item()) for x in allr] + [int(allr[-1][2].item())]
+        new_cuts = sharding.rebalance_cuts(cuts, times)
+        balance = {"equal_blocks_kernel_ms": [round(t, 5) for t in times], "rows_per_rank": [new_cuts[i + 1] - new_cuts[i] for i in range(world)]}
+        dw0.free()
+        m.free()
+        del g, w
+        g, w, (rb, re), total, t_gen2 = make_workload(acg, args, world, rank, rows=(new_cuts[rank], new_cuts[rank + 1]))
+        t_gen += t_gen2
+        t1 = time.perf_counter()
+        m = ctx.upload_r1cs(g)
+        m.set_row_offset(rb)
+        t_up += time.perf_counter() - t1
     dws = [ctx.upload_witness(w), ctx.upload_witness(w)]   # two resident witnesses, checked alternately
     algo_bytes = m.algorithmic_bytes
     if world > 1:  # shards differ (later rows reference a larger part of the witness): the mean over the ranks
@@ -624,6 +660,8 @@ def run_ours(args, rank, world, local_rank):
         }
         if peer_check is not None:
             line["config"]["peer_allreduce_check"] = peer_check
+        if balance is not None:
+            line["config"]["row_blocks"] = dict(balance, note="contiguous blocks balanced by measured cost (one timing pass over equal blocks)")
         if world == 1 and not args.no_cpu_baseline:
             from oracle import c_oracle as CO
             CO.build()

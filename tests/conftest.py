@@ -33,7 +33,7 @@ def _ctx_bls(acg):
     c.close()
 
 
-@pytest.fixture(params=[0, 1, 2, 3, 4, 5, 6, 7], ids=["tile128", "tile256", "tile64", "tile32", "tile128nat", "tile64nat", "tile128ip", "tile128ip1far"])
+@pytest.fixture(params=[0, 1, 2, 3, 4, 5, 6, 7, 8], ids=["tile128", "tile256", "tile64", "tile32", "tile128nat", "tile64nat", "tile128ip", "tile128ip1far", "tile128dense"])
 def tile_variant(request):
     """Every GPU test runs under both tile geometries of the tiled kernel (bound at upload time)."""
     return request.param

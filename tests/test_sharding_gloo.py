@@ -132,3 +132,22 @@ def test_witness_slices_one_allgather(n):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert got == [(0, True), (1, True)]
+
+
+def test_rebalance_cuts():
+    """Cost-balanced row blocks from one timing of equal blocks: contiguous, ordered, non-empty, and equal in cost under
+    the piecewise-constant cost model."""
+    from arithmetic_circuits_b200 import sharding
+    n, world = 1 << 24, 8
+    cuts = [sharding.row_shard(n, world, r)[0] for r in range(world)] + [n]
+    times = [0.1159, 0.1174, 0.1195, 0.1225, 0.1245, 0.1273, 0.129, 0.1308]
+    new = sharding.rebalance_cuts(cuts, times)
+    assert new[0] == 0 and new[-1] == n and all(a < b for a, b in zip(new, new[1:]))
+    dens = [t / (cuts[i + 1] - cuts[i]) for i, t in enumerate(times)]
+    cost = lambda a, b: sum(dens[i] * max(0, min(b, cuts[i + 1]) - max(a, cuts[i])) for i in range(world))
+    costs = [cost(new[i], new[i + 1]) for i in range(world)]
+    assert max(costs) - min(costs) < 1e-6 * max(costs) * 100
+    assert new[1] - new[0] > new[-1] - new[-2]      # the cheap early rows: bigger blocks
+    assert sharding.rebalance_cuts([0, 10, 20], [1.0, 1.0]) == [0, 10, 20]
+    assert sharding.rebalance_cuts([0, 1, 2, 3], [1.0, 5.0, 1.0]) == [0, 1, 2, 3]      # nothing to move
+    assert sharding.rebalance_cuts([0, 100, 200], [3.0, 1.0]) == [0, 67, 200]
