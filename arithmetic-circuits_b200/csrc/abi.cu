@@ -44,6 +44,9 @@ struct acg_ctx {
     unsigned long long* d_result = nullptr;  // {n_violations, first_bad_row}
     unsigned long long* d_accum = nullptr;   // scratch pair the check kernels accumulate into + CTA ticket (u32)
     unsigned int* d_ticket = nullptr;        //   both reset by the finalising CTA of every check (CheckEpilogue)
+    unsigned long long* d_gate = nullptr;    // ring of kGateRing gate words of the direct hand-over (CheckEpilogue::gate)
+    unsigned long long gate_seq = 0;         //   .. and the running number of the checks that used it
+    bool direct_handover = true;             // ACG_K2_TICKET=1 (a measurement aid): always the ticket path
     int* d_flag = nullptr;
     unsigned long long* h_result = nullptr;  // pinned
     int* h_flag = nullptr;                   // pinned
@@ -89,6 +92,12 @@ struct acg_r1cs {
     std::vector<std::pair<uint32_t, uint32_t>> long_ranges;  // local row ranges too wide for a tile
     CtaRun* d_runs = nullptr;         // weighted runs of the tiled kernel's CTAs (kernels.h CtaRun), or null
     uint32_t n_runs = 0;
+    // the plan behind d_runs: the blocks in the order their runs follow each other in the stream, the run length of
+    // every block, and the tile records (a run carries its first tile's)
+    std::vector<uint32_t> run_order, run_cnt;
+    std::vector<TileMeta> h_meta;
+    std::vector<uint32_t> h_far_cols;  // host copy of d_far_cols
+    uint32_t* d_run_far = nullptr;     // DevTileStream::run_far
     uint32_t* d_long_rows = nullptr;  // .. flattened: the rows the warp-per-row kernel handles in one launch
     uint32_t n_long_rows = 0;
 };
@@ -111,6 +120,7 @@ struct acg_peer {  // exchange buffers of a group of row-shard ranks (one proces
     unsigned long long* local = nullptr;  // this rank's buffer (cudaMalloc)
     void* mapped[kMaxPeers] = {};         // peers' buffers as opened here (null for self / not connected)
     PeerSlots slots{};
+    unsigned long long** d_table = nullptr;  // PeerSlots::base
     unsigned long long seq = 0;
     bool connected = false;
 };
@@ -364,6 +374,40 @@ int get_placement(acg_ctx* ctx, int variant, const std::vector<uint32_t>** out) 
     return ACG_OK;
 }
 
+// (Re)builds the CtaRun table of a system from its plan (run_order, run_cnt, h_meta) and puts it on the device.
+int upload_runs(acg_ctx* ctx, acg_r1cs* m) {
+    const uint32_t grid = (uint32_t)m->run_cnt.size();
+    std::vector<CtaRun> runs(grid);
+    uint32_t t = 0;
+    for (uint32_t b : m->run_order) {
+        CtaRun& run = runs[b];
+        run = CtaRun{};
+        run.t_begin = t;
+        run.t_end = t + m->run_cnt[b];
+        if (run.t_begin < run.t_end) run.first = m->h_meta[run.t_begin];
+        t = run.t_end;
+    }
+    if (t != m->n_tiles) return fail(ctx, ACG_ERR_INTERNAL, "upload_runs: the runs do not cover the tiles");
+    const uint32_t max_far = kTileGeom[m->variant].max_far;
+    std::vector<uint32_t> run_far((size_t)grid * max_far, 0u);
+    for (uint32_t b = 0; b < grid; ++b) {
+        const TileMeta& f = runs[b].first;
+        if (runs[b].t_begin >= runs[b].t_end || f.n_far == 0) continue;
+        if (f.n_far > max_far || (size_t)f.far_off + f.n_far > m->h_far_cols.size())
+            return fail(ctx, ACG_ERR_INTERNAL, "upload_runs: far columns out of range");
+        std::copy(m->h_far_cols.begin() + f.far_off, m->h_far_cols.begin() + f.far_off + f.n_far,
+                  run_far.begin() + (size_t)b * max_far);
+    }
+    if (!m->d_runs) CU(ctx, cudaMalloc(&m->d_runs, runs.size() * sizeof(CtaRun)));
+    if (!m->d_run_far) CU(ctx, cudaMalloc(&m->d_run_far, run_far.size() * sizeof(uint32_t)));
+    CU(ctx, cudaMemcpyAsync(m->d_runs, runs.data(), runs.size() * sizeof(CtaRun), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(m->d_run_far, run_far.data(), run_far.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                            ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));  // (`runs` is about to go out of scope)
+    m->n_runs = grid;
+    return ACG_OK;
+}
+
 struct HostTile {
     uint32_t row0, nrows, e0[3], ne[3], width[3];
 };
@@ -499,6 +543,7 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* wv, unsigned l
             ts.n_cols = m->n_cols;
             ts.runs = m->d_runs;
             ts.n_runs = m->n_runs;
+            ts.run_far = m->d_run_far;
             // back-to-back checks of the same system may overlap (see CheckEpilogue): every entry point bumps ctx->ops,
             // so "the previous operation was that check" is ops == last_check_op + 1 -- nothing, in particular no
             // witness update, was enqueued through this context in between (the witnesses of the two checks may be
@@ -508,6 +553,10 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* wv, unsigned l
             const bool chain = single && !emit && !prof && ctx->overlap_checks && ctx->last_m == m &&
                                ctx->last_stream == s && ctx->ops == ctx->last_check_op + 1;
             if (chain) fin.overlap = 1u;
+            if (!chain && !peer && ctx->direct_handover) {  // one GPU, no overlap: nothing to do at the end of a clean check
+                fin.gate_seq = ++ctx->gate_seq;
+                fin.gate = ctx->d_gate + fin.gate_seq % kGateRing;
+            }
             CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin + m->row_offset, fin, Aw, Bw, Cw, ctx->sm_count, s));
             ++*launches;
             finalised = true;
@@ -603,13 +652,18 @@ int acg_ctx_create(int field_id, int device, acg_ctx** out) {
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc(&ctx->d_result, 2 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMalloc(&ctx->d_accum, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->d_accum, (4 + kGateRing) * sizeof(unsigned long long))) != cudaSuccess)
+        return bail(e, "cudaMalloc");
     ctx->d_ticket = reinterpret_cast<unsigned int*>(ctx->d_accum + 2);
+    ctx->d_gate = ctx->d_accum + 4;
     {
+        if ((e = cudaMemset(ctx->d_accum, 0, (4 + kGateRing) * sizeof(unsigned long long))) != cudaSuccess)
+            return bail(e, "cudaMemset");
         const unsigned long long init[4] = {0ull, ~0ull, 0ull, 0ull};
         if ((e = cudaMemcpy(ctx->d_accum, init, sizeof init, cudaMemcpyHostToDevice)) != cudaSuccess)
             return bail(e, "cudaMemcpy");
     }
+    if (const char* t = getenv("ACG_K2_TICKET")) ctx->direct_handover = atoi(t) == 0;
     if ((e = cudaMalloc(&ctx->d_flag, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMallocHost(&ctx->h_result, 2 * sizeof(unsigned long long))) != cudaSuccess)
         return bail(e, "cudaMallocHost");
@@ -757,6 +811,7 @@ void acg_r1cs_free(acg_r1cs* m) {
     cudaFree(m->d_far_cols);
     cudaFree(m->d_long_rows);
     cudaFree(m->d_runs);
+    cudaFree(m->d_run_far);
     delete m;
 }
 
@@ -1197,28 +1252,16 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
                     ++cnt[p][best];
                 }
             }
-            std::vector<uint32_t> region0(n_w + 1, 0);  // first tile of rank k's region
-            for (unsigned k = 0; k < n_w; ++k) {
-                uint32_t sum_k = 0;
-                for (uint32_t p = 0; p < n_sm; ++p) sum_k += cnt[p][k];
-                region0[k + 1] = region0[k] + sum_k;
-            }
-            std::vector<std::vector<uint32_t>> before(n_w, std::vector<uint32_t>(n_sm + 1, 0));
-            for (unsigned k = 0; k < n_w; ++k)
-                for (uint32_t p = 0; p < n_sm; ++p) before[k][p + 1] = before[k][p] + cnt[p][k];
-            std::vector<CtaRun> runs(grid);
-            for (uint32_t b = 0; b < grid; ++b) {
-                const uint32_t k = rank[b], p = pos[b];
-                CtaRun& run = runs[b];
-                run = CtaRun{};
-                run.t_begin = region0[k] + before[k][p];
-                run.t_end = run.t_begin + cnt[p][k];
-                if (run.t_begin < run.t_end) run.first = metas[run.t_begin];
-            }
-            CU(ctx, cudaMalloc(&m->d_runs, runs.size() * sizeof(CtaRun)));
-            CU(ctx, cudaMemcpyAsync(m->d_runs, runs.data(), runs.size() * sizeof(CtaRun), cudaMemcpyHostToDevice, ctx->stream));
-            CU(ctx, cudaStreamSynchronize(ctx->stream));  // (`runs` is about to go out of scope)
-            m->n_runs = grid;
+            // stream order of the blocks: rank by rank, inside a rank SM position by SM position
+            std::vector<uint32_t> block_at((size_t)n_w * n_sm);
+            for (uint32_t b = 0; b < grid; ++b) block_at[(size_t)rank[b] * n_sm + pos[b]] = b;
+            m->run_order.assign(block_at.begin(), block_at.end());
+            m->run_cnt.assign(grid, 0u);
+            for (uint32_t b = 0; b < grid; ++b) m->run_cnt[b] = cnt[pos[b]][rank[b]];
+            m->h_meta = metas;
+            m->h_far_cols = far_all;
+            int urc = upload_runs(ctx, m);
+            if (urc) return urc;
         }
     }
     m->dev.tagged = 1;
@@ -2312,16 +2355,21 @@ int acg_peer_connect(acg_ctx* ctx, acg_peer* p, const uint8_t* handles) {
     int rc = activate(ctx);
     if (rc) return rc;
     if (!p || p->ctx != ctx || !handles || p->connected) return fail(ctx, ACG_ERR_BAD_ARG, "acg_peer_connect: bad argument");
+    unsigned long long* bases[kMaxPeers] = {};
     for (uint32_t r = 0; r < p->world; ++r) {
         if (r == p->rank) {
-            p->slots.base[r] = p->local;
+            bases[r] = p->local;
             continue;
         }
         cudaIpcMemHandle_t h;
         std::memcpy(&h, handles + (size_t)r * sizeof h, sizeof h);
         CU(ctx, cudaIpcOpenMemHandle(&p->mapped[r], h, cudaIpcMemLazyEnablePeerAccess));
-        p->slots.base[r] = static_cast<unsigned long long*>(p->mapped[r]);
+        bases[r] = static_cast<unsigned long long*>(p->mapped[r]);
     }
+    if (!p->d_table) CU(ctx, cudaMalloc(&p->d_table, sizeof bases));
+    CU(ctx, cudaMemcpy(p->d_table, bases, sizeof bases, cudaMemcpyHostToDevice));
+    p->slots.base = p->d_table;
+    p->slots.own = p->local;
     p->slots.world = p->world;
     p->slots.rank = p->rank;
     p->connected = true;
@@ -2335,6 +2383,7 @@ void acg_peer_free(acg_peer* p) {
     for (uint32_t r = 0; r < kMaxPeers; ++r)
         if (p->mapped[r]) cudaIpcCloseMemHandle(p->mapped[r]);
     cudaFree(p->local);
+    cudaFree(p->d_table);
     delete p;
 }
 

@@ -65,6 +65,17 @@ __device__ __forceinline__ void tma_load_1d_stream(void* smem_dst, const void* g
     tma_load_1d(smem_dst, gmem_src, bytes, bar);
 #endif
 }
+// .. and for the little that the NEXT launch reads before anything else (the first tile of every CTA's run): L2
+// evict-last, so that back-to-back checks of a resident system start from L2 instead of DRAM
+__device__ __forceinline__ void tma_load_1d_evict_last(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
 // pull [p, p + bytes) towards L2 (bytes % 16 == 0, p 16-byte aligned); no completion to wait for
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");

@@ -186,6 +186,10 @@ struct DevTileStream {
     // [runs[b].t_begin, runs[b].t_end).  The runs are UNEQUAL (see CtaRun); runs == nullptr: equal runs.
     const CtaRun* runs;
     uint32_t n_runs;
+    // .. with them, the far witness columns of every run's FIRST tile at a fixed place (max_far words per run, CTA b's at
+    // run_far + b * max_far): a CTA reads them alongside its run record instead of after it -- one round trip to memory
+    // less before the first tile can be staged
+    const uint32_t* run_far;
 };
 // The warp scheduler does not share an SM evenly between its resident CTAs: the first-launched CTA of an SM retires
 // tiles ~30 % faster than the fifth (profiles/r02_cta_timeline_*), and the block scheduler's placement of blocks on SMs
@@ -207,8 +211,11 @@ static_assert(sizeof(CtaRun) == 64, "CtaRun must be 64 bytes");
 // mapped into this process, 2 (sequence parity) x kMaxPeers slots of 4 x u64 {count, first bad row, sequence, pad}.
 constexpr uint32_t kMaxPeers = 8;
 constexpr size_t kPeerBufferBytes = 2 * kMaxPeers * 4 * sizeof(unsigned long long);
+// (The table of bases lives in device memory, not in the struct: a kernel parameter indexed by lane would make the
+// compiler copy the whole parameter block of the check kernel to local memory at the start of every thread.)
 struct PeerSlots {
-    unsigned long long* base[kMaxPeers];
+    unsigned long long* const* base;  // device array of kMaxPeers pointers
+    unsigned long long* own;          // == base[rank]
     uint32_t world, rank;
 };
 // How a check kernel hands over its result.  The kernels accumulate {violation count, first bad row} into the
@@ -220,6 +227,12 @@ struct PeerSlots {
 // same stream (cudaLaunchAttributeProgrammaticStreamSerialization): its CTAs take the place of the previous check's
 // CTAs as those run out of tiles, and it waits for that check to complete (griddepcontrol.wait) only before it
 // touches the shared scratch pair -- consecutive checks overlap their tails, launch latency and cold starts.
+// gate != nullptr (tiled kernel, one GPU, no overlap): the DIRECT hand-over, which costs a clean check nothing at its
+// end.  Block 0 starts by moving the scratch pair (what earlier launches of the same check accumulated; {0, none}
+// otherwise) to `out` and then opens the gate -- a release store of gate_seq, the context's running check number, into
+// one word of a ring --; a warp that finds violated rows (rare) waits for that word and updates `out` itself with
+// atomics.  Nobody finalises: when the grid has drained, `out` is the result.  The ticket path costs the LAST CTA a
+// fence, an atomic round trip, another fence and a load after its last tile -- about 3 us of a 63 us check.
 struct CheckEpilogue {
     unsigned long long* accum;
     unsigned int* ticket;
@@ -227,7 +240,10 @@ struct CheckEpilogue {
     PeerSlots peers;
     unsigned long long seq;
     uint32_t overlap;
+    unsigned long long* gate;
+    unsigned long long gate_seq;
 };
+constexpr uint32_t kGateRing = 256;  // checks of one context that may be in flight on different streams at once
 // Publishes d_result[0..1] to every peer, waits for every peer's pair of step `seq`, leaves {sum of the counts,
 // min of the first bad rows} in d_result (count = ~0 if a peer did not arrive within ~4 s).
 cudaError_t launch_peer_allreduce(const PeerSlots& ps, unsigned long long seq, unsigned long long* d_result,

@@ -109,8 +109,10 @@ __device__ __forceinline__ void peer_allreduce_warp(const PeerSlots& ps, unsigne
                                                     unsigned long long& first) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t par = (uint32_t)(seq & 1ull);
+    unsigned long long* base_lane = lane < ps.world ? ps.base[lane] : nullptr;
+    unsigned long long* base_own = ps.own;
     if (lane < ps.world) {
-        unsigned long long* dst = ps.base[lane] + (size_t)(par * kMaxPeers + ps.rank) * 4u;
+        unsigned long long* dst = base_lane + (size_t)(par * kMaxPeers + ps.rank) * 4u;
         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(cnt) : "memory");
         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(first) : "memory");
         st_release_sys(dst + 2, seq);
@@ -118,7 +120,7 @@ __device__ __forceinline__ void peer_allreduce_warp(const PeerSlots& ps, unsigne
     unsigned long long c = 0ull, f = ~0ull;
     bool timed_out = false;
     if (lane < ps.world) {
-        const unsigned long long* src = ps.base[ps.rank] + (size_t)(par * kMaxPeers + lane) * 4u;
+        const unsigned long long* src = base_own + (size_t)(par * kMaxPeers + lane) * 4u;
         const long long t0 = clock64();
         while (ld_acquire_sys(src + 2) != seq) {
             if (clock64() - t0 > 8000000000ll) {  // ~4 s: a peer never arrived; report instead of hanging the GPU
@@ -150,9 +152,48 @@ __global__ void k_peer_allreduce(PeerSlots ps, unsigned long long seq, unsigned 
     }
 }
 
+// Direct hand-over (kernels.h CheckEpilogue), one thread of block 0: out <- what earlier launches of this check
+// accumulated, scratch reset, gate opened.
+__device__ __forceinline__ void open_gate(const CheckEpilogue& ep) {
+    const unsigned long long cnt = __ldcg(ep.accum), first = __ldcg(ep.accum + 1);
+    ep.out[0] = cnt;
+    ep.out[1] = first;
+    if (cnt != 0ull || first != ~0ull) {
+        ep.accum[0] = 0ull;
+        ep.accum[1] = ~0ull;
+    }
+    __threadfence();
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(ep.gate), "l"(ep.gate_seq) : "memory");
+}
+// One lane of a warp that found violated rows (rare, and kept out of line so that it costs the tile loop no
+// registers): into `out` behind the gate (direct hand-over), else into the scratch pair.
+__device__ __noinline__ void report_violations(unsigned long long* gate, unsigned long long gate_seq,
+                                               unsigned long long* out, unsigned long long* accum, uint32_t overlap,
+                                               unsigned long long n_bad, unsigned long long first) {
+    if (gate != nullptr && out != nullptr) {
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long g;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(g) : "l"(gate) : "memory");
+            if (g == gate_seq) break;
+            // block 0 is dispatched before any other block of the grid, so this wait is microseconds; a word that
+            // never matches means the ring was lapped (kGateRing later checks started while this one ran): fail loudly
+            if (clock64() - t0 > 8000000000ll) __trap();
+            __nanosleep(64);
+        }
+        atomicAdd(&out[0], n_bad);
+        atomicMin(&out[1], first);
+        return;
+    }
+    if (overlap) griddep_wait();  // the scratch pair belongs to the previous check until it completes
+    atomicAdd(&accum[0], n_bad);
+    atomicMin(&accum[1], first);
+}
+
 // End of a check kernel (every thread of every CTA calls it): see CheckEpilogue in kernels.h.
 __device__ __forceinline__ void finish_check(const CheckEpilogue& ep) {
     if (ep.out == nullptr) return;  // an earlier launch of the same check: it only accumulates
+    if (ep.gate != nullptr) return;  // direct hand-over (kernels.h CheckEpilogue): `out` is complete when the grid is
     if (ep.overlap) griddep_wait();  // the previous check has finalised (and reset) the scratch pair
     __shared__ uint32_t s_last;
     __syncthreads();  // every warp of this CTA has reported
@@ -385,9 +426,13 @@ __device__ __forceinline__ fr_t neg_lazy(const fr_t& x) {
 // one thread: bulk copies of a tile blob and of the tile's witness window (into the first term slots)
 __device__ __forceinline__ void issue_tile_load(const DevTileStream& ts, const fr_t* __restrict__ w, uint32_t blob_off16,
                                                 uint32_t blob_bytes, uint32_t win_lo, uint32_t win_n,
-                                                uint8_t* blob_dst, uint8_t* win_dst, uint64_t* bar) {
+                                                uint8_t* blob_dst, uint8_t* win_dst, uint64_t* bar,
+                                                bool first_of_run = false) {
     mbar_arrive_expect_tx(bar, blob_bytes + win_n * 32u);
-    tma_load_1d_stream(blob_dst, ts.blobs + (size_t)blob_off16 * 16u, blob_bytes, bar);
+    if (first_of_run)
+        tma_load_1d_evict_last(blob_dst, ts.blobs + (size_t)blob_off16 * 16u, blob_bytes, bar);
+    else
+        tma_load_1d_stream(blob_dst, ts.blobs + (size_t)blob_off16 * 16u, blob_bytes, bar);
     if (win_n) tma_load_1d_keep(win_dst, w + win_lo, win_n * 32u, bar);
 }
 // one thread: pull what most likely comes after the tile being loaded towards L2 -- the stream is linear per
@@ -499,6 +544,19 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
+#ifndef ACG_FIRST_TILE_KEEP
+#define ACG_FIRST_TILE_KEEP 1
+#endif
+constexpr bool kFirstTileKeep = ACG_FIRST_TILE_KEEP != 0;
+#ifndef ACG_RUN_FAR
+#define ACG_RUN_FAR 1
+#endif
+constexpr bool kRunFar = ACG_RUN_FAR != 0;
+#ifndef ACG_DIRECT_GATE
+#define ACG_DIRECT_GATE 1
+#endif
+constexpr bool kDirectGate = ACG_DIRECT_GATE != 0;
+
 // One CTA walks a contiguous run of tiles.  While tile i computes:
 //   * its far witness elements are already in the far buffer (i & 1): they were gathered with 16-byte cp.async
 //     copies issued during tile i - 1, from the far witness columns that blob i - 1 carried;
@@ -520,6 +578,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     if (!ep.overlap) griddep_wait();   // (an overlapped launch reads only what the previous check also only read)
     griddep_launch_dependents();       // the next check may move in as CTAs of this one exit
     const uint32_t tid = threadIdx.x;
+    if (kDirectGate && ep.gate != nullptr && blockIdx.x == 0u && tid == C::kThreads - 1u) open_gate(ep);  // (not the thread that loads)
     const uint32_t lane = tid & 31u;
     const bool rec = TIMING && (tid == 0u || tid == C::kThreads - 32u);
     const uint32_t rw = tid == 0u ? 0u : 1u;
@@ -537,8 +596,14 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     // this CTA's run of tiles
     uint32_t t_begin, t_end;
     TileMeta tm;
-    const bool planned = ts.runs != nullptr && gridDim.x == ts.n_runs;  // weighted runs (kernels.h CtaRun)
+    const bool planned = ts.runs != nullptr && ts.run_far != nullptr && gridDim.x == ts.n_runs;  // weighted runs (CtaRun)
+    uint32_t first_far_col[kFarPerThread];  // this thread's far columns of the run's first tile (DevTileStream::run_far)
     if (planned) {
+#pragma unroll
+        for (uint32_t k = 0; k < kFarPerThread; ++k) {
+            const uint32_t f = tid + k * C::kThreads;
+            if (kRunFar) first_far_col[k] = f < C::kFarN ? __ldg(ts.run_far + (size_t)blockIdx.x * C::kFarN + f) : 0u;
+        }
         const CtaRun run = ts.runs[blockIdx.x];
         t_begin = run.t_begin;
         t_end = run.t_end;
@@ -579,11 +644,25 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
             mbar_fence_init();
             store_term(smem4, C::term_chunk(C::kZero), fr_zero<P>());
             issue_tile_load(ts, w, tm.blob_off16, tm.blob_bytes, tm.win_lo, tm.win_n, smem, smem + C::kOffTerms,
-                            &full_bar);
+                            &full_bar, kFirstTileKeep);
             prefetch_behind(ts, w, tm.blob_off16, tm.blob_bytes, tm.win_lo, tm.win_n);
         }
         next_off16 = tm.blob_off16 + tm.blob_bytes / 16u;
-        gather_far_async(t_begin, tm.n_far, ts.far_cols + tm.far_off);
+        if (planned && kRunFar) {
+            const uint32_t far0 = C::kFar0 + (C::kFarDouble ? (t_begin & 1u) * C::kFarN : 0u);
+#pragma unroll
+            for (uint32_t k = 0; k < kFarPerThread; ++k) {
+                const uint32_t f = tid + k * C::kThreads;
+                if (f < tm.n_far) {
+                    const uint4* src = reinterpret_cast<const uint4*>(w + first_far_col[k]);
+                    const uint32_t c = C::term_chunk(far0 + f);
+                    cp_async16(smem4 + c, src);
+                    cp_async16(smem4 + (c ^ 1u), src + 1);
+                }
+            }
+        } else {
+            gather_far_async(t_begin, tm.n_far, ts.far_cols + tm.far_off);
+        }
     }
     const bool w0_is_one = fr_is_one<P>(w0_first);
     __syncthreads();  // mbarrier initialised before anyone waits on it
@@ -654,11 +733,9 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         const uint32_t bal = __ballot_sync(0xffffffffu, bad);
         if (bal != 0u) {  // rare: violated rows -- count them and find the smallest ORIGINAL row among them
             const uint32_t first = __reduce_min_sync(0xffffffffu, bad ? (uint32_t)blob[kTilePermOffset + tid] : 0xFFFFFFFFu);
-            if (lane == 0u) {
-                if (ep.overlap) griddep_wait();  // the scratch pair belongs to the previous check until it completes
-                atomicAdd(&ep.accum[0], (unsigned long long)__popc(bal));
-                atomicMin(&ep.accum[1], (unsigned long long)(row_base + h.row0 + first));
-            }
+            if (lane == 0u)
+                report_violations(kDirectGate ? ep.gate : nullptr, ep.gate_seq, ep.out, ep.accum, ep.overlap,
+                                  (unsigned long long)__popc(bal), (unsigned long long)(row_base + h.row0 + first));
         }
         mark(4);
         if (tile + 1u == t_end) break;

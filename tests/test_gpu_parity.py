@@ -927,3 +927,42 @@ def test_overlapping_consecutive_checks(acg, ctx_bn):
         dwb.free()
     ctx_bn.set_overlap_checks(False)   # the default: a plain launch per check
     _reset(acg, ctx_bn)
+
+
+def test_direct_and_ticket_handover_agree(acg, _ctx_bn):
+    """kernels.h CheckEpilogue: a plain check hands its result over directly (block 0 opens a gate, violating warps
+    update the result themselves, nothing happens at the end of a clean check); overlapped checks go through the
+    scratch pair and the last CTA's ticket.  Clean, a few violated rows, violations in every tile: both are what the
+    oracle says, repeatedly (the gate ring and the scratch pair are reused from check to check)."""
+    ctx = _ctx_bn
+    _default_geometry(acg, ctx)
+    n = 1 << 18          # 2048 tiles: more than the 740 CTAs of the grid, so the runs are planned
+    g, w = acg.synth_r1cs(0, n, 4242)
+    m = ctx.upload_r1cs(g)
+    few = w.copy()
+    few[1025 + n // 5, 0] ^= np.uint64(2)
+    few[1025 + n // 2 + 77, 2] ^= np.uint64(1 << 9)
+    many = w.copy()
+    many[1025:1025 + n // 2:37, 1] ^= np.uint64(1)
+    cases = [w, few, many]
+    wants = []
+    for wi in cases:
+        ref = oracle_check(0, g, wi)
+        wants.append((ref["n_violations"], ref["first_bad_row"]))
+    assert wants[0] == (0, -1) and 0 < wants[1][0] < 16 and wants[2][0] > 2048
+    vecs = [ctx.upload_witness(wi) for wi in cases]
+    for _ in range(3):
+        assert [ctx.r1cs_check(m, v) for v in vecs] == wants
+    ctx.set_overlap_checks(True)      # chained checks take the ticket path
+    try:
+        for v, want in zip(vecs, wants):
+            assert [ctx.r1cs_check(m, v) for _ in range(3)] == [want] * 3
+    finally:
+        ctx.set_overlap_checks(False)
+    assert [ctx.r1cs_check(m, v) for v in reversed(vecs)] == list(reversed(wants))
+    # more checks than the gate ring has words
+    for i in range(600):
+        assert ctx.r1cs_check(m, vecs[i % 3]) == wants[i % 3]
+    for x in vecs:
+        x.free()
+    m.free()
