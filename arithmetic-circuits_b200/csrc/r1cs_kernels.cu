@@ -330,8 +330,11 @@ __device__ __forceinline__ fr_t row_dot_warp(const DevCsr& M, uint32_t row, cons
     for (int o = 16; o > 0; o >>= 1) acc = fr_add<P>(acc, shfl_xor_fr(acc, o));
     return acc;  // on every lane
 }
+#ifndef ACG_LONGROWS_MIN_CTAS
+#define ACG_LONGROWS_MIN_CTAS 3
+#endif
 template <class P, bool EMIT>
-__global__ void __launch_bounds__(128, 4) k_r1cs_longrows(DevR1cs m, const fr_t* __restrict__ w,
+__global__ void __launch_bounds__(128, ACG_LONGROWS_MIN_CTAS) k_r1cs_longrows(DevR1cs m, const fr_t* __restrict__ w,
                                                        const uint32_t* __restrict__ rows, uint32_t n_rows,
                                                        uint64_t row_base, CheckEpilogue ep, fr_t* __restrict__ Aw,
                                                        fr_t* __restrict__ Bw, fr_t* __restrict__ Cw) {
@@ -677,6 +680,8 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         mark(0);
         __syncthreads();      // .. and everybody else's
         mark(1);
+        // (a copy in registers on purpose: reading the fields from shared memory where they are used -- fewer live
+        // registers in P3 -- measured 2 us SLOWER at 2^20 rows)
         const TileHeader h = *reinterpret_cast<const TileHeader*>(blob);
         const uint32_t* words = reinterpret_cast<const uint32_t*>(blob + h.off_words);
         const uint16_t* gop = reinterpret_cast<const uint16_t*>(blob + h.off_gop);
@@ -686,13 +691,15 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
 
         // ---- P2: dense 256-bit Montgomery products, one general entry per lane (no divergence between
         //          coefficient kinds): product slot <- coefficient * operand slot
-        for (uint32_t j = tid; j < h.n_general; j += C::kThreads)
-            store_term(smem4, C::kProdInPlace ? C::blob_chunk(h.off_gval, j) : C::term_chunk(C::kProd0 + j),
-                       fr_mul<P>(load_term(smem4, C::blob_chunk(h.off_gval, j)), load_term(smem4, gop[j])));
+        const uint32_t n_general = h.n_general, off_gval = h.off_gval;  // (the stores below could alias the header)
+        for (uint32_t j = tid; j < n_general; j += C::kThreads)
+            store_term(smem4, C::kProdInPlace ? C::blob_chunk(off_gval, j) : C::term_chunk(C::kProd0 + j),
+                       fr_mul<P>(load_term(smem4, C::blob_chunk(off_gval, j)), load_term(smem4, gop[j])));
         if (!w0_is_one) {  // not a witness of the reference: coefficient * w[0] in place, inside the blob
             const fr_t w0 = ld_witness(w);
-            for (uint32_t j = h.n_general + tid; j < h.n_general + h.n_const; j += C::kThreads) {
-                const uint32_t c = C::blob_chunk(h.off_gval, j);
+            const uint32_t n_all = n_general + h.n_const;
+            for (uint32_t j = n_general + tid; j < n_all; j += C::kThreads) {
+                const uint32_t c = C::blob_chunk(off_gval, j);
                 store_term(smem4, c, fr_mul<P>(load_term(smem4, c), w0));
             }
         }
@@ -739,13 +746,15 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         }
         mark(4);
         if (tile + 1u == t_end) break;
+        const uint32_t nx_bytes = h.next_bytes, nx_win_lo = h.next_win_lo, nx_win_n = h.next_win_n;
+        const uint32_t nx_n_far = C::kFarDouble ? 0u : h.next_n_far;
         // one far buffer: this thread's far columns of the next tile leave the blob before it is refilled
         uint32_t next_far_col[kFarPerThread];
         if (!C::kFarDouble) {
 #pragma unroll
             for (uint32_t k = 0; k < kFarPerThread; ++k) {
                 const uint32_t f = tid + k * C::kThreads;
-                next_far_col[k] = f < h.next_n_far ? reinterpret_cast<const uint32_t*>(blob + h.off_next_far)[f] : 0u;
+                next_far_col[k] = f < nx_n_far ? reinterpret_cast<const uint32_t*>(blob + h.off_next_far)[f] : 0u;
             }
         }
         // blob and window were read (and the term array written) through the generic proxy; order that before
@@ -757,7 +766,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
 #pragma unroll
             for (uint32_t k = 0; k < kFarPerThread; ++k) {
                 const uint32_t f = tid + k * C::kThreads;
-                if (f < h.next_n_far) {
+                if (f < nx_n_far) {
                     const uint4* src = reinterpret_cast<const uint4*>(w + next_far_col[k]);
                     const uint32_t c = C::term_chunk(C::kFar0 + f);
                     cp_async16(smem4 + c, src);
@@ -766,11 +775,10 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
             }
         }
         if (tid == 0)
-            issue_tile_load(ts, w, next_off16, h.next_bytes, h.next_win_lo, h.next_win_n, smem, smem + C::kOffTerms,
-                            &full_bar);
+            issue_tile_load(ts, w, next_off16, nx_bytes, nx_win_lo, nx_win_n, smem, smem + C::kOffTerms, &full_bar);
         else if (tid == C::kThreads - 1u)  // another warp: the prefetches do not delay the loads
-            prefetch_behind(ts, w, next_off16, h.next_bytes, h.next_win_lo, h.next_win_n);
-        next_off16 += h.next_bytes / 16u;
+            prefetch_behind(ts, w, next_off16, nx_bytes, nx_win_lo, nx_win_n);
+        next_off16 += nx_bytes / 16u;
         mark(6);
     }
     if (TIMING && rec) {

@@ -862,10 +862,14 @@ class QAP:
     little-endian coefficients; `target` is a stripped integer coefficient list.  kind: "fft" (roots = powers of the
     2^k-th root of unity, src/QAP.hs:512-525) or "lagrange" (arbitrary roots, :486-508)."""
 
-    def __init__(self, field: int, layout, n_rows: int, left, right, out, target: List[int], kind: str, roots=None):
+    def __init__(self, field: int, layout, n_rows: int, left, right, out, target: List[int], kind: str, roots=None,
+                 present=None):
         self.field, self.layout, self.n_rows = field, tuple(layout), n_rows
         self.left, self.right, self.out = left, right, out
         self.target, self.kind, self.roots = target, kind, roots
+        # per set, which wires the reference's Map has a key for: the wires that occur in some gate's row of that set
+        # (createMapGenQap, src/QAP.hs:233-239; addMissingZeroes fills in ROOTS of those wires, not wires).  None: all.
+        self.present = present
         self._dev = None   # (Context, acg_qap handle): the value resident on the device, uploaded on first use
 
     def device_handle(self, ctx: "Context"):
@@ -901,17 +905,29 @@ class QAP:
         return strip(from_limbs(getattr(self, which)[col]))
 
     def sets(self):
-        """-> three (constant, {i: poly}, {i: poly}, {i: poly}) tuples in the reference's QapSet shape (all wires of
-        the layout present, as after addMissingZeroes, src/QAP.hs:566-576) -- what json_io.qap_to_json takes."""
+        """-> three (constant, {i: poly}, {i: poly}, {i: poly}) tuples in the reference's QapSet shape -- what
+        json_io.qap_to_json takes.  A set holds the wires that occur in it (`present`): the reference's Maps are sparse
+        in wires (src/QAP.hs:563-566), a wire without a key counts as the zero polynomial."""
         n_in, n_mid, n_out = self.layout
         res = []
-        for which in ("left", "right", "out"):
+        for k, which in enumerate(("left", "right", "out")):
             arr = getattr(self, which)
             polys = [strip(from_limbs(arr[c])) for c in range(self.n_cols)]
-            res.append((polys[0], {i: polys[1 + i] for i in range(n_in)},
-                        {i: polys[1 + n_in + i] for i in range(n_mid)},
-                        {i: polys[1 + n_in + n_mid + i] for i in range(n_out)}))
+            has = (lambda c: True) if self.present is None else (lambda c, k=k: bool(self.present[k][c]))
+            res.append((polys[0], {i: polys[1 + i] for i in range(n_in) if has(1 + i)},
+                        {i: polys[1 + n_in + i] for i in range(n_mid) if has(1 + n_in + i)},
+                        {i: polys[1 + n_in + n_mid + i] for i in range(n_out) if has(1 + n_in + n_mid + i)}))
         return res
+
+
+def _present_wires(g: GenQAP):
+    """Per set, the columns with an entry in some row (QAP.present)."""
+    res = []
+    for _, col, _ in g.mats:
+        mask = np.zeros(g.n_cols, bool)
+        mask[np.asarray(col, dtype=np.int64)] = True
+        res.append(mask)
+    return tuple(res)
 
 
 def _dense_columns(g: GenQAP, N: int) -> List[np.ndarray]:
@@ -938,7 +954,7 @@ def create_polynomials_fft_qap(ctx: Context, g: GenQAP, target_full_domain: bool
     # FFT.fftTargetPoly (src/QAP.hs:524): prod_{i < n} (X - omega^i), or X^N - 1 with the convention switch of
     # DESIGN.md section 3 (identical when n is a power of two)
     target = ctx.fft_target(N if target_full_domain else g.n_rows)
-    return QAP(g.field, g.layout, g.n_rows, polys[0], polys[1], polys[2], target, "fft")
+    return QAP(g.field, g.layout, g.n_rows, polys[0], polys[1], polys[2], target, "fft", present=_present_wires(g))
 
 
 def arith_circuit_to_qap_fft(ctx: Context, circuit: ArithCircuit, roots: Optional[Sequence[Sequence[int]]] = None,
@@ -961,7 +977,7 @@ def create_polynomials_qap(ctx: Context, g: GenQAP) -> QAP:
         for k, p in enumerate(polys):
             arr[k, :len(p)] = to_limbs(p) if len(p) else np.zeros((0, 4), np.uint64)
         outs.append(arr)
-    return QAP(g.field, g.layout, n, outs[0], outs[1], outs[2], strip(target), "lagrange", xs)
+    return QAP(g.field, g.layout, n, outs[0], outs[1], outs[2], strip(target), "lagrange", xs, present=_present_wires(g))
 
 
 def arith_circuit_to_qap(ctx: Context, circuit: ArithCircuit, roots: Optional[Sequence[Sequence[int]]] = None,

@@ -566,12 +566,21 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    l_w0 = ctx.kernel_launch_count()
-    t0 = time.perf_counter()
-    e2e_run(e2e_steps)
-    torch.cuda.synchronize()
-    e2e_w_s = time.perf_counter() - t0
-    l_w = ctx.kernel_launch_count() - l_w0
+    # The region is run e2e_trials times and the MEDIAN trial is reported (all trials are listed): the host-to-device
+    # copies share the box's PCIe switches and host memory with whatever else runs on it, and single trials were seen
+    # 40 % apart on the same box within a minute.
+    e2e_trials = 5
+    trial_s = []
+    for _ in range(e2e_trials):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l_w0 = ctx.kernel_launch_count()
+        t0 = time.perf_counter()
+        e2e_run(e2e_steps)
+        torch.cuda.synchronize()
+        trial_s.append(time.perf_counter() - t0)
+        l_w = ctx.kernel_launch_count() - l_w0
     for d in dws:
         d.status()   # (raises if an asynchronous update had met a non-canonical element)
     # the floor of that step: the host-to-device copies alone (every rank its slice, all ranks at once), no all-gather,
@@ -590,10 +599,11 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         h2d_only_ms = 1e3 * float(tt.item()) / 10
     sampler.stop()
-    t = torch.tensor([e2e_w_s], dtype=torch.float64, device=dev)
+    t = torch.tensor(trial_s, dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_w_s = float(t.item())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)   # every trial: the slowest rank
+    trial_s = sorted(float(x) for x in t.tolist())
+    e2e_w_s = trial_s[len(trial_s) // 2]
     e2e_w_value = total * e2e_steps / e2e_w_s
 
     if rank == 0:
@@ -651,6 +661,7 @@ def run_ours(args, rank, world, local_rank):
                                        "all-gather over NVLink completes it; two device vectors, copy i+1 overlaps all-gather + check i" % world)
                                       if sliced else "whole witness, copy stream; two device vectors, copy i+1 overlaps check i",
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_w_s / e2e_steps,
+                    "trials_ms_per_step": [round(1e3 * x / e2e_steps, 5) for x in trial_s], "reported": "median trial",
                     "h2d_only_ms_per_step": h2d_only_ms,
                     "call": "acg_witness_update_async (new witness from pinned host memory) + acg_r1cs_check against the system "
                             "resident on the device -- the reference, too, keeps its QAP value in memory between calls",

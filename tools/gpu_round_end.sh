@@ -12,6 +12,7 @@ echo "=== bench ours (defaults)"; timeout 900 python bench.py 2>&1 | tail -1 | t
 S="--no-cpu-baseline --no-qap --no-one-shot"
 echo "=== bench ours bls"; timeout 900 python bench.py --field bls12_381 $S 2>&1 | tail -1 | tee gpurun_out/bench_ours_bls.json | cut -c1-200
 echo "=== bench ours equal runs"; ACG_K2_WAVE_SHARES=0 timeout 900 python bench.py $S 2>&1 | tail -1 | tee gpurun_out/bench_ours_equal_runs.json | cut -c1-200
+echo "=== bench ours, ticket hand-over (A/B of the direct hand-over)"; ACG_K2_TICKET=1 timeout 900 python bench.py $S 2>&1 | tail -1 | tee gpurun_out/bench_ours_ticket.json | cut -c1-200
 for v in 2 4 6; do echo "=== bench ours variant $v"; timeout 600 python bench.py --variant $v $S 2>&1 | tail -1 | tee gpurun_out/bench_ours_variant$v.json | cut -c1-120; done
 echo "=== bench ours 2^21"; timeout 900 python bench.py --scaling weak --log-rows 21 $S 2>&1 | tail -1 | tee gpurun_out/bench_ours_21.json | cut -c1-200
 echo "=== bench ours 2^22"; timeout 900 python bench.py --scaling weak --log-rows 22 --steps 50 $S 2>&1 | tail -1 | tee gpurun_out/bench_ours_22.json | cut -c1-200

@@ -10,11 +10,12 @@ for l in sys.stdin:
         print('   isolated %.5f ms frac %.4f' % (r['kernel_ms_mean'], r['frac']))
     elif 'rror' in l or 'ssert' in l: print(l.strip())
 "; }
-echo "=== pytest"; timeout 900 python -m pytest tests -m gpu -q --tb=short -x -k "synth_parity or edge_shapes or handover or overlap or pipelined or full_size" 2>&1 | tail -3
+echo "=== pytest"; timeout 900 python -m pytest tests -m gpu -q --tb=short -x -k "synth_parity or edge_shapes or handover or gate_mix or full_size" 2>&1 | tail -3
 for rep in 1 2; do
-echo "=== HEAD copy (ticket)"; (cd _ab/head && timeout 300 python bench.py $B 2>&1 | show)
-echo "=== working tree, ticket"; ACG_K2_TICKET=1 timeout 300 python bench.py $B 2>&1 | show
-echo "=== working tree, direct"; timeout 300 python bench.py $B "$@" 2>&1 | show
+echo "=== HEAD copy"; (cd _ab/head && timeout 300 python bench.py $B 2>&1 | show)
+echo "=== working tree"; timeout 300 python bench.py $B 2>&1 | show
 done
-echo "=== working tree direct 2^22"; timeout 300 python bench.py $B --log-rows 22 2>&1 | show
-echo "=== working tree direct bls"; timeout 300 python bench.py $B --field bls12_381 2>&1 | show
+for a in "--workload mix" "--dense" "--field bls12_381" "--log-rows 22"; do
+echo "=== HEAD copy $a"; (cd _ab/head && timeout 300 python bench.py $B $a 2>&1 | show)
+echo "=== working tree $a"; timeout 300 python bench.py $B $a 2>&1 | show
+done
