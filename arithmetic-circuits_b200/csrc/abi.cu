@@ -1466,6 +1466,14 @@ int acg_generate_assignment_device(acg_ctx* ctx, const acg_circuit* c, const uin
         return fail(ctx, rc, "acg_generate_assignment_device: gate list is not in single-assignment, define-before-use "
                              "form; use acg_generate_assignment (sequential fold)");
     if (rc) return fail(ctx, rc, "acg_generate_assignment_device: cannot plan the circuit");
+    if (!plan.required_inputs.empty()) {  // an Equal / Split gate on an input the caller did not supply: the reference panics
+        std::vector<uint8_t> supplied((size_t)plan.n_in + 1, 0);
+        for (uint32_t i = 0; i < n_inputs; ++i) supplied[(size_t)input_ix[i] + 1] = 1;
+        for (uint32_t col : plan.required_inputs)
+            if (!supplied[col])
+                return fail(ctx, ACG_ERR_BAD_ARG, "acg_generate_assignment_device: an Equal or Split gate reads an input wire "
+                                                  "that was not supplied (src/QAP.hs:445,474)");
+    }
     static_assert(sizeof(host::GateRec) == sizeof(WitnessGate), "gate record layouts differ");
     const uint64_t n_cols64 = 1ull + plan.n_in + plan.n_mid + plan.n_out;
     if (n_cols64 > kColMask) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_generate_assignment_device: too many wires");

@@ -507,11 +507,13 @@ int build_gate_plan(const acg_circuit* c, uint32_t n_in, uint32_t n_mid, uint32_
                 r.magic = lay.col(g.w1);
                 r.out = lay.col(g.w2);
                 if (r.in > lay.n_in && !written[r.in]) return (int)ACG_ERR_BAD_ARG;  // lookup fails: reference panics
+                if (r.in >= 1 && r.in <= lay.n_in) out.required_inputs.push_back(r.in);
                 lvl = col_level[r.in];
                 if (!produce(r.magic, lvl + 1) || !produce(r.out, lvl + 1)) return (int)ACG_ERR_UNSUPPORTED;
             } else {
                 r.in = lay.col(g.w0);
                 if (r.in > lay.n_in && !written[r.in]) return (int)ACG_ERR_BAD_ARG;
+                if (r.in >= 1 && r.in <= lay.n_in) out.required_inputs.push_back(r.in);
                 lvl = col_level[r.in];
                 r.l0 = (uint32_t)out.split_outs.size();
                 for (uint64_t o : g.outs) {

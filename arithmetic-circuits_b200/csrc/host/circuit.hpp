@@ -48,6 +48,10 @@ struct GatePlan {
     std::vector<uint64_t> term_coef;    // 4 limbs each, Montgomery form
     std::vector<uint32_t> split_outs;   // witness columns of Split outputs
     uint32_t max_width = 0;             // widest level
+    // input wires (columns 1 .. n_in) that an Equal or Split gate takes as its input: the reference looks those up
+    // and panics when the assignment lacks them (src/QAP.hs:445,474) -- unlike the terms of a Mul gate, for which a
+    // missing wire counts as 0 (src/Circuit/Affine.hs:121-125)
+    std::vector<uint32_t> required_inputs;
 };
 // affineCircuitToAffineMap per Mul side + levelisation.  0 / ACG_ERR_*; ACG_ERR_UNSUPPORTED when the gate list is
 // not in single-assignment, define-before-use form (then only the sequential host fold is faithful).

@@ -325,6 +325,17 @@ def test_device_witness_generation_wide_and_special(acg, ctx_bn):
     with pytest.raises(acg.AcgError) as e:
         ctx_bn.generate_assignment(bad, {0: 1, 1: 2})
     assert e.value.code == -6
+    # an Equal / Split gate on an input wire the assignment lacks: the reference's lookup panics (src/QAP.hs:445,474), the
+    # host fold returns BAD_ARG, and so does the device path (a missing wire counts as 0 only inside a Mul gate's terms)
+    eq = acg.ArithCircuit(0, [acg.Equal(acg.InputWire(1), acg.IntermediateWire(0), acg.OutputWire(0))])
+    sp = acg.ArithCircuit(0, [acg.Split(acg.InputWire(2), [acg.IntermediateWire(i) for i in range(8)])])
+    for circ, need in ((eq, 1), (sp, 2)):
+        for gen in (lambda cc, ii: acg.generate_assignment(cc, ii), lambda cc, ii: ctx_bn.generate_assignment(cc, ii)):
+            with pytest.raises(acg.AcgError) as e:
+                gen(circ, {0: 5})
+            assert e.value.code == -1
+        dwx, _ = ctx_bn.generate_assignment(circ, {0: 5, need: 3})
+        assert (dwx.download() == acg.generate_assignment(circ, {0: 5, need: 3}).to_vector()).all()
 
 
 @pytest.mark.parametrize("fid,n,seed,dense", [(0, 96, 20260002, False), (0, 64, 7, True), (1, 96, 20260005, False),

@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 CS=/usr/local/cuda/bin/compute-sanitizer
 for tool in memcheck racecheck synccheck; do
-  for part in k2 mix qap; do
+  for part in ${PARTS:-k2 mix qap}; do
     [ "$tool" != "memcheck" ] && [ "$part" = "qap" ] && continue   # racecheck / synccheck: the shared-memory kernels (K2, long rows) + mix
     echo "=== $tool $part"
     timeout 1500 $CS --tool $tool --error-exitcode 9 python tools/sanitize_cases.py $part > gpurun_out/sanitizer_${tool}_${part}.log 2>&1

@@ -30,6 +30,16 @@ def k2(n, variant):
     dwb = ctx.upload_witness(wb)
     bad = ctx.r1cs_check(m, dwb)
     assert bad[0] > 0
+    # violated rows in (nearly) every tile: every CTA reports through the gate of the direct hand-over at once
+    wm = w.copy()
+    wm[1025:1025 + n // 2:19, 1] ^= np.uint64(1)
+    dwm = ctx.upload_witness(wm)
+    many = ctx.r1cs_check(m, dwm)
+    ctx.set_check_kernel(acg.CHECK_ROWWISE)
+    assert many[0] > n // 128 and ctx.r1cs_check(m, dwm) == many
+    ctx.set_check_kernel(acg.CHECK_TILED)
+    assert ctx.r1cs_check(m, dwm) == many and ctx.r1cs_check(m, dw) == (0, -1)
+    dwm.free()
     # 12 back-to-back launches, overlapping (PDL chain), alternating the two witnesses
     ctx.set_overlap_checks(True)
     res = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(12)]
@@ -44,7 +54,7 @@ def k2(n, variant):
 
 
 if which in ("all", "k2"):
-    for n, v in ((1 << 12, 0), (1 << 16, 0), (1 << 14, 2), (1 << 13, 7)):
+    for n, v in ((1 << 12, 0), (1 << 16, 0), (1 << 17, 0), (1 << 14, 2), (1 << 13, 7), (1 << 13, 8)):   # 2^17: planned runs
         k2(n, v)
     print("k2 ok")
 if which in ("all", "mix"):
