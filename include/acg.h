@@ -164,8 +164,10 @@ void* acg_vec_device_ptr(acg_vec* v);
  * GLOBAL row index, or UINT64_MAX when valid.  valid <=> *n_violations == 0  (verifyAssignment). */
 int acg_r1cs_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* n_violations,
                    uint64_t* first_bad_row);
-/* Enqueue only: d_result points to 2 device uint64 {n_violations, first_bad_row}, written by the last CTA of the
- * check (no initialisation needed).  For timing the kernels with CUDA events on `stream`, for back-to-back checks
+/* Enqueue only: d_result points to 2 device uint64 {n_violations, first_bad_row}; no initialisation needed, valid once
+ * the check has completed on `stream` (its first block writes {0, none}, warps that find violated rows update the
+ * pair, nothing runs at the end of a clean check).  Checks of ONE context share its scratch: order them on the device
+ * (one stream, or events between streams).  For timing the kernels with CUDA events on `stream`, for back-to-back checks
  * (see acg_ctx_set_overlap_checks) and for callers that reduce the pair across row shards themselves
  * (acg_r1cs_check_async_allreduce does it inside the kernel). */
 int acg_r1cs_check_async(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* w, uint64_t* d_result,
