@@ -100,6 +100,9 @@ struct acg_r1cs {
     uint32_t* d_run_far = nullptr;     // DevTileStream::run_far
     uint32_t* d_long_rows = nullptr;  // .. flattened: the rows the warp-per-row kernel handles in one launch
     uint32_t n_long_rows = 0;
+    DevLongRows* d_long_desc = nullptr;  // kernels.h DevLongRows on the device: the tiled kernel checks them itself
+    unsigned int* d_long_counter = nullptr;  //   .. claiming them from this counter,
+    mutable uint32_t long_claims = 0;        //   .. which has been advanced this far by the checks enqueued so far
 };
 
 struct acg_vec {
@@ -524,7 +527,11 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* wv, unsigned l
     } else {
         // rows too long for a tile first -- all of them in one warp-per-row launch (accumulate only) --, the tiled
         // kernel last: it finalises the check.  At most two launches, however many Split gates the circuit has.
-        if (m->n_long_rows) {
+        // .. unless the tiled kernel of this geometry checks them itself after its tiles: then one launch
+        static const bool separate_long = getenv("ACG_K2_SEPARATE_LONGROWS") != nullptr;  // (a measurement aid)
+        const bool fused_long = m->n_long_rows && m->n_tiles && m->d_long_desc && !separate_long &&
+                                tiled_checks_long_rows(m->variant);
+        if (m->n_long_rows && !fused_long) {
             const bool last = m->n_tiles == 0;
             CU(ctx, launch_r1cs_longrows(ctx->field, m->dev, w, m->d_long_rows, m->n_long_rows, m->row_begin + m->row_offset,
                                          last ? fin : acc, Aw, Bw, Cw, s));
@@ -557,7 +564,8 @@ int enqueue_check(acg_ctx* ctx, const acg_r1cs* m, const acg_vec* wv, unsigned l
                 fin.gate_seq = ++ctx->gate_seq;
                 fin.gate = ctx->d_gate + fin.gate_seq % kGateRing;
             }
-            CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin + m->row_offset, fin, Aw, Bw, Cw, ctx->sm_count, s));
+            CU(ctx, launch_r1cs_tiled(ctx->field, ts, w, m->row_begin + m->row_offset, fin, Aw, Bw, Cw, ctx->sm_count, s,
+                                      fused_long ? m->d_long_desc : nullptr, m->n_long_rows, &m->long_claims));
             ++*launches;
             finalised = true;
             if (single && !emit && !prof) {
@@ -810,6 +818,8 @@ void acg_r1cs_free(acg_r1cs* m) {
     cudaFree(m->d_meta);
     cudaFree(m->d_far_cols);
     cudaFree(m->d_long_rows);
+    cudaFree(m->d_long_desc);
+    cudaFree(m->d_long_counter);
     cudaFree(m->d_runs);
     cudaFree(m->d_run_far);
     delete m;
@@ -1265,6 +1275,13 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
         }
     }
     m->dev.tagged = 1;
+    if (m->n_long_rows) {  // the description of the long rows the tiled kernel reads (kernels.h DevLongRows)
+        CU(ctx, cudaMalloc(&m->d_long_counter, sizeof(unsigned int)));
+        CU(ctx, cudaMemset(m->d_long_counter, 0, sizeof(unsigned int)));
+        const DevLongRows desc{m->dev, m->d_long_rows, m->n_long_rows, m->d_long_counter};
+        CU(ctx, cudaMalloc(&m->d_long_desc, sizeof desc));
+        CU(ctx, cudaMemcpy(m->d_long_desc, &desc, sizeof desc, cudaMemcpyHostToDevice));
+    }
     CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));

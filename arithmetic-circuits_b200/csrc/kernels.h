@@ -271,9 +271,26 @@ cudaError_t launch_probe_placement(int variant, int sm_count, uint32_t* d_smid, 
                                    uint32_t* grid_out, cudaStream_t s);
 // resident CTAs per SM of the tiled kernel for geometry `variant`
 uint32_t tiled_ctas_per_sm(int variant);
-// TMA-staged tile kernel over the tile stream.
+// Rows too long for a tile (kMaxEllWidth), checked by the CTAs of the tiled kernel AFTER their runs of tiles, a warp
+// per row on the plain CSR arrays: the same launch, all resident warps of the chip at once.  The warps CLAIM rows from
+// a counter as they run out of tiles, so the CTAs that finish their tiles early take more of them.  The counter is
+// never reset: every warp of the grid claims until it draws an index past the end, so one check advances it by exactly
+// n_rows + (warps of the grid), and the launcher passes each check the value its claims start from (checks of one system
+// are ordered on the device, include/acg.h).
+struct DevLongRows {
+    DevR1cs m;
+    const uint32_t* rows;   // shard-local row indices
+    uint32_t n_rows;
+    unsigned int* counter;  // device word, see above
+};
+bool tiled_checks_long_rows(int variant);  // whether geometry `variant` has that form of the kernel
+// TMA-staged tile kernel over the tile stream.  long_rows: null, or the device copy of the DevLongRows whose rows are to
+// be checked in the same launch, with n_long_rows = its n_rows and *long_claims = the host's running count of claims
+// (advanced by the call).
 cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w, uint64_t row_base,
-                              const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count, cudaStream_t s);
+                              const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count, cudaStream_t s,
+                              const DevLongRows* long_rows = nullptr, uint32_t n_long_rows = 0,
+                              uint32_t* long_claims = nullptr);
 // general values inside the blobs: canonical -> Montgomery in place; offs[i] = byte offset / 16 of value i
 cudaError_t launch_to_mont_scattered(int field, uint8_t* blobs, const uint32_t* offs, uint64_t n, int* d_bad_flag,
                                      cudaStream_t s);

@@ -294,9 +294,8 @@ __device__ __forceinline__ fr_t shfl_xor_fr(const fr_t& x, int mask) {
 // witness elements and coefficient values -- 2 * kBatch independent 32-byte loads in flight per lane -- and only then
 // the products: the kernel is bound by the latency of the two dependent loads (column -> witness element), so the
 // loads of a batch must not wait for the arithmetic of the previous entry.
-template <class P>
+template <class P, int kBatch = 2>
 __device__ __forceinline__ fr_t row_dot_warp(const DevCsr& M, uint32_t row, const fr_t* __restrict__ w, bool tagged) {
-    constexpr int kBatch = 2;
     fr_t acc = fr_zero<P>();
     const uint32_t s = M.rowptr[row], e = M.rowptr[row + 1];
     for (uint32_t k0 = s + lane_id(); k0 < e; k0 += 32u * kBatch) {
@@ -566,10 +565,40 @@ constexpr bool kDirectGate = ACG_DIRECT_GATE != 0;
 //   * the gathers of tile i + 1 are in flight into the other far buffer;
 //   * the blob and window of tile i + 1 are in (or on their way to) L2 (cp.async.bulk.prefetch.L2 issued a tile
 //     earlier), so that the bulk copies issued the moment P3 of tile i is done complete after one L2 round trip.
-template <class P, bool EMIT, int V, bool TIMING = false>
+// The long rows of a system, checked by the tiled kernel's CTAs after their tiles (kernels.h DevLongRows): warp per row,
+// rows claimed from the system's counter.  (Only in the LONG instantiations of the kernel: the one every Split-free
+// system runs is untouched.  __noinline__ here crashes nvcc 12.9.)
+template <class P, bool EMIT>
+__device__ __forceinline__ void check_long_rows(const DevLongRows* lrp, uint32_t claim_base, const fr_t* w,
+                                                uint64_t row_base, unsigned long long* gate, unsigned long long gate_seq,
+                                                unsigned long long* out, unsigned long long* accum, uint32_t overlap,
+                                                fr_t* __restrict__ Aw, fr_t* __restrict__ Bw, fr_t* __restrict__ Cw) {
+    const DevLongRows& lr = *lrp;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane_id() == 0u) i = atomicAdd(lr.counter, 1u) - claim_base;  // (wraps consistently with the host's count)
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= lr.n_rows) break;
+        const uint32_t row = lr.rows[i];
+        const fr_t a = row_dot_warp<P, 1>(lr.m.m[0], row, w, lr.m.tagged != 0);
+        const fr_t b = row_dot_warp<P, 1>(lr.m.m[1], row, w, lr.m.tagged != 0);
+        const fr_t c = row_dot_warp<P, 1>(lr.m.m[2], row, w, lr.m.tagged != 0);
+        if (lane_id() == 0u) {
+            if (EMIT) {
+                if (Aw) Aw[row] = a;
+                if (Bw) Bw[row] = b;
+                if (Cw) Cw[row] = c;
+            }
+            if (!fr_eq(fr_mul<P>(a, b), c)) report_violations(gate, gate_seq, out, accum, overlap, 1ull, row_base + row);
+        }
+    }
+}
+
+template <class P, bool EMIT, int V, bool TIMING = false, bool LONG = false>
 __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerSm)
     k_r1cs_tiled(DevTileStream ts, const fr_t* __restrict__ w, uint64_t row_base, CheckEpilogue ep,
-                 fr_t* __restrict__ Aw, fr_t* __restrict__ Bw, fr_t* __restrict__ Cw) {
+                 fr_t* __restrict__ Aw, fr_t* __restrict__ Bw, fr_t* __restrict__ Cw,
+                 const DevLongRows* __restrict__ long_rows, uint32_t long_claim_base) {
     using namespace tiled;
     using C = Cfg<V>;
     static_assert(kTileGeom[V].max_far <= kFarPerThread * C::kThreads, "far slots exceed the per-thread gathers");
@@ -616,6 +645,9 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         t_end = (uint32_t)((uint64_t)(blockIdx.x + 1u) * ts.n_tiles / gridDim.x);
     }
     if (t_begin >= t_end) {  // (the launcher never makes the grid larger than the tile count)
+        if (LONG)
+            check_long_rows<P, EMIT>(long_rows, long_claim_base, w, row_base, kDirectGate ? ep.gate : nullptr, ep.gate_seq,
+                                     ep.out, ep.accum, ep.overlap, Aw, Bw, Cw);
         finish_check(ep);
         return;
     }
@@ -792,6 +824,9 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         g_tiled_cta_marks[blockIdx.x][4] = smid;
         g_tiled_cta_marks[blockIdx.x][5] = t_end - t_begin;
     }
+    if (LONG)
+        check_long_rows<P, EMIT>(long_rows, long_claim_base, w, row_base, kDirectGate ? ep.gate : nullptr, ep.gate_seq,
+                                 ep.out, ep.accum, ep.overlap, Aw, Bw, Cw);
     finish_check(ep);
     if (TIMING && tid == 0u && blockIdx.x < kMaxTimedCtas) g_tiled_cta_marks[blockIdx.x][3] = globaltimer_ns();
 }
@@ -948,10 +983,17 @@ uint32_t tiled_ctas_per_sm(int variant) {
     return variant >= 0 && variant < kNumTileVariants ? tile_ctas_per_sm(kTileGeom[variant]) : 0u;
 }
 
-template <class P, bool EMIT, int V>
+// geometries whose kernel also exists in the form that checks the long rows in the same launch (the default and the
+// dense one; the others take the separate warp-per-row launch first)
+bool tiled_checks_long_rows(int variant) {
+    return variant == 0 || variant == kDenseTileVariant;
+}
+
+template <class P, bool EMIT, int V, bool LONG = false>
 static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uint64_t row_base,
                                      const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count,
-                                     cudaStream_t s) {
+                                     cudaStream_t s, const DevLongRows* long_rows = nullptr, uint32_t n_long_rows = 0,
+                                     uint32_t* long_claims = nullptr) {
     using C = tiled::Cfg<V>;
     // ACG_K2_CTAS_PER_SM=k (a measurement aid): pad the dynamic shared memory so that only k CTAs fit on an SM
     static const int limit_ctas = getenv("ACG_K2_CTAS_PER_SM") ? atoi(getenv("ACG_K2_CTAS_PER_SM")) : 0;
@@ -961,15 +1003,15 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
         smem_bytes = (227u * 1024u) / ctas - 1024u - 256u;
     }
     {
-        cudaError_t e = cudaFuncSetAttribute(k_r1cs_tiled<P, EMIT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(k_r1cs_tiled<P, EMIT, V, false, LONG>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
     }
     unsigned grid = (unsigned)sm_count * ctas;
     if (grid > ts.n_tiles) grid = ts.n_tiles;
     const DevTileStream& tsw = ts;
 #ifdef ACG_TILED_TIMING_BUILD  // measurement build only (ACG_NVCC_EXTRA=-DACG_TILED_TIMING_BUILD python build.py --force)
-    if (V == 0 && !EMIT) {  // ACG_TILED_TIMING=1: run the instrumented instantiation and print its counters
+    if (V == 0 && !EMIT && !LONG) {  // ACG_TILED_TIMING=1: run the instrumented instantiation and print its counters
         static const bool timing = getenv("ACG_TILED_TIMING") != nullptr;
         if (timing) {
             cudaFuncSetAttribute(k_r1cs_tiled<P, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -977,7 +1019,7 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
             unsigned long long z[2][8] = {};
             cudaMemcpyToSymbolAsync(g_tiled_phase_cycles, z, sizeof z, 0, cudaMemcpyHostToDevice, s);
             k_r1cs_tiled<P, false, 0, true><<<grid, kTileGeom[0].threads, C::kBytes, s>>>(tsw, w, row_base, ep, Aw, Bw,
-                                                                                          Cw);
+                                                                                          Cw, nullptr, 0u);
             cudaMemcpyFromSymbolAsync(z, g_tiled_phase_cycles, sizeof z, 0, cudaMemcpyDeviceToHost, s);
             static unsigned long long marks[kMaxTimedCtas][6];
             cudaMemcpyFromSymbolAsync(marks, g_tiled_cta_marks, sizeof marks, 0, cudaMemcpyDeviceToHost, s);
@@ -1031,13 +1073,34 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = ep.overlap ? 1u : 0u;
-    return cudaLaunchKernelEx(&cfg, k_r1cs_tiled<P, EMIT, V>, tsw, w, row_base, ep, Aw, Bw, Cw);
+    uint32_t claim_base = 0;
+    if (LONG && long_claims) {  // this check's claims: one per long row and one (past the end) per warp of the grid
+        claim_base = *long_claims;
+        *long_claims += n_long_rows + grid * (kTileGeom[V].threads / 32u);
+    }
+    return cudaLaunchKernelEx(&cfg, k_r1cs_tiled<P, EMIT, V, false, LONG>, tsw, w, row_base, ep, Aw, Bw, Cw, long_rows,
+                              claim_base);
 }
 
 cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w, uint64_t row_base,
-                              const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count, cudaStream_t s) {
+                              const CheckEpilogue& ep, fr_t* Aw, fr_t* Bw, fr_t* Cw, int sm_count, cudaStream_t s,
+                              const DevLongRows* long_rows, uint32_t n_long_rows, uint32_t* long_claims) {
     if (ts.n_tiles == 0) return cudaSuccess;
     const bool emit = Aw || Bw || Cw;
+    if (long_rows != nullptr) {  // the tiles and, in the same launch, the long rows
+        if (!tiled_checks_long_rows((int)ts.variant) || long_claims == nullptr) return cudaErrorInvalidValue;
+#define ACG_TILED_LONG(EMITV, VAR)                                                                                   \
+    ACG_DISPATCH_FIELD(field, return (launch_tiled_impl<P, EMITV, VAR, true>(ts, w, row_base, ep, Aw, Bw, Cw, sm_count, s, \
+                                                                             long_rows, n_long_rows, long_claims)))
+        if (ts.variant == 0u) {
+            if (emit) ACG_TILED_LONG(true, 0);
+            ACG_TILED_LONG(false, 0);
+        } else {
+            if (emit) ACG_TILED_LONG(true, kDenseTileVariant);
+            ACG_TILED_LONG(false, kDenseTileVariant);
+        }
+#undef ACG_TILED_LONG
+    }
 #define ACG_TILED(EMITV, VAR)                                                                                     \
     ACG_DISPATCH_FIELD(field, return (launch_tiled_impl<P, EMITV, VAR>(ts, w, row_base, ep, Aw, Bw, Cw, sm_count, s)))
 #define ACG_TILED_V(VAR)                \

@@ -636,11 +636,12 @@ def test_lagrange_matches_reference_qap_build(acg, ctx_bn):
         assert O.p_eval(F, polys[0], xs[i]) == ys[i]
 
 
-def test_reference_gate_mix_split_rows_one_launch(acg, ctx_bn):
+def test_reference_gate_mix_split_rows_one_launch(acg, ctx_bn, tile_variant):
     """A circuit with the gate mix of the reference's own generator (Mul : Equal : Split = 50 : 10 : 1, 256-bit Split,
     test/Test/Circuit/Arithmetic.hs:77-126): every Split contributes one 256-entry row of general coefficients 2^i.
-    However many there are, a check is at most two launches (all long rows in one warp-per-row launch, then the tiles);
-    counts, first bad row and the emitted A.w, B.w, C.w equal the C oracle's."""
+    However many there are, a check of the default geometry is ONE launch (the tiled kernel's warps claim the long rows
+    after their tiles; other geometries: one warp-per-row launch first, then the tiles); counts, first bad row and the
+    emitted A.w, B.w, C.w equal the C oracle's -- repeatedly (the claim counter is never reset) and for both forms."""
     n = 1 << 15
     g, w = acg.synth_mixed_r1cs(0, n, 99)
     lens = np.diff(g.mats[0][0].astype(np.int64))
@@ -649,10 +650,19 @@ def test_reference_gate_mix_split_rows_one_launch(acg, ctx_bn):
     assert ref["n_violations"] == 0
     m, dw = ctx_bn.upload_r1cs(g), ctx_bn.upload_witness(w)
     _select(acg, ctx_bn, "tiled", 0)
-    assert ctx_bn.r1cs_check(m, dw) == (0, -1)
-    assert ctx_bn.last_timing()["kernel_launches"] <= 2
+    for _ in range(3):
+        assert ctx_bn.r1cs_check(m, dw) == (0, -1)
+        assert ctx_bn.last_timing()["kernel_launches"] == (1 if tile_variant in (0, 8) else 2)
     aw, bw, cw = ctx_bn.r1cs_eval(m, dw)
     assert (aw == ref["Aw"]).all() and (bw == ref["Bw"]).all() and (cw == ref["Cw"]).all()
+    other = 2 if tile_variant in (0, 8) else 0   # the other form of the check (geometry is bound at upload)
+    ctx_bn.set_tiled_variant(other)
+    m2 = ctx_bn.upload_r1cs(g)
+    assert ctx_bn.r1cs_check(m2, dw) == (0, -1)
+    assert ctx_bn.last_timing()["kernel_launches"] == (2 if other == 2 else 1)
+    aw2, bw2, cw2 = ctx_bn.r1cs_eval(m2, dw)
+    assert (aw2 == ref["Aw"]).all() and (bw2 == ref["Bw"]).all() and (cw2 == ref["Cw"]).all()
+    ctx_bn.set_tiled_variant(tile_variant)
     # flip one output bit of every tenth Split and one Equal/Mul wire
     wb = w.copy()
     long_rows = np.nonzero(lens > 8)[0]
@@ -664,8 +674,12 @@ def test_reference_gate_mix_split_rows_one_launch(acg, ctx_bn):
     assert refb["n_violations"] > len(long_rows[::10])
     dw.update(wb)
     assert _both_kernels(acg, ctx_bn, lambda: ctx_bn.r1cs_check(m, dw)) == (refb["n_violations"], refb["first_bad_row"])
+    assert ctx_bn.r1cs_check(m2, dw) == (refb["n_violations"], refb["first_bad_row"])
+    for _ in range(3):
+        assert ctx_bn.r1cs_check(m, dw) == (refb["n_violations"], refb["first_bad_row"])
     dw.free()
     m.free()
+    m2.free()
 
 
 @pytest.mark.parametrize("modulus_id", [2, 0, 1])

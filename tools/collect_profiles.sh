@@ -3,7 +3,7 @@
 set -u
 R=${1:-r02}
 G=gpurun_out; P=profiles
-for f in bench_ours bench_ours_driver_cmd bench_reference bench_ours_bls bench_ours_equal_runs bench_ours_ticket bench_ours_variant2 bench_ours_variant4 bench_ours_variant6 bench_ours_21 bench_ours_22 bench_ours_dense bench_ours_rowwise bench_ours_mix bench_qap_20; do
+for f in bench_ours bench_ours_driver_cmd bench_reference bench_ours_bls bench_ours_equal_runs bench_ours_ticket bench_ours_variant2 bench_ours_variant4 bench_ours_variant6 bench_ours_21 bench_ours_22 bench_ours_dense bench_ours_rowwise bench_ours_mix bench_ours_mix_separate bench_qap_20; do
   [ -s $G/$f.json ] && cp $G/$f.json $P/${R}_$f.json
 done
 [ -s $G/fr_mul_throughput.txt ] && cp $G/fr_mul_throughput.txt $P/${R}_fr_mul_throughput.txt

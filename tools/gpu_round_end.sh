@@ -19,6 +19,7 @@ echo "=== bench ours 2^22"; timeout 900 python bench.py --scaling weak --log-row
 echo "=== bench ours dense"; timeout 900 python bench.py --dense $S 2>&1 | tail -1 | tee gpurun_out/bench_ours_dense.json | cut -c1-200
 echo "=== bench ours rowwise"; timeout 900 python bench.py --kernel rowwise $S 2>&1 | tail -1 | tee gpurun_out/bench_ours_rowwise.json | cut -c1-200
 echo "=== bench ours mix"; timeout 900 python bench.py --workload mix --steps 50 --no-qap --no-one-shot 2>&1 | tail -1 | tee gpurun_out/bench_ours_mix.json | cut -c1-200
+echo "=== bench ours mix, separate long-row launch"; ACG_K2_SEPARATE_LONGROWS=1 timeout 900 python bench.py --workload mix --steps 50 $S 2>&1 | tail -1 | tee gpurun_out/bench_ours_mix_separate.json | cut -c1-200
 echo "=== bench qap 2^20"; timeout 900 python bench_qap.py --log-n 20 2>&1 | tail -6 | tee gpurun_out/bench_qap_20.json | cut -c1-300
 echo "=== K1 ceiling"; nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I arithmetic-circuits_b200/csrc -I tools/microbench tools/microbench/fr_mul_throughput.cu -o /tmp/fr_mul_throughput 2>/dev/null; timeout 300 /tmp/fr_mul_throughput > gpurun_out/fr_mul_throughput.txt 2>&1; tail -2 gpurun_out/fr_mul_throughput.txt | cut -c1-160
 N="--steps 5 --warmup 3 --no-cpu-baseline --no-qap --no-one-shot --e2e-steps 2"
