@@ -20,6 +20,8 @@
  *     (mirrors `Nothing`, src/QAP.hs:310-312): it is reported through the out-parameters.
  *   - One in-flight call per context.  Blocking calls return when the result is on the host.
  *     `_async` calls only enqueue on the given CUDA stream (cudaStream_t passed as void*).
+ *     Enqueued checks are NOT replayable from a captured CUDA graph: every check carries per-call sequence numbers
+ *     in its kernel arguments (result hand-over, long-row claims, peer exchange).
  *   - There is NO CPU fallback: without a CUDA device every compute call fails with ACG_ERR_NO_DEVICE.
  */
 #ifndef ACG_H
