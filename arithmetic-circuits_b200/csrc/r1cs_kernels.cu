@@ -1073,13 +1073,13 @@ static cudaError_t launch_tiled_impl(const DevTileStream& ts, const fr_t* w, uin
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = ep.overlap ? 1u : 0u;
-    uint32_t claim_base = 0;
-    if (LONG && long_claims) {  // this check's claims: one per long row and one (past the end) per warp of the grid
-        claim_base = *long_claims;
-        *long_claims += n_long_rows + grid * (kTileGeom[V].threads / 32u);
-    }
-    return cudaLaunchKernelEx(&cfg, k_r1cs_tiled<P, EMIT, V, false, LONG>, tsw, w, row_base, ep, Aw, Bw, Cw, long_rows,
-                              claim_base);
+    const uint32_t claim_base = LONG && long_claims ? *long_claims : 0u;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_r1cs_tiled<P, EMIT, V, false, LONG>, tsw, w, row_base, ep, Aw, Bw, Cw,
+                                             long_rows, claim_base);
+    // this check's claims: one per long row and one (past the end) per warp of the grid -- counted only for a launch
+    // that was accepted, so that host and device counts cannot drift apart
+    if (e == cudaSuccess && LONG && long_claims) *long_claims += n_long_rows + grid * (kTileGeom[V].threads / 32u);
+    return e;
 }
 
 cudaError_t launch_r1cs_tiled(int field, const DevTileStream& ts, const fr_t* w, uint64_t row_base,
