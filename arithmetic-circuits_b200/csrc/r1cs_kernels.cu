@@ -329,11 +329,8 @@ __device__ __forceinline__ fr_t row_dot_warp(const DevCsr& M, uint32_t row, cons
     for (int o = 16; o > 0; o >>= 1) acc = fr_add<P>(acc, shfl_xor_fr(acc, o));
     return acc;  // on every lane
 }
-#ifndef ACG_LONGROWS_MIN_CTAS
-#define ACG_LONGROWS_MIN_CTAS 3
-#endif
 template <class P, bool EMIT>
-__global__ void __launch_bounds__(128, ACG_LONGROWS_MIN_CTAS) k_r1cs_longrows(DevR1cs m, const fr_t* __restrict__ w,
+__global__ void __launch_bounds__(128, 3) k_r1cs_longrows(DevR1cs m, const fr_t* __restrict__ w,
                                                        const uint32_t* __restrict__ rows, uint32_t n_rows,
                                                        uint64_t row_base, CheckEpilogue ep, fr_t* __restrict__ Aw,
                                                        fr_t* __restrict__ Bw, fr_t* __restrict__ Cw) {
@@ -546,18 +543,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-#ifndef ACG_FIRST_TILE_KEEP
-#define ACG_FIRST_TILE_KEEP 1
-#endif
-constexpr bool kFirstTileKeep = ACG_FIRST_TILE_KEEP != 0;
-#ifndef ACG_RUN_FAR
-#define ACG_RUN_FAR 1
-#endif
-constexpr bool kRunFar = ACG_RUN_FAR != 0;
-#ifndef ACG_DIRECT_GATE
-#define ACG_DIRECT_GATE 1
-#endif
-constexpr bool kDirectGate = ACG_DIRECT_GATE != 0;
 
 // One CTA walks a contiguous run of tiles.  While tile i computes:
 //   * its far witness elements are already in the far buffer (i & 1): they were gathered with 16-byte cp.async
@@ -610,7 +595,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     if (!ep.overlap) griddep_wait();   // (an overlapped launch reads only what the previous check also only read)
     griddep_launch_dependents();       // the next check may move in as CTAs of this one exit
     const uint32_t tid = threadIdx.x;
-    if (kDirectGate && ep.gate != nullptr && blockIdx.x == 0u && tid == C::kThreads - 1u) open_gate(ep);  // (not the thread that loads)
+    if (ep.gate != nullptr && blockIdx.x == 0u && tid == C::kThreads - 1u) open_gate(ep);  // (not the thread that loads)
     const uint32_t lane = tid & 31u;
     const bool rec = TIMING && (tid == 0u || tid == C::kThreads - 32u);
     const uint32_t rw = tid == 0u ? 0u : 1u;
@@ -634,7 +619,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
 #pragma unroll
         for (uint32_t k = 0; k < kFarPerThread; ++k) {
             const uint32_t f = tid + k * C::kThreads;
-            if (kRunFar) first_far_col[k] = f < C::kFarN ? __ldg(ts.run_far + (size_t)blockIdx.x * C::kFarN + f) : 0u;
+            first_far_col[k] = f < C::kFarN ? __ldg(ts.run_far + (size_t)blockIdx.x * C::kFarN + f) : 0u;
         }
         const CtaRun run = ts.runs[blockIdx.x];
         t_begin = run.t_begin;
@@ -646,7 +631,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
     }
     if (t_begin >= t_end) {  // (the launcher never makes the grid larger than the tile count)
         if (LONG)
-            check_long_rows<P, EMIT>(long_rows, long_claim_base, w, row_base, kDirectGate ? ep.gate : nullptr, ep.gate_seq,
+            check_long_rows<P, EMIT>(long_rows, long_claim_base, w, row_base, ep.gate, ep.gate_seq,
                                      ep.out, ep.accum, ep.overlap, Aw, Bw, Cw);
         finish_check(ep);
         return;
@@ -679,11 +664,11 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
             mbar_fence_init();
             store_term(smem4, C::term_chunk(C::kZero), fr_zero<P>());
             issue_tile_load(ts, w, tm.blob_off16, tm.blob_bytes, tm.win_lo, tm.win_n, smem, smem + C::kOffTerms,
-                            &full_bar, kFirstTileKeep);
+                            &full_bar, true);
             prefetch_behind(ts, w, tm.blob_off16, tm.blob_bytes, tm.win_lo, tm.win_n);
         }
         next_off16 = tm.blob_off16 + tm.blob_bytes / 16u;
-        if (planned && kRunFar) {
+        if (planned) {
             const uint32_t far0 = C::kFar0 + (C::kFarDouble ? (t_begin & 1u) * C::kFarN : 0u);
 #pragma unroll
             for (uint32_t k = 0; k < kFarPerThread; ++k) {
@@ -773,7 +758,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         if (bal != 0u) {  // rare: violated rows -- count them and find the smallest ORIGINAL row among them
             const uint32_t first = __reduce_min_sync(0xffffffffu, bad ? (uint32_t)blob[kTilePermOffset + tid] : 0xFFFFFFFFu);
             if (lane == 0u)
-                report_violations(kDirectGate ? ep.gate : nullptr, ep.gate_seq, ep.out, ep.accum, ep.overlap,
+                report_violations(ep.gate, ep.gate_seq, ep.out, ep.accum, ep.overlap,
                                   (unsigned long long)__popc(bal), (unsigned long long)(row_base + h.row0 + first));
         }
         mark(4);
@@ -825,7 +810,7 @@ __global__ void __launch_bounds__(kTileGeom[V].threads, tiled::Cfg<V>::kCtasPerS
         g_tiled_cta_marks[blockIdx.x][5] = t_end - t_begin;
     }
     if (LONG)
-        check_long_rows<P, EMIT>(long_rows, long_claim_base, w, row_base, kDirectGate ? ep.gate : nullptr, ep.gate_seq,
+        check_long_rows<P, EMIT>(long_rows, long_claim_base, w, row_base, ep.gate, ep.gate_seq,
                                  ep.out, ep.accum, ep.overlap, Aw, Bw, Cw);
     finish_check(ep);
     if (TIMING && tid == 0u && blockIdx.x < kMaxTimedCtas) g_tiled_cta_marks[blockIdx.x][3] = globaltimer_ns();
