@@ -36,6 +36,8 @@ PROTOTYPES = {
     "acg_ctx_set_tiled_variant": (C.c_int, [vp, C.c_int]),
     "acg_r1cs_stream_bytes": (C.c_uint64, [vp]),
     "acg_r1cs_set_row_offset": (C.c_int, [vp, C.c_uint64]),
+    "acg_tile_stream_digest": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(AcgCsr), C.POINTER(AcgCsr),
+                                        C.POINTER(AcgCsr), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "acg_last_timing": (C.c_int, [vp, C.POINTER(AcgTiming)]),
     "acg_kernel_launch_count": (C.c_uint64, [vp]),
     "acg_profile_begin": (C.c_int, [vp, C.c_uint32]),

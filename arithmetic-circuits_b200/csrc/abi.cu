@@ -3,12 +3,14 @@
 // of r1cs_kernels.cu / ntt_kernels.cu / lagrange_kernels.cu.  There is no CPU fallback: every compute
 // entry point needs a CUDA device and reports ACG_ERR_NO_DEVICE / ACG_ERR_CUDA otherwise.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -492,6 +494,443 @@ void build_tiles(const TileGeometry& geom, const uint32_t* rp[3], const uint32_t
     }
 }
 
+// Host pass over the uploaded slice of a system: structural validation, shard-local row pointers, column words tagged
+// with the coefficient class (+1 / -1 / general), running counts of general entries (all / on column 0) per row.
+struct HostRows {
+    std::vector<uint32_t> local_rp[3], tagged_col[3], gcum[3], ccum[3];
+};
+inline int host_rows_fail(const char** why, int code, const char* msg) {
+    if (why) *why = msg;
+    return code;
+}
+int host_rows(int field, uint32_t n_rows, uint32_t n_cols, const acg_csr* const (&src)[3], uint32_t row_begin,
+              uint32_t row_end, HostRows& out, const char** why) {
+    const uint32_t n_local = row_end - row_begin;
+    // canonical 1 and r-1: the two coefficient values with a multiplication-free fast path
+    uint64_t modulus[4], minus_one[4];
+    acg_field_constants(field, modulus, nullptr, nullptr, nullptr, nullptr);
+    std::memcpy(minus_one, modulus, 32);
+    minus_one[0] -= 1;  // r is odd
+    // host pass over the uploaded slice: structural validation, coefficient tags, per-row general counts
+    std::vector<uint32_t> (&local_rp)[3] = out.local_rp, (&tagged_col)[3] = out.tagged_col, (&gcum)[3] = out.gcum, (&ccum)[3] = out.ccum;
+    for (int k = 0; k < 3; ++k) {
+        const acg_csr* M = src[k];
+        if (!M->rowptr || (M->nnz && (!M->col || !M->val)) || M->nnz > 0xFFFFFFF0ull)
+            return host_rows_fail(why, ACG_ERR_BAD_ARG, "null array or nnz too large");
+        if (M->rowptr[n_rows] != M->nnz) return host_rows_fail(why, ACG_ERR_BAD_ARG, "rowptr[n_rows] != nnz");
+        for (uint32_t r = row_begin; r < row_end; ++r)
+            if (M->rowptr[r] > M->rowptr[r + 1])
+                return host_rows_fail(why, ACG_ERR_BAD_ARG, "rowptr not monotone");
+        const uint32_t e0 = M->rowptr[row_begin], e1 = M->rowptr[row_end];
+        if (e1 > M->nnz) return host_rows_fail(why, ACG_ERR_BAD_ARG, "rowptr exceeds nnz");
+        local_rp[k].resize((size_t)n_local + 1);
+        gcum[k].resize((size_t)n_local + 1);
+        ccum[k].resize((size_t)n_local + 1);
+        tagged_col[k].resize((size_t)(e1 - e0));
+        uint32_t bad = 0, gen = 0, cst = 0;
+        for (uint32_t r = 0; r < n_local; ++r) {
+            local_rp[k][r] = M->rowptr[row_begin + r] - e0;
+            gcum[k][r] = gen;
+            ccum[k][r] = cst;
+            for (uint32_t e = M->rowptr[row_begin + r]; e < M->rowptr[row_begin + r + 1]; ++e) {
+                const uint32_t c = M->col[e];
+                bad |= (c >= n_cols);
+                const uint64_t* v = M->val + 4ull * e;
+                uint32_t tag = kTagGeneral;
+                if (v[0] == 1 && (v[1] | v[2] | v[3]) == 0)
+                    tag = kTagPlusOne;
+                else if (k != 2 && v[0] == minus_one[0] && v[1] == minus_one[1] && v[2] == minus_one[2] &&
+                         v[3] == minus_one[3])
+                    tag = kTagMinusOne;  // (a -1 in C stays general: C.w is compared, so its terms are never negated)
+                gen += (tag == kTagGeneral);
+                cst += (tag == kTagGeneral && c == 0u);
+                tagged_col[k][e - e0] = (c & kColMask) | (tag << 30);
+            }
+        }
+        local_rp[k][n_local] = e1 - e0;
+        gcum[k][n_local] = gen;
+        ccum[k][n_local] = cst;
+        if (bad) return host_rows_fail(why, ACG_ERR_BAD_ARG, "column index >= n_cols");
+    }
+    return ACG_OK;
+}
+
+// The geometry a system is bound to: the requested one, except that the default gives way to the roomier one for
+// systems dense in general coefficients (more than 1.6 products per row).
+int pick_variant(int requested, const HostRows& hr, uint32_t n_local) {
+    if (requested != 0 || n_local == 0) return requested;
+    uint64_t prods = 0;
+    for (int k = 0; k < 3; ++k) prods += (uint64_t)hr.gcum[k][n_local] - hr.ccum[k][n_local];
+    return prods * 10u > (uint64_t)n_local * 16u ? kDenseTileVariant : 0;
+}
+
+// Worker threads of the host-side tile-stream build: ACG_HOST_THREADS, else the hardware concurrency (at most 32).
+unsigned upload_threads() {
+    if (const char* e = getenv("ACG_HOST_THREADS")) {
+        const long v = strtol(e, nullptr, 10);
+        if (v >= 1) return (unsigned)std::min<long>(v, 256);
+    }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(hc ? hc : 1u, 32u));
+}
+// f(t, begin, end) over T contiguous chunks of [0, n) on T threads (T = 1: on the caller's).  Nothing escapes a worker;
+// if the system refuses a thread, the chunks that did not get one run on the caller's thread afterwards.
+template <class F>
+int run_chunks(size_t n, size_t T, F&& f) {
+    if (T <= 1 || n == 0) return f((size_t)0, (size_t)0, n);
+    std::vector<int> rcs(T, ACG_OK);
+    std::vector<uint8_t> started(T, 0);
+    std::vector<std::thread> workers;
+    workers.reserve(T);
+    auto guarded = [&](size_t t) {
+        try {
+            rcs[t] = f(t, n * t / T, n * (t + 1) / T);
+        } catch (const std::bad_alloc&) {
+            rcs[t] = ACG_ERR_OOM;
+        } catch (...) {
+            rcs[t] = ACG_ERR_INTERNAL;
+        }
+    };
+    for (size_t t = 0; t < T; ++t) {
+        try {
+            workers.emplace_back(guarded, t);
+            started[t] = 1;
+        } catch (...) {
+            break;
+        }
+    }
+    for (auto& w : workers) w.join();
+    for (size_t t = 0; t < T; ++t)
+        if (!started[t]) guarded(t);
+    for (int rc : rcs)
+        if (rc != ACG_OK) return rc;
+    return ACG_OK;
+}
+
+// The execution-ready form of a system for the tiled kernel (kernels.h): blobs, tile records, far column lists, where
+// the general coefficient values sit (for the Montgomery conversion on the device), and the rows that fit no tile.
+struct TileStream {
+    std::vector<uint8_t> stream;
+    std::vector<uint32_t> gval_offs;  // 16-byte units; bit 31: the high half sits BEFORE the low one
+    std::vector<TileMeta> metas;
+    std::vector<uint32_t> far_all;
+    std::vector<std::pair<uint32_t, uint32_t>> extra_long;  // tiles dropped for their far columns
+};
+struct FinalTile {
+    HostTile t;
+    uint32_t win_lo, win_n, far_off, n_far;
+};
+// Pure host code, no CUDA calls.  The tiles are independent of each other apart from what blob i says about tile i + 1
+// (window, far columns, size), so both passes run over contiguous chunks of the tile list on worker threads and the
+// pieces are concatenated in order: the result does not depend on the number of threads (acg_tile_stream_digest, tested
+// on CPU).  rp / tagged_col: the shard-local CSR structure with tagged column words; val0[k]: value of local entry 0.
+int build_tile_stream(const TileGeometry& geom, uint32_t n_cols, const std::vector<HostTile>& tiles,
+                      const std::vector<uint32_t> (&rp)[3], const std::vector<uint32_t> (&tagged_col)[3],
+                      const uint64_t* const (&val0)[3], unsigned threads, TileStream& out) {
+    const uint32_t kProd0 = tile_prod_slot0(geom), kZero = tile_term_slots(geom) - 1u;
+    static const bool timing = getenv("ACG_UPLOAD_TIMING") != nullptr;  // (a measurement aid: phase times on stderr)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto t_start = now();
+    // ---- pass 1: window and far columns of every tile; a tile whose distinct far references exceed the far slots is
+    //      split in two (rows stay multiples of 4)
+    const size_t T1 = std::min<size_t>(threads, tiles.size() / 64 + 1);
+    struct Part1 {
+        std::vector<FinalTile> tiles;
+        std::vector<uint32_t> far;
+        std::vector<std::pair<uint32_t, uint32_t>> dropped;
+    };
+    std::vector<Part1> p1(T1);
+    int rc = run_chunks(tiles.size(), T1, [&](size_t t, size_t begin, size_t end) -> int {
+        Part1& part = p1[t];
+        std::vector<uint32_t> ref_cols, far_cols;
+        std::vector<HostTile> work(std::make_reverse_iterator(tiles.begin() + (ptrdiff_t)end),
+                                   std::make_reverse_iterator(tiles.begin() + (ptrdiff_t)begin));  // pop from the back
+        while (!work.empty()) {
+            HostTile tl = work.back();
+            work.pop_back();
+            // witness window: the contiguous slice of geom.window elements that covers most references of the tile
+            ref_cols.clear();
+            for (int k = 0; k < 3; ++k)
+                for (uint32_t e = 0; e < tl.ne[k]; ++e) ref_cols.push_back(tagged_col[k][tl.e0[k] + e] & kColMask);
+            std::sort(ref_cols.begin(), ref_cols.end());
+            const uint32_t win_n = std::min<uint32_t>(geom.window, n_cols);
+            uint32_t win_lo = 0;
+            {
+                size_t best = 0, lo_i = 0;
+                for (size_t hi_i = 0; hi_i < ref_cols.size(); ++hi_i) {
+                    while (ref_cols[hi_i] - ref_cols[lo_i] >= win_n) ++lo_i;
+                    if (hi_i - lo_i + 1 > best) {
+                        best = hi_i - lo_i + 1;
+                        win_lo = ref_cols[lo_i];
+                    }
+                }
+                if (win_lo + win_n > n_cols) win_lo = n_cols - win_n;
+            }
+            far_cols.clear();
+            for (uint32_t c : ref_cols)
+                if ((c < win_lo || c - win_lo >= win_n) && (far_cols.empty() || far_cols.back() != c)) far_cols.push_back(c);
+            if (far_cols.size() > geom.max_far && tl.nrows > 4) {
+                const uint32_t half = ((tl.nrows / 2 + 3) / 4) * 4;
+                HostTile lo_t{}, hi_t{};
+                lo_t.row0 = tl.row0;
+                lo_t.nrows = half;
+                hi_t.row0 = tl.row0 + half;
+                hi_t.nrows = tl.nrows - half;
+                for (HostTile* q : {&lo_t, &hi_t})
+                    for (int k = 0; k < 3; ++k) {
+                        q->e0[k] = rp[k][q->row0];
+                        q->ne[k] = rp[k][q->row0 + q->nrows] - q->e0[k];
+                        q->width[k] = 0;
+                        for (uint32_t r = q->row0; r < q->row0 + q->nrows; ++r)
+                            q->width[k] = std::max(q->width[k], rp[k][r + 1] - rp[k][r]);
+                    }
+                work.push_back(hi_t);
+                work.push_back(lo_t);
+                continue;
+            }
+            if (far_cols.size() > geom.max_far) {  // 4 rows with more distinct far columns than slots: row-wise kernel
+                part.dropped.emplace_back(tl.row0, tl.row0 + tl.nrows);
+                continue;
+            }
+            FinalTile ft{};
+            ft.t = tl;
+            ft.win_lo = win_lo;
+            ft.win_n = win_n;
+            ft.far_off = (uint32_t)part.far.size();  // (relative to the part; rebased below)
+            ft.n_far = (uint32_t)far_cols.size();
+            part.far.insert(part.far.end(), far_cols.begin(), far_cols.end());
+            part.tiles.push_back(ft);
+        }
+        return ACG_OK;
+    });
+    if (rc) return rc;
+    std::vector<FinalTile> final_tiles;
+    {
+        size_t n_final = 0, n_far = 0;
+        for (const Part1& part : p1) {
+            n_final += part.tiles.size();
+            n_far += part.far.size();
+        }
+        if (n_far > 0xFFFFFFF0ull) return ACG_ERR_UNSUPPORTED;
+        final_tiles.reserve(n_final);
+        out.far_all.reserve(n_far);
+        for (Part1& part : p1) {
+            const uint32_t base = (uint32_t)out.far_all.size();
+            for (FinalTile ft : part.tiles) {
+                ft.far_off += base;
+                final_tiles.push_back(ft);
+            }
+            out.far_all.insert(out.far_all.end(), part.far.begin(), part.far.end());
+            out.extra_long.insert(out.extra_long.end(), part.dropped.begin(), part.dropped.end());
+            std::vector<FinalTile>().swap(part.tiles);
+            std::vector<uint32_t>().swap(part.far);
+        }
+    }
+    const std::vector<uint32_t>& far_all = out.far_all;
+    const auto t_pass1 = now();
+    // ---- pass 2: emit the blobs.  Blob i also carries what the kernel needs to start tile i + 1 while blob i is
+    //      still the only one in shared memory: its far witness columns and, in the header, its size and window.
+    const size_t T2 = std::min<size_t>(threads, final_tiles.size() / 64 + 1);
+    struct Part2 {
+        std::vector<uint8_t> stream;
+        std::vector<uint32_t> gval_offs;  // relative to the part's stream
+        std::vector<TileMeta> metas;      // blob_off16 relative to the part's stream
+    };
+    std::vector<Part2> p2(T2);
+    rc = run_chunks(final_tiles.size(), T2, [&](size_t t, size_t begin, size_t end) -> int {
+        Part2& part = p2[t];
+        std::vector<uint8_t>& stream = part.stream;
+        stream.reserve((end - begin) * (size_t)(tile_blob_capacity(geom) / 2u + 256u));
+        auto align16 = [&]() { stream.resize((stream.size() + 15) & ~(size_t)15, 0); };
+        auto put16 = [&](uint16_t v) {
+            stream.push_back((uint8_t)(v & 0xFF));
+            stream.push_back((uint8_t)(v >> 8));
+        };
+        auto put32 = [&](uint32_t v) {
+            for (int i = 0; i < 4; ++i) stream.push_back((uint8_t)(v >> (8 * i)));
+        };
+        std::vector<int32_t> gid[3];
+        std::vector<uint32_t> order;
+        for (size_t ti = begin; ti < end; ++ti) {
+            const FinalTile& ft = final_tiles[ti];
+            const HostTile& tl = ft.t;
+            const uint32_t win_lo = ft.win_lo, win_n = ft.win_n;
+            const uint32_t* far_b = far_all.data() + ft.far_off;
+            const uint32_t* far_e = far_b + ft.n_far;
+            // chunk (16-byte unit from the start of shared memory) of the low half of a term slot / of the 32-byte
+            // value j of a blob section; the window is written by a linear bulk copy and stays in natural order
+            const uint32_t term_base16 = tile_terms_offset(geom) / 16u;
+            auto term_chunk = [&](uint32_t slot, bool in_window) -> uint32_t {
+                const uint32_t c = term_base16 + 2u * slot;
+                return (geom.swizzle && !in_window) ? swz16(c) : c;
+            };
+            auto blob_chunk = [&](uint32_t off, uint32_t j) -> uint32_t {
+                const uint32_t c = off / 16u + 2u * j;
+                return geom.swizzle ? swz16(c) : c;
+            };
+            auto chunk_of = [&](uint32_t c) -> uint32_t {  // witness column -> chunk of its term
+                if (c >= win_lo && c - win_lo < win_n) return term_chunk(c - win_lo, true);
+                return term_chunk(tile_far_slot0(geom, (uint32_t)ti) + (uint32_t)(std::lower_bound(far_b, far_e, c) - far_b),
+                                  false);
+            };
+            align16();
+            const size_t base = stream.size();
+            TileMeta tm{};
+            tm.blob_off16 = (uint32_t)(base / 16);
+            tm.win_lo = win_lo;
+            tm.win_n = win_n;
+            tm.far_off = ft.far_off;
+            tm.n_far = ft.n_far;
+            stream.resize(base + sizeof(TileHeader), 0);
+            TileHeader h{};
+            h.row0 = tl.row0;
+            h.nrows = tl.nrows;
+            for (int k = 0; k < 3; ++k) h.width[k] = tl.width[k];
+            if (ti + 1 < final_tiles.size()) {
+                const FinalTile& nx = final_tiles[ti + 1];
+                h.next_win_lo = nx.win_lo;
+                h.next_win_n = nx.win_n;
+                h.next_n_far = nx.n_far;
+            }
+            // general entries, numbered A rows, then B rows, then C rows, entry order -- separately for the ones that
+            // need a product (gid >= 0: product index) and the ones on column 0 (gid < 0: ~index among those)
+            uint32_t n_prod = 0, n_const = 0;
+            for (int k = 0; k < 3; ++k) {
+                gid[k].assign(tl.ne[k], 0);
+                for (uint32_t e = 0; e < tl.ne[k]; ++e) {
+                    const uint32_t word = tagged_col[k][tl.e0[k] + e];
+                    if ((word >> 30) != kTagGeneral) continue;
+                    gid[k][e] = (word & kColMask) == 0u ? ~(int32_t)(n_const++) : (int32_t)(n_prod++);
+                }
+            }
+            h.n_general = n_prod;
+            h.n_const = n_const;
+            // rows sorted by shape (lengths of their A, B, C rows: rows of one shape end up in the same warps), and the
+            // ELL widths per warp of that order (kernels.h TileWarp)
+            order.resize(tl.nrows);
+            for (uint32_t r = 0; r < tl.nrows; ++r) order[r] = r;
+            auto row_len = [&](int k, uint32_t r) { return rp[k][tl.row0 + r + 1] - rp[k][tl.row0 + r]; };
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+                const uint32_t kx = (row_len(1, x) << 16) | (row_len(0, x) << 8) | row_len(2, x);
+                const uint32_t ky = (row_len(1, y) << 16) | (row_len(0, y) << 8) | row_len(2, y);
+                return kx < ky;
+            });
+            TileWarp warps[kMaxTileWarps] = {};
+            const uint32_t n_warps = (tl.nrows + 31u) / 32u;
+            uint32_t n_words = 0;
+            for (uint32_t q = 0; q < n_warps; ++q) {
+                TileWarp& tw = warps[q];
+                tw.words0 = (uint16_t)n_words;
+                tw.nrows = (uint8_t)std::min(32u, tl.nrows - 32u * q);
+                for (uint32_t l = 0; l < tw.nrows; ++l)
+                    for (int k = 0; k < 3; ++k)
+                        tw.width[k] = std::max<uint8_t>(tw.width[k], (uint8_t)row_len(k, order[32u * q + l]));
+                n_words += (uint32_t)(tw.width[0] + tw.width[1] + tw.width[2]) * tw.nrows;
+            }
+            // layout (offsets from the blob start; the blob lands at shared-memory offset 0)
+            auto up = [](uint32_t x, uint32_t a) { return (x + a - 1) / a * a; };
+            h.off_words = up(kTilePermOffset + tl.nrows, 16);
+            h.off_next_far = up(h.off_words + n_words * 4u, 16);
+            h.off_gop = up(h.off_next_far + h.next_n_far * 4u, 16);
+            h.off_gval = up(h.off_gop + n_prod * 2u, 32);
+            // warp records, row offsets, then the entry words: per warp, slot-major over the warp's rows
+            stream.resize(base + kTileWarpsOffset, 0);
+            for (uint32_t q = 0; q < kMaxTileWarps; ++q) {
+                put16(warps[q].words0);
+                stream.push_back(warps[q].nrows);
+                for (int k = 0; k < 3; ++k) stream.push_back(warps[q].width[k]);
+                put16(0);
+            }
+            for (uint32_t r = 0; r < tl.nrows; ++r) stream.push_back((uint8_t)order[r]);
+            stream.resize(base + h.off_words, 0);
+            for (uint32_t q = 0; q < n_warps; ++q)
+                for (int k = 0; k < 3; ++k)
+                    for (uint32_t j = 0; j < warps[q].width[k]; ++j)
+                        for (uint32_t l = 0; l < warps[q].nrows; ++l) {
+                            const uint32_t r = order[32u * q + l];
+                            const uint32_t s0 = rp[k][tl.row0 + r], s1 = rp[k][tl.row0 + r + 1];
+                            if (s0 + j >= s1) {
+                                put32(term_chunk(kZero, false));
+                                continue;
+                            }
+                            const uint32_t word = tagged_col[k][s0 + j];
+                            const uint32_t tag = word >> 30;
+                            if (tag == kTagGeneral) {
+                                const int32_t g = gid[k][s0 + j - tl.e0[k]];
+                                put32(g >= 0 ? (geom.prod_in_place ? blob_chunk(h.off_gval, (uint32_t)g)
+                                                                   : term_chunk(kProd0 + (uint32_t)g, false))
+                                             : blob_chunk(h.off_gval, n_prod + (uint32_t)(~g)));
+                            } else {
+                                put32((tag == kTagMinusOne ? kTermSign : 0u) | chunk_of(word & kColMask));
+                            }
+                        }
+            stream.resize(base + h.off_next_far, 0);
+            for (uint32_t f = 0; f < h.next_n_far; ++f) put32(far_all[final_tiles[ti + 1].far_off + f]);
+            stream.resize(base + h.off_gop, 0);
+            for (int k = 0; k < 3; ++k)
+                for (uint32_t e = 0; e < tl.ne[k]; ++e) {
+                    const uint32_t word = tagged_col[k][tl.e0[k] + e];
+                    if ((word >> 30) == kTagGeneral && gid[k][e] >= 0) put16((uint16_t)chunk_of(word & kColMask));
+                }
+            stream.resize(base + h.off_gval + (size_t)(n_prod + n_const) * 32u, 0);
+            for (int k = 0; k < 3; ++k)
+                for (uint32_t e = 0; e < tl.ne[k]; ++e)
+                    if ((tagged_col[k][tl.e0[k] + e] >> 30) == kTagGeneral) {
+                        const int32_t g = gid[k][e];
+                        const uint32_t lo = blob_chunk(h.off_gval, g >= 0 ? (uint32_t)g : n_prod + (uint32_t)(~g));
+                        const uint64_t* v = val0[k] + 4ull * (tl.e0[k] + e);
+                        std::memcpy(stream.data() + base + (size_t)lo * 16u, v, 16);
+                        std::memcpy(stream.data() + base + (size_t)(lo ^ 1u) * 16u, v + 2, 16);
+                        // (the conversion kernel finds the high half before / after the low one: bit 31)
+                        part.gval_offs.push_back((uint32_t)(base / 16 + lo) | ((lo & 1u) ? 0x80000000u : 0u));
+                    }
+            align16();
+            h.bytes = (uint32_t)(stream.size() - base);
+            std::memcpy(stream.data() + base, &h, sizeof h);
+            tm.blob_bytes = h.bytes;
+            part.metas.push_back(tm);
+        }
+        align16();
+        return ACG_OK;
+    });
+    if (rc) return rc;
+    const auto t_pass2 = now();
+    {   // concatenate the parts (every part is a multiple of 16 bytes) and rebase what points into the stream
+        size_t bytes = 0, n_g = 0;
+        for (const Part2& part : p2) {
+            bytes += part.stream.size();
+            n_g += part.gval_offs.size();
+        }
+        if (bytes / 16 > 0x7FFFFFF0ull) return ACG_ERR_UNSUPPORTED;
+        out.stream.resize(bytes);
+        out.gval_offs.reserve(n_g);
+        out.metas.reserve(final_tiles.size());
+        size_t at = 0;
+        for (Part2& part : p2) {
+            if (!part.stream.empty()) std::memcpy(out.stream.data() + at, part.stream.data(), part.stream.size());
+            const uint32_t base16 = (uint32_t)(at / 16);
+            for (uint32_t g : part.gval_offs) out.gval_offs.push_back(((g & 0x7FFFFFFFu) + base16) | (g & 0x80000000u));
+            for (TileMeta tm : part.metas) {
+                tm.blob_off16 += base16;
+                out.metas.push_back(tm);
+            }
+            at += part.stream.size();
+            std::vector<uint8_t>().swap(part.stream);
+        }
+    }
+    for (size_t ti = 0; ti + 1 < out.metas.size(); ++ti) {  // next_bytes: known once the next blob is laid out
+        const uint32_t nb = out.metas[ti + 1].blob_bytes;
+        std::memcpy(out.stream.data() + (size_t)out.metas[ti].blob_off16 * 16u + offsetof(TileHeader, next_bytes), &nb, sizeof nb);
+    }
+    if (timing)
+        fprintf(stderr, "[tile stream] %zu tiles, %u threads: windows / far columns %.1f ms, blobs %.1f ms, concatenation %.1f ms\n",
+                out.metas.size(), threads, ms(t_start, t_pass1), ms(t_pass1, t_pass2), ms(t_pass2, now()));
+    return ACG_OK;
+}
+
 // Enqueues one check of the shard: the kernels accumulate into the context's scratch pair and the LAST launch
 // finalises into d_result (kernels.h CheckEpilogue) -- including, when `peer` is given, the all-reduce over peer
 // memory.  No initialisation launch; one kernel for a system without over-long rows.
@@ -836,52 +1275,13 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     *out = nullptr;
     const acg_csr* src[3] = {A, B, C};
     const uint32_t n_local = row_end - row_begin;
-    // canonical 1 and r-1: the two coefficient values with a multiplication-free fast path
-    uint64_t modulus[4], minus_one[4];
-    acg_field_constants(ctx->field, modulus, nullptr, nullptr, nullptr, nullptr);
-    std::memcpy(minus_one, modulus, 32);
-    minus_one[0] -= 1;  // r is odd
-    // host pass over the uploaded slice: structural validation, coefficient tags, per-row general counts
-    std::vector<uint32_t> local_rp[3], tagged_col[3], gcum[3], ccum[3];  // ccum: general entries on column 0
-    for (int k = 0; k < 3; ++k) {
-        const acg_csr* M = src[k];
-        if (!M->rowptr || (M->nnz && (!M->col || !M->val)) || M->nnz > 0xFFFFFFF0ull)
-            return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: null array or nnz too large");
-        if (M->rowptr[n_rows] != M->nnz) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: rowptr[n_rows] != nnz");
-        for (uint32_t r = row_begin; r < row_end; ++r)
-            if (M->rowptr[r] > M->rowptr[r + 1])
-                return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: rowptr not monotone");
-        const uint32_t e0 = M->rowptr[row_begin], e1 = M->rowptr[row_end];
-        if (e1 > M->nnz) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: rowptr exceeds nnz");
-        local_rp[k].resize((size_t)n_local + 1);
-        gcum[k].resize((size_t)n_local + 1);
-        ccum[k].resize((size_t)n_local + 1);
-        tagged_col[k].resize((size_t)(e1 - e0));
-        uint32_t bad = 0, gen = 0, cst = 0;
-        for (uint32_t r = 0; r < n_local; ++r) {
-            local_rp[k][r] = M->rowptr[row_begin + r] - e0;
-            gcum[k][r] = gen;
-            ccum[k][r] = cst;
-            for (uint32_t e = M->rowptr[row_begin + r]; e < M->rowptr[row_begin + r + 1]; ++e) {
-                const uint32_t c = M->col[e];
-                bad |= (c >= n_cols);
-                const uint64_t* v = M->val + 4ull * e;
-                uint32_t tag = kTagGeneral;
-                if (v[0] == 1 && (v[1] | v[2] | v[3]) == 0)
-                    tag = kTagPlusOne;
-                else if (k != 2 && v[0] == minus_one[0] && v[1] == minus_one[1] && v[2] == minus_one[2] &&
-                         v[3] == minus_one[3])
-                    tag = kTagMinusOne;  // (a -1 in C stays general: C.w is compared, so its terms are never negated)
-                gen += (tag == kTagGeneral);
-                cst += (tag == kTagGeneral && c == 0u);
-                tagged_col[k][e - e0] = (c & kColMask) | (tag << 30);
-            }
-        }
-        local_rp[k][n_local] = e1 - e0;
-        gcum[k][n_local] = gen;
-        ccum[k][n_local] = cst;
-        if (bad) return fail(ctx, ACG_ERR_BAD_ARG, "acg_r1cs_upload: column index >= n_cols");
+    HostRows hr;
+    {
+        const char* why = nullptr;
+        int prc = host_rows(ctx->field, n_rows, n_cols, src, row_begin, row_end, hr, &why);
+        if (prc) return fail(ctx, prc, std::string("acg_r1cs_upload: ") + (why ? why : "bad argument"));
     }
+    std::vector<uint32_t> (&local_rp)[3] = hr.local_rp, (&tagged_col)[3] = hr.tagged_col, (&gcum)[3] = hr.gcum, (&ccum)[3] = hr.ccum;
     acg_r1cs* m = new (std::nothrow) acg_r1cs();
     if (!m) return ACG_ERR_OOM;
     m->ctx = ctx;
@@ -942,244 +1342,23 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     const uint32_t* gc[3] = {gcum[0].data(), gcum[1].data(), gcum[2].data()};
     const uint32_t* cc[3] = {ccum[0].data(), ccum[1].data(), ccum[2].data()};
     // ---- tile stream (see kernels.h): one self-contained blob per tile, entries in ELL order
-    m->variant = ctx->tiled_variant;
-    if (m->variant == 0 && n_local) {  // default geometry: systems dense in general coefficients get the roomier one
-        uint64_t prods = 0;
-        for (int k = 0; k < 3; ++k) prods += (uint64_t)gcum[k][n_local] - ccum[k][n_local];
-        if (prods * 10u > (uint64_t)n_local * 16u) m->variant = kDenseTileVariant;  // > 1.6 products per row
-    }
+    m->variant = pick_variant(ctx->tiled_variant, hr, n_local);
     const TileGeometry geom = kTileGeom[m->variant];
     std::vector<HostTile> tiles;
     build_tiles(geom, rp, gc, cc, n_local, tiles, m->long_ranges);
-    std::vector<uint8_t> stream;
-    std::vector<uint32_t> gval_offs;  // 16-byte units
-    std::vector<TileMeta> metas;
-    std::vector<uint32_t> far_all;
-    stream.reserve((size_t)n_local * 96 + 4096);
-    auto align16 = [&]() { stream.resize((stream.size() + 15) & ~(size_t)15, 0); };
-    auto put16 = [&](uint16_t v) {
-        stream.push_back((uint8_t)(v & 0xFF));
-        stream.push_back((uint8_t)(v >> 8));
-    };
-    auto put32 = [&](uint32_t v) {
-        for (int i = 0; i < 4; ++i) stream.push_back((uint8_t)(v >> (8 * i)));
-    };
-    const uint32_t kProd0 = tile_prod_slot0(geom), kZero = tile_term_slots(geom) - 1u;
-    std::vector<uint32_t> ref_cols, far_cols;
-    // a tile whose distinct far references exceed the far slots is split in two (rows stay multiples of 4)
-    std::vector<HostTile> work(tiles.rbegin(), tiles.rend());
-    struct FinalTile {
-        HostTile t;
-        uint32_t win_lo, win_n, far_off, n_far;
-    };
-    std::vector<FinalTile> final_tiles;
-    // ---- pass 1: window and far columns of every tile (splitting tiles with too many far columns)
-    while (!work.empty()) {
-        HostTile t = work.back();
-        work.pop_back();
-        // witness window: the contiguous slice of geom.window elements that covers most references of the tile
-        ref_cols.clear();
-        for (int k = 0; k < 3; ++k)
-            for (uint32_t e = 0; e < t.ne[k]; ++e) ref_cols.push_back(tagged_col[k][t.e0[k] + e] & kColMask);
-        std::sort(ref_cols.begin(), ref_cols.end());
-        const uint32_t win_n = std::min<uint32_t>(geom.window, n_cols);
-        uint32_t win_lo = 0;
-        {
-            size_t best = 0, lo_i = 0;
-            for (size_t hi_i = 0; hi_i < ref_cols.size(); ++hi_i) {
-                while (ref_cols[hi_i] - ref_cols[lo_i] >= win_n) ++lo_i;
-                if (hi_i - lo_i + 1 > best) {
-                    best = hi_i - lo_i + 1;
-                    win_lo = ref_cols[lo_i];
-                }
-            }
-            if (win_lo + win_n > n_cols) win_lo = n_cols - win_n;
-        }
-        far_cols.clear();
-        for (uint32_t c : ref_cols)
-            if ((c < win_lo || c - win_lo >= win_n) && (far_cols.empty() || far_cols.back() != c)) far_cols.push_back(c);
-        if (far_cols.size() > geom.max_far && t.nrows > 4) {
-            const uint32_t half = ((t.nrows / 2 + 3) / 4) * 4;
-            HostTile lo_t{}, hi_t{};
-            lo_t.row0 = t.row0;
-            lo_t.nrows = half;
-            hi_t.row0 = t.row0 + half;
-            hi_t.nrows = t.nrows - half;
-            for (HostTile* q : {&lo_t, &hi_t})
-                for (int k = 0; k < 3; ++k) {
-                    q->e0[k] = rp[k][q->row0];
-                    q->ne[k] = rp[k][q->row0 + q->nrows] - q->e0[k];
-                    q->width[k] = 0;
-                    for (uint32_t r = q->row0; r < q->row0 + q->nrows; ++r)
-                        q->width[k] = std::max(q->width[k], rp[k][r + 1] - rp[k][r]);
-                }
-            work.push_back(hi_t);
-            work.push_back(lo_t);
-            continue;
-        }
-        if (far_cols.size() > geom.max_far) {  // 4 rows with more distinct far columns than slots: row-wise kernel
-            m->long_ranges.emplace_back(t.row0, t.row0 + t.nrows);
-            continue;
-        }
-        FinalTile ft{};
-        ft.t = t;
-        ft.win_lo = win_lo;
-        ft.win_n = win_n;
-        ft.far_off = (uint32_t)far_all.size();
-        ft.n_far = (uint32_t)far_cols.size();
-        far_all.insert(far_all.end(), far_cols.begin(), far_cols.end());
-        final_tiles.push_back(ft);
+    TileStream tstream;
+    {
+        const uint64_t* const val0[3] = {src[0]->val + 4ull * src[0]->rowptr[row_begin], src[1]->val + 4ull * src[1]->rowptr[row_begin],
+                                         src[2]->val + 4ull * src[2]->rowptr[row_begin]};
+        int brc = build_tile_stream(geom, n_cols, tiles, local_rp, tagged_col, val0, upload_threads(), tstream);
+        if (brc == ACG_ERR_UNSUPPORTED) return fail(ctx, brc, "acg_r1cs_upload: tile stream too large");
+        if (brc) return fail(ctx, brc, "acg_r1cs_upload: tile-stream build failed");
     }
-    // ---- pass 2: emit the blobs.  Blob i also carries what the kernel needs to start tile i + 1 while blob i is
-    //      still the only one in shared memory: its far witness columns and, in the header, its size and window.
-    std::vector<size_t> bases;
-    for (size_t ti = 0; ti < final_tiles.size(); ++ti) {
-        const FinalTile& ft = final_tiles[ti];
-        const HostTile& t = ft.t;
-        const uint32_t win_lo = ft.win_lo, win_n = ft.win_n;
-        const uint32_t* far_b = far_all.data() + ft.far_off;
-        const uint32_t* far_e = far_b + ft.n_far;
-        // chunk (16-byte unit from the start of shared memory) of the low half of a term slot / of the 32-byte value
-        // j of a blob section; the window is written by a linear bulk copy and stays in natural order (kernels.h)
-        const uint32_t term_base16 = tile_terms_offset(geom) / 16u;
-        auto term_chunk = [&](uint32_t slot, bool in_window) -> uint32_t {
-            const uint32_t c = term_base16 + 2u * slot;
-            return (geom.swizzle && !in_window) ? swz16(c) : c;
-        };
-        auto blob_chunk = [&](uint32_t off, uint32_t j) -> uint32_t {
-            const uint32_t c = off / 16u + 2u * j;
-            return geom.swizzle ? swz16(c) : c;
-        };
-        auto chunk_of = [&](uint32_t c) -> uint32_t {  // witness column -> chunk of its term
-            if (c >= win_lo && c - win_lo < win_n) return term_chunk(c - win_lo, true);
-            return term_chunk(tile_far_slot0(geom, (uint32_t)ti) + (uint32_t)(std::lower_bound(far_b, far_e, c) - far_b),
-                              false);
-        };
-        align16();
-        const size_t base = stream.size();
-        bases.push_back(base);
-        TileMeta tm{};
-        tm.blob_off16 = (uint32_t)(base / 16);
-        tm.win_lo = win_lo;
-        tm.win_n = win_n;
-        tm.far_off = ft.far_off;
-        tm.n_far = ft.n_far;
-        stream.resize(base + sizeof(TileHeader), 0);
-        TileHeader h{};
-        h.row0 = t.row0;
-        h.nrows = t.nrows;
-        for (int k = 0; k < 3; ++k) h.width[k] = t.width[k];
-        if (ti + 1 < final_tiles.size()) {
-            const FinalTile& nx = final_tiles[ti + 1];
-            h.next_win_lo = nx.win_lo;
-            h.next_win_n = nx.win_n;
-            h.next_n_far = nx.n_far;
-        }
-        // general entries, numbered A rows, then B rows, then C rows, entry order -- separately for the ones that
-        // need a product (gid >= 0: product index) and the ones on column 0 (gid < 0: ~index among those)
-        std::vector<int32_t> gid[3];
-        uint32_t n_prod = 0, n_const = 0;
-        for (int k = 0; k < 3; ++k) {
-            gid[k].assign(t.ne[k], 0);
-            for (uint32_t e = 0; e < t.ne[k]; ++e) {
-                const uint32_t word = tagged_col[k][t.e0[k] + e];
-                if ((word >> 30) != kTagGeneral) continue;
-                gid[k][e] = (word & kColMask) == 0u ? ~(int32_t)(n_const++) : (int32_t)(n_prod++);
-            }
-        }
-        h.n_general = n_prod;
-        h.n_const = n_const;
-        // rows sorted by shape (lengths of their A, B, C rows: rows of one shape end up in the same warps), and the ELL
-        // widths per warp of that order (kernels.h TileWarp)
-        std::vector<uint32_t> order(t.nrows);
-        for (uint32_t r = 0; r < t.nrows; ++r) order[r] = r;
-        auto row_len = [&](int k, uint32_t r) { return local_rp[k][t.row0 + r + 1] - local_rp[k][t.row0 + r]; };
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-            const uint32_t kx = (row_len(1, x) << 16) | (row_len(0, x) << 8) | row_len(2, x);
-            const uint32_t ky = (row_len(1, y) << 16) | (row_len(0, y) << 8) | row_len(2, y);
-            return kx < ky;
-        });
-        TileWarp warps[kMaxTileWarps] = {};
-        const uint32_t n_warps = (t.nrows + 31u) / 32u;
-        uint32_t n_words = 0;
-        for (uint32_t q = 0; q < n_warps; ++q) {
-            TileWarp& tw = warps[q];
-            tw.words0 = (uint16_t)n_words;
-            tw.nrows = (uint8_t)std::min(32u, t.nrows - 32u * q);
-            for (uint32_t l = 0; l < tw.nrows; ++l)
-                for (int k = 0; k < 3; ++k) tw.width[k] = std::max<uint8_t>(tw.width[k], (uint8_t)row_len(k, order[32u * q + l]));
-            n_words += (uint32_t)(tw.width[0] + tw.width[1] + tw.width[2]) * tw.nrows;
-        }
-        // layout (offsets from the blob start; the blob lands at shared-memory offset 0)
-        auto up = [](uint32_t x, uint32_t a) { return (x + a - 1) / a * a; };
-        h.off_words = up(kTilePermOffset + t.nrows, 16);
-        h.off_next_far = up(h.off_words + n_words * 4u, 16);
-        h.off_gop = up(h.off_next_far + h.next_n_far * 4u, 16);
-        h.off_gval = up(h.off_gop + n_prod * 2u, 32);
-        // warp records, row offsets, then the entry words: per warp, slot-major over the warp's rows
-        stream.resize(base + kTileWarpsOffset, 0);
-        for (uint32_t q = 0; q < kMaxTileWarps; ++q) {
-            put16(warps[q].words0);
-            stream.push_back(warps[q].nrows);
-            for (int k = 0; k < 3; ++k) stream.push_back(warps[q].width[k]);
-            put16(0);
-        }
-        for (uint32_t r = 0; r < t.nrows; ++r) stream.push_back((uint8_t)order[r]);
-        stream.resize(base + h.off_words, 0);
-        for (uint32_t q = 0; q < n_warps; ++q)
-            for (int k = 0; k < 3; ++k)
-                for (uint32_t j = 0; j < warps[q].width[k]; ++j)
-                    for (uint32_t l = 0; l < warps[q].nrows; ++l) {
-                        const uint32_t r = order[32u * q + l];
-                        const uint32_t s0 = local_rp[k][t.row0 + r], s1 = local_rp[k][t.row0 + r + 1];
-                        if (s0 + j >= s1) {
-                            put32(term_chunk(kZero, false));
-                            continue;
-                        }
-                        const uint32_t word = tagged_col[k][s0 + j];
-                        const uint32_t tag = word >> 30;
-                        if (tag == kTagGeneral) {
-                            const int32_t g = gid[k][s0 + j - t.e0[k]];
-                            put32(g >= 0 ? (geom.prod_in_place ? blob_chunk(h.off_gval, (uint32_t)g)
-                                                               : term_chunk(kProd0 + (uint32_t)g, false))
-                                         : blob_chunk(h.off_gval, n_prod + (uint32_t)(~g)));
-                        } else {
-                            put32((tag == kTagMinusOne ? kTermSign : 0u) | chunk_of(word & kColMask));
-                        }
-                    }
-        stream.resize(base + h.off_next_far, 0);
-        for (uint32_t f = 0; f < h.next_n_far; ++f) put32(far_all[final_tiles[ti + 1].far_off + f]);
-        stream.resize(base + h.off_gop, 0);
-        for (int k = 0; k < 3; ++k)
-            for (uint32_t e = 0; e < t.ne[k]; ++e) {
-                const uint32_t word = tagged_col[k][t.e0[k] + e];
-                if ((word >> 30) == kTagGeneral && gid[k][e] >= 0) put16((uint16_t)chunk_of(word & kColMask));
-            }
-        stream.resize(base + h.off_gval + (size_t)(n_prod + n_const) * 32u, 0);
-        for (int k = 0; k < 3; ++k) {
-            const acg_csr* M = src[k];
-            const uint32_t g0 = M->rowptr[row_begin];
-            for (uint32_t e = 0; e < t.ne[k]; ++e)
-                if ((tagged_col[k][t.e0[k] + e] >> 30) == kTagGeneral) {
-                    const int32_t g = gid[k][e];
-                    const uint32_t lo = blob_chunk(h.off_gval, g >= 0 ? (uint32_t)g : n_prod + (uint32_t)(~g));
-                    const uint64_t* v = M->val + 4ull * (g0 + t.e0[k] + e);
-                    std::memcpy(stream.data() + base + (size_t)lo * 16u, v, 16);
-                    std::memcpy(stream.data() + base + (size_t)(lo ^ 1u) * 16u, v + 2, 16);
-                    // (the conversion kernel finds the high half before / after the low one: bit 31)
-                    gval_offs.push_back((uint32_t)(base / 16 + lo) | ((lo & 1u) ? 0x80000000u : 0u));
-                }
-        }
-        align16();
-        h.bytes = (uint32_t)(stream.size() - base);
-        std::memcpy(stream.data() + base, &h, sizeof h);
-        tm.blob_bytes = h.bytes;
-        metas.push_back(tm);
-    }
-    for (size_t ti = 0; ti + 1 < metas.size(); ++ti) {  // next_bytes: known once the next blob is laid out
-        const uint32_t nb = metas[ti + 1].blob_bytes;
-        std::memcpy(stream.data() + bases[ti] + offsetof(TileHeader, next_bytes), &nb, sizeof nb);
-    }
+    std::vector<uint8_t>& stream = tstream.stream;
+    std::vector<uint32_t>& gval_offs = tstream.gval_offs;
+    std::vector<TileMeta>& metas = tstream.metas;
+    std::vector<uint32_t>& far_all = tstream.far_all;
+    m->long_ranges.insert(m->long_ranges.end(), tstream.extra_long.begin(), tstream.extra_long.end());
     const uint32_t n_tiles_out = (uint32_t)metas.size();
     std::sort(m->long_ranges.begin(), m->long_ranges.end());
     {   // the rows the tiles leave out, as one list
@@ -1192,8 +1371,6 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
             CU(ctx, cudaMemcpy(m->d_long_rows, long_rows.data(), long_rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
     }
-    align16();
-    if (stream.size() / 16 > 0x7FFFFFF0ull) return fail(ctx, ACG_ERR_UNSUPPORTED, "acg_r1cs_upload: tile stream too large");
     m->n_tiles = n_tiles_out;
     // what one check streams from HBM besides the witness: blobs, tile records, far column lists
     m->blob_bytes = stream.size();
@@ -1292,6 +1469,64 @@ int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_cs
     *out = m;
     return ACG_OK;
     ACG_CATCH(ctx)
+}
+
+// Host-only (no device needed): builds the tile stream acg_r1cs_upload would build for this slice and geometry on
+// n_threads worker threads (0: as the upload chooses) and returns digests of everything it produced -- the test that
+// the multi-threaded build is the single-threaded one, byte for byte.
+int acg_tile_stream_digest(int field_id, int variant, uint32_t n_rows, uint32_t n_cols, const acg_csr* A, const acg_csr* B,
+                           const acg_csr* C, uint32_t row_begin, uint32_t row_end, uint32_t n_threads, uint64_t* out4) {
+    try {
+        if (!A || !B || !C || !out4 || row_begin > row_end || row_end > n_rows || n_cols == 0 || n_cols > kColMask ||
+            variant < 0 || variant >= kNumTileVariants || (field_id != ACG_FIELD_BN254_FR && field_id != ACG_FIELD_BLS12_381_FR))
+            return ACG_ERR_BAD_ARG;
+        const acg_csr* src[3] = {A, B, C};
+        HostRows hr;
+        int rc = host_rows(field_id, n_rows, n_cols, src, row_begin, row_end, hr, nullptr);
+        if (rc) return rc;
+        const uint32_t n_local = row_end - row_begin;
+        const int v = pick_variant(variant, hr, n_local);
+        const uint32_t* rp[3] = {hr.local_rp[0].data(), hr.local_rp[1].data(), hr.local_rp[2].data()};
+        const uint32_t* gc[3] = {hr.gcum[0].data(), hr.gcum[1].data(), hr.gcum[2].data()};
+        const uint32_t* cc[3] = {hr.ccum[0].data(), hr.ccum[1].data(), hr.ccum[2].data()};
+        std::vector<HostTile> tiles;
+        std::vector<std::pair<uint32_t, uint32_t>> long_ranges;
+        build_tiles(kTileGeom[v], rp, gc, cc, n_local, tiles, long_ranges);
+        const uint64_t* const val0[3] = {A->val + 4ull * A->rowptr[row_begin], B->val + 4ull * B->rowptr[row_begin],
+                                         C->val + 4ull * C->rowptr[row_begin]};
+        TileStream ts;
+        rc = build_tile_stream(kTileGeom[v], n_cols, tiles, hr.local_rp, hr.tagged_col, val0,
+                               n_threads ? n_threads : upload_threads(), ts);
+        if (rc) return rc;
+        long_ranges.insert(long_ranges.end(), ts.extra_long.begin(), ts.extra_long.end());
+        std::sort(long_ranges.begin(), long_ranges.end());
+        auto fnv = [](uint64_t h, const void* p, size_t n) {
+            const uint8_t* b = static_cast<const uint8_t*>(p);
+            for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 0x100000001b3ull;
+            return h;
+        };
+        uint64_t h1 = fnv(0xcbf29ce484222325ull, ts.stream.data(), ts.stream.size());
+        uint64_t h2 = 0xcbf29ce484222325ull;
+        for (const TileMeta& tm : ts.metas) {  // field by field: the struct may have padding
+            const uint32_t f[6] = {tm.blob_off16, tm.blob_bytes, tm.win_lo, tm.win_n, tm.far_off, tm.n_far};
+            h2 = fnv(h2, f, sizeof f);
+        }
+        h2 = fnv(h2, ts.far_all.data(), ts.far_all.size() * sizeof(uint32_t));
+        h2 = fnv(h2, ts.gval_offs.data(), ts.gval_offs.size() * sizeof(uint32_t));
+        for (const auto& lr : long_ranges) {
+            const uint32_t f[2] = {lr.first, lr.second};
+            h2 = fnv(h2, f, sizeof f);
+        }
+        out4[0] = h1;
+        out4[1] = h2;
+        out4[2] = ts.stream.size();
+        out4[3] = ts.metas.size();
+        return ACG_OK;
+    } catch (const std::bad_alloc&) {
+        return ACG_ERR_OOM;
+    } catch (...) {
+        return ACG_ERR_INTERNAL;
+    }
 }
 
 uint64_t acg_r1cs_algorithmic_bytes(const acg_r1cs* m) {

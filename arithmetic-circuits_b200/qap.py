@@ -297,6 +297,16 @@ class GenQAP:
     def nnz(self) -> Tuple[int, int, int]:
         return tuple(len(m[1]) for m in self.mats)
 
+    def tile_stream_digest(self, variant: int = 0, n_threads: int = 0, rows: Optional[Tuple[int, int]] = None):
+        """Host-only: digests of the tile stream acg_r1cs_upload would build for this system (acg_tile_stream_digest):
+        (hash of the blobs, hash of the records, blob bytes, tiles).  Independent of n_threads by construction."""
+        a, b, c = self.csr_structs()
+        out = (C.c_uint64 * 4)()
+        r0, r1 = rows if rows is not None else (0, self.n_rows)
+        _check(_lib.lib().acg_tile_stream_digest(self.field, variant, self.n_rows, self.n_cols, C.byref(a), C.byref(b),
+                                                 C.byref(c), r0, r1, n_threads, out), None)
+        return tuple(int(x) for x in out)
+
 
 class _HostR1cs:
     def __init__(self, h):

@@ -120,6 +120,14 @@ int acg_root_of_unity(int field_id, uint32_t k, uint64_t out[4]);
 int acg_r1cs_upload(acg_ctx* ctx, uint32_t n_rows, uint32_t n_cols, const acg_csr* A, const acg_csr* B,
                     const acg_csr* C, uint32_t row_begin, uint32_t row_end, acg_r1cs** out);
 void acg_r1cs_free(acg_r1cs* m);
+/* Host-only diagnostic (no device needed): builds the tile stream acg_r1cs_upload would build for rows
+ * [row_begin, row_end) under tile geometry `variant` on n_threads host threads (0: as the upload chooses:
+ * ACG_HOST_THREADS or the hardware concurrency) and returns out4 = {FNV-1a of the blobs, FNV-1a of the tile records +
+ * far columns + value offsets + rows left to the long-row path, bytes of the blobs, number of tiles}.  The build runs
+ * on worker threads over contiguous chunks of the tile list; this is how the tests show that its result does not depend
+ * on the number of threads. */
+int acg_tile_stream_digest(int field_id, int variant, uint32_t n_rows, uint32_t n_cols, const acg_csr* A, const acg_csr* B,
+                           const acg_csr* C, uint32_t row_begin, uint32_t row_end, uint32_t n_threads, uint64_t* out4);
 /* Algorithmic bytes one check of this (shard of the) system reads: SURVEY.md 8(d) formula
  * sum_M [nnz_M*(32+4) + 4*(rows+1)] + 32*(witness columns the rows reference) + 8.  For a whole system that is
  * 32*n_cols (every wire occurs in some row); a row shard of a larger system is charged only the witness elements its

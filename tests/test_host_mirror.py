@@ -231,3 +231,26 @@ def test_parallel_lowering_is_deterministic(acg, monkeypatch):
             ref = snap
         else:
             assert all((a == b).all() for ma, mb in zip(ref, snap) for a, b in zip(ma, mb)), th
+
+
+def test_tile_stream_build_does_not_depend_on_threads(acg):
+    """acg_r1cs_upload builds the tile stream of the tiled kernel on worker threads over contiguous chunks of the tile
+    list (both passes: windows / far columns, then the blobs).  The host-only acg_tile_stream_digest hashes everything
+    the build produces -- blobs, tile records, far columns, value offsets, the rows left to the long-row path: equal
+    for 1, 2, 5 and 16 threads, for every tile geometry, for a dense system (the roomier geometry is chosen), for the
+    reference generator's gate mix (long rows) and for a row shard."""
+    systems = {"S": acg.synth_r1cs(0, 1 << 15, 7)[0], "dense": acg.synth_r1cs(0, 1 << 13, 8, True)[0],
+               "mix": acg.synth_mixed_r1cs(0, 1 << 14, 5)[0], "bls": acg.synth_r1cs(1, 5000, 3)[0]}
+    for name, g in systems.items():
+        for variant in range(9):
+            d = [g.tile_stream_digest(variant, t) for t in (1, 2, 5, 16)]
+            assert all(x == d[0] for x in d), (name, variant, d)
+            assert d[0][2] > 0 and d[0][3] > 0
+        d = [g.tile_stream_digest(0, t, (1000, g.n_rows - 777)) for t in (1, 3, 8)]
+        assert all(x == d[0] for x in d), name
+    # the dense system is bound to the roomier geometry when the default is asked for
+    assert systems["dense"].tile_stream_digest(0, 1) == systems["dense"].tile_stream_digest(8, 1)
+    assert systems["S"].tile_stream_digest(0, 1) != systems["S"].tile_stream_digest(8, 1)
+    with pytest.raises(acg.AcgError) as e:
+        systems["S"].tile_stream_digest(99, 1)
+    assert e.value.code == -1
