@@ -5,9 +5,10 @@
 // evaluation-domain form.  Everything on the device is in Montgomery form, so
 // the test  a*b*R^-1 == c  is exactly  (A.w)(B.w) == (C.w)  on canonical residues.
 //
-// Two kernels compute the same thing:
-//   k_r1cs_rowwise : thread per row, direct global loads.  Used for one-shot checks (no preprocessing)
-//                    and for rows too long to stage in shared memory.
+// Three kernels compute the same thing:
+//   k_r1cs_rowwise : thread per row, direct global loads.  Used for one-shot checks (no preprocessing).
+//   k_r1cs_longrows: warp per row over a list of rows too long for a tile (Split gates); only for tile geometries
+//                    without the LONG form of the tiled kernel, and for shards without tiles.
 //   k_r1cs_tiled   : persistent CTAs, each walking a contiguous run of the tiles (<= 128 / 256 / 64 / 32 rows) that
 //                    upload laid out as a stream of execution-ready blobs (kernels.h).  Per tile:
 //                    (load) two TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP): the blob and the tile's
@@ -26,8 +27,12 @@
 //                    The coefficient classification (+1 / -1 / general / general on the constant wire) is computed
 //                    once at upload: the sparsity pattern is static, and the 32-byte encodings of +-1 never need to
 //                    be re-read.  HBM traffic per check is one pass over the blobs; the witness is read via L2.
-// Both end with finish_check(): the last CTA of the last launch of a check finalises the result pair and, for row
-// shards on several GPUs, all-reduces it over peer memory (CheckEpilogue / PeerSlots in kernels.h).
+//                    (long)  LONG instantiations: once a CTA has run out of tiles its warps claim the rows too long
+//                           for a tile from a counter and check them on the plain CSR arrays (kernels.h DevLongRows).
+// Hand-over of the result (kernels.h CheckEpilogue): a plain single-GPU check starts by writing {0, none} and opening
+// a gate, violating warps update the result themselves, and nothing runs at the end; sharded and overlapped checks end
+// with finish_check(): the last CTA of the last launch finalises the result pair and, for row shards on several GPUs,
+// all-reduces it over peer memory (PeerSlots).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
