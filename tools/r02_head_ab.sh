@@ -1,6 +1,10 @@
 #!/bin/bash
 # same-box A/B: a full copy of an earlier commit under _ab/head (built there) against the working tree
 #   usage: tools/r02_head_ab.sh "<pytest -k expression>" "<bench args>" ["<bench args>" ...]
+#   the copy (here, before the gpurun call; _ab/ is git-ignored but travels to the GPU box):
+#     rm -rf _ab/head && mkdir -p _ab/head && git archive <commit> arithmetic-circuits_b200 arithmetic_circuits_b200 \
+#       bench.py oracle include tests/helpers.py | tar -x -C _ab/head/ && cp MEASURED_PEAKS.json _ab/head/ && \
+#       python _ab/head/arithmetic-circuits_b200/build.py
 set -u
 B="--steps 200 --warmup 10 --no-cpu-baseline --e2e-steps 3 --no-qap --no-one-shot --no-overlap"
 show() { python -c "
