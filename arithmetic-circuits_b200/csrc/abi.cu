@@ -931,6 +931,133 @@ int build_tile_stream(const TileGeometry& geom, uint32_t n_cols, const std::vect
     return ACG_OK;
 }
 
+// Structural check of a tile stream against everything the tiled kernel assumes about it (host-only; run by
+// acg_tile_stream_digest, i.e. by the CPU test suite): sizes within the geometry's capacities, sections inside the blob
+// and in order, every entry / operand word a chunk inside the CTA's shared memory (and inside the blob, the witness
+// window, the far buffer of the tile's parity, the product slots or the zero slot), warp records consistent with the
+// row count, the row offsets a permutation, the hand-over fields of blob i equal to tile i + 1's record, far columns
+// sorted, distinct and outside the window, and tiles plus long ranges covering every row exactly once.
+// Returns nullptr or what is wrong.
+const char* validate_tile_stream(const TileGeometry& geom, uint32_t n_local, uint32_t n_cols, const TileStream& ts,
+                                 const std::vector<std::pair<uint32_t, uint32_t>>& long_ranges) {
+    const uint32_t smem_chunks = tile_smem_bytes(geom) / 16u, terms16 = tile_terms_offset(geom) / 16u;
+    const uint32_t kZero = tile_term_slots(geom) - 1u, kProd0 = tile_prod_slot0(geom);
+    std::vector<uint8_t> covered(n_local, 0);
+    for (const auto& lr : long_ranges) {
+        if (lr.first > lr.second || lr.second > n_local) return "long range out of bounds";
+        for (uint32_t r = lr.first; r < lr.second; ++r) {
+            if (covered[r]) return "row covered twice";
+            covered[r] = 1;
+        }
+    }
+    auto unswz = [&](uint32_t chunk) { return geom.swizzle ? swz16(chunk) : chunk; };  // (swz16 is an involution)
+    for (size_t ti = 0; ti < ts.metas.size(); ++ti) {
+        const TileMeta& tm = ts.metas[ti];
+        if ((size_t)tm.blob_off16 * 16u + tm.blob_bytes > ts.stream.size()) return "blob outside the stream";
+        if (tm.blob_bytes % 16u || tm.blob_bytes > tile_blob_capacity(geom)) return "blob size";
+        if (tm.win_n > geom.window || (uint64_t)tm.win_lo + tm.win_n > n_cols) return "window";
+        if (tm.n_far > geom.max_far || (size_t)tm.far_off + tm.n_far > ts.far_all.size()) return "far columns";
+        const uint32_t* far = ts.far_all.data() + tm.far_off;
+        for (uint32_t f = 0; f < tm.n_far; ++f) {
+            if (far[f] >= n_cols) return "far column out of range";
+            if (f && far[f] <= far[f - 1]) return "far columns not strictly ascending";
+            if (far[f] >= tm.win_lo && far[f] - tm.win_lo < tm.win_n) return "far column inside the window";
+        }
+        const uint8_t* blob = ts.stream.data() + (size_t)tm.blob_off16 * 16u;
+        TileHeader h;
+        std::memcpy(&h, blob, sizeof h);
+        if (h.bytes != tm.blob_bytes) return "header size != record size";
+        if (h.nrows == 0 || h.nrows > geom.threads || (uint64_t)h.row0 + h.nrows > n_local) return "rows of a tile";
+        if (h.n_general > geom.max_gen || h.n_const > geom.max_const) return "general entries beyond the caps";
+        if (h.width[0] + h.width[1] + h.width[2] > geom.max_slots) return "ELL widths beyond the slots";
+        for (uint32_t r = h.row0; r < h.row0 + h.nrows; ++r) {
+            if (covered[r]) return "row covered twice";
+            covered[r] = 1;
+        }
+        if (!(kTilePermOffset + h.nrows <= h.off_words && h.off_words <= h.off_next_far && h.off_next_far <= h.off_gop &&
+              h.off_gop <= h.off_gval && h.off_gval % 32u == 0 &&
+              h.off_gval + (uint64_t)(h.n_general + h.n_const) * 32u <= h.bytes))
+            return "blob sections out of order";
+        if (ti + 1 < ts.metas.size()) {
+            const TileMeta& nx = ts.metas[ti + 1];
+            if (h.next_bytes != nx.blob_bytes || h.next_win_lo != nx.win_lo || h.next_win_n != nx.win_n ||
+                h.next_n_far != nx.n_far || nx.blob_off16 != tm.blob_off16 + tm.blob_bytes / 16u)
+                return "hand-over fields != the next tile's record";
+            if (h.off_next_far + (uint64_t)h.next_n_far * 4u > h.off_gop) return "next far columns overflow their section";
+            if (h.next_n_far && std::memcmp(blob + h.off_next_far, ts.far_all.data() + nx.far_off, (size_t)nx.n_far * 4u))
+                return "next far columns != the next tile's";
+        } else if (h.next_bytes || h.next_n_far) {
+            return "last tile hands over to nothing";
+        }
+        // warp records and the row permutation
+        const uint32_t n_warps = (h.nrows + 31u) / 32u;
+        uint32_t rows_seen = 0, n_words = 0;
+        for (uint32_t q = 0; q < kMaxTileWarps; ++q) {
+            TileWarp tw;
+            std::memcpy(&tw, blob + kTileWarpsOffset + q * sizeof(TileWarp), sizeof tw);
+            if (q >= n_warps) {
+                if (tw.nrows) return "warp record beyond the tile's warps";
+                continue;
+            }
+            if (tw.nrows == 0 || tw.nrows > 32u || tw.words0 != n_words) return "warp record";
+            if (tw.width[0] > h.width[0] || tw.width[1] > h.width[1] || tw.width[2] > h.width[2]) return "warp wider than its tile";
+            rows_seen += tw.nrows;
+            n_words += (uint32_t)(tw.width[0] + tw.width[1] + tw.width[2]) * tw.nrows;
+        }
+        if (rows_seen != h.nrows || h.off_words + (uint64_t)n_words * 4u > h.off_next_far) return "warp records != rows / words";
+        std::vector<uint8_t> seen(h.nrows, 0);
+        for (uint32_t r = 0; r < h.nrows; ++r) {
+            const uint8_t o = blob[kTilePermOffset + r];
+            if (o >= h.nrows || seen[o]) return "row offsets are not a permutation";
+            seen[o] = 1;
+        }
+        // where a term may live: window, this tile's far buffer, a product slot / an in-place value, the zero slot
+        const uint32_t far0 = tile_far_slot0(geom, (uint32_t)ti);
+        auto term_ok = [&](uint32_t chunk, bool allow_values) {
+            if (chunk >= smem_chunks) return false;
+            if (chunk >= terms16) {  // the term array: the window is linear, the rest swizzled
+                const uint32_t lin = chunk - terms16;
+                if (lin < 2u * geom.window) return (lin & 1u) == 0u && lin / 2u < tm.win_n;
+                const uint32_t c = unswz(chunk);
+                if (c < terms16 || ((c - terms16) & 1u)) return false;
+                const uint32_t slot = (c - terms16) / 2u;
+                if (slot >= far0 && slot < far0 + tm.n_far) return true;
+                if (allow_values && !geom.prod_in_place && slot >= kProd0 && slot < kProd0 + h.n_general) return true;
+                return allow_values && slot == kZero;
+            }
+            if (!allow_values) return false;  // inside the blob: a value of the general section
+            const uint32_t c = unswz(chunk);
+            if ((uint64_t)c * 16u < h.off_gval || ((c * 16u - h.off_gval) % 32u)) return false;
+            const uint32_t j = (c * 16u - h.off_gval) / 32u;
+            return geom.prod_in_place ? j < h.n_general + h.n_const : (j >= h.n_general && j < h.n_general + h.n_const);
+        };
+        for (uint32_t k = 0; k < n_words; ++k) {
+            uint32_t word;
+            std::memcpy(&word, blob + h.off_words + 4u * k, 4);
+            if (!term_ok(word & ~kTermSign, true)) return "entry word outside its legal places";
+        }
+        if (h.off_gop + (uint64_t)h.n_general * 2u > h.off_gval) return "operand words overflow their section";
+        for (uint32_t j = 0; j < h.n_general; ++j) {
+            uint16_t op;
+            std::memcpy(&op, blob + h.off_gop + 2u * j, 2);
+            if (!term_ok(op, false)) return "operand word is not a witness term";
+        }
+    }
+    for (uint32_t r = 0; r < n_local; ++r)
+        if (!covered[r]) return "row not covered";
+    // value offsets: one per general entry, inside the stream
+    uint64_t n_values = 0;
+    for (const TileMeta& tm : ts.metas) {
+        TileHeader h;
+        std::memcpy(&h, ts.stream.data() + (size_t)tm.blob_off16 * 16u, sizeof h);
+        n_values += h.n_general + h.n_const;
+    }
+    if (n_values != ts.gval_offs.size()) return "value offsets != general entries";
+    for (uint32_t g : ts.gval_offs)
+        if (((size_t)(g & 0x7FFFFFFFu) + 1u) * 16u > ts.stream.size()) return "value offset outside the stream";
+    return nullptr;
+}
+
 // Enqueues one check of the shard: the kernels accumulate into the context's scratch pair and the LAST launch
 // finalises into d_result (kernels.h CheckEpilogue) -- including, when `peer` is given, the all-reduce over peer
 // memory.  No initialisation launch; one kernel for a system without over-long rows.
@@ -1500,6 +1627,10 @@ int acg_tile_stream_digest(int field_id, int variant, uint32_t n_rows, uint32_t 
         if (rc) return rc;
         long_ranges.insert(long_ranges.end(), ts.extra_long.begin(), ts.extra_long.end());
         std::sort(long_ranges.begin(), long_ranges.end());
+        if (const char* wrong = validate_tile_stream(kTileGeom[v], n_local, n_cols, ts, long_ranges)) {
+            fprintf(stderr, "acg_tile_stream_digest: invalid tile stream: %s\n", wrong);
+            return ACG_ERR_INTERNAL;
+        }
         auto fnv = [](uint64_t h, const void* p, size_t n) {
             const uint8_t* b = static_cast<const uint8_t*>(p);
             for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 0x100000001b3ull;

@@ -123,7 +123,10 @@ void acg_r1cs_free(acg_r1cs* m);
 /* Host-only diagnostic (no device needed): builds the tile stream acg_r1cs_upload would build for rows
  * [row_begin, row_end) under tile geometry `variant` on n_threads host threads (0: as the upload chooses:
  * ACG_HOST_THREADS or the hardware concurrency) and returns out4 = {FNV-1a of the blobs, FNV-1a of the tile records +
- * far columns + value offsets + rows left to the long-row path, bytes of the blobs, number of tiles}.  The build runs
+ * far columns + value offsets + rows left to the long-row path, bytes of the blobs, number of tiles}.  Before hashing,
+ * the stream is checked against everything the tiled kernel assumes about it (capacities, section order, every entry
+ * and operand word inside its legal places of the CTA's shared memory, warp records, row permutation, hand-over
+ * fields, far columns, row coverage): ACG_ERR_INTERNAL and a line on stderr if not.  The build runs
  * on worker threads over contiguous chunks of the tile list; this is how the tests show that its result does not depend
  * on the number of threads. */
 int acg_tile_stream_digest(int field_id, int variant, uint32_t n_rows, uint32_t n_cols, const acg_csr* A, const acg_csr* B,

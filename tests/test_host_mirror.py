@@ -238,7 +238,10 @@ def test_tile_stream_build_does_not_depend_on_threads(acg):
     list (both passes: windows / far columns, then the blobs).  The host-only acg_tile_stream_digest hashes everything
     the build produces -- blobs, tile records, far columns, value offsets, the rows left to the long-row path: equal
     for 1, 2, 5 and 16 threads, for every tile geometry, for a dense system (the roomier geometry is chosen), for the
-    reference generator's gate mix (long rows) and for a row shard."""
+    reference generator's gate mix (long rows) and for a row shard.  The same call validates the stream structurally
+    (validate_tile_stream in abi.cu: every entry / operand word inside its legal places of the CTA's shared memory,
+    section order, warp records, row permutation, hand-over fields, far columns, each row covered exactly once) and
+    fails with ACG_ERR_INTERNAL otherwise -- the builder is checked on CPU for every geometry without a device."""
     systems = {"S": acg.synth_r1cs(0, 1 << 15, 7)[0], "dense": acg.synth_r1cs(0, 1 << 13, 8, True)[0],
                "mix": acg.synth_mixed_r1cs(0, 1 << 14, 5)[0], "bls": acg.synth_r1cs(1, 5000, 3)[0]}
     for name, g in systems.items():
